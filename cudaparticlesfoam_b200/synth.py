@@ -1,0 +1,228 @@
+"""Synthetic OpenFOAM-style inputs for the particle hot path.
+
+These are *input generators* for tests and bench.py -- meshes, frozen velocity fields and seeded
+particle clouds of the shapes BASELINE.json names.  They emit the raw polyMesh arrays an OpenFOAM
+``fvMesh`` exposes (points, faces, owner, neighbour, patch starts, cell centres), i.e. exactly what
+the glue in ``src/initCuda.H`` hands to the library; the tet decomposition itself is done by the
+library (``cpf_mesh_upload_poly``) and, independently, by the oracle.
+
+No OpenFOAM is available in this environment, so the face/point numbering follows blockMesh
+conventions restated from the OpenFOAM documentation: upper-triangular internal face order, boundary
+patches last, face normals pointing owner -> neighbour / out of the domain, hex-model face vertex
+cycles.  (reference: /root/reference/tutorials/incompressible/*/system/blockMeshDict)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# OpenFOAM hex cell model: local vertices 0..7 = (0,0,0),(1,0,0),(1,1,0),(0,1,0),(0,0,1),(1,0,1),(1,1,1),(0,1,1)
+# outward-pointing face cycles of the hex model
+_HEX_FACES = {
+    "x-": (0, 4, 7, 3),
+    "x+": (1, 2, 6, 5),
+    "y-": (0, 1, 5, 4),
+    "y+": (3, 7, 6, 2),
+    "z-": (0, 3, 2, 1),
+    "z+": (4, 5, 6, 7),
+}
+_HEX_OFFS = np.array(
+    [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)], dtype=np.int64
+)
+
+PATCH_NAMES = ("x-", "x+", "y-", "y+", "z-", "z+")
+
+
+@dataclass
+class PolyMesh:
+    """Raw polyMesh arrays (all int32 / float64, C-contiguous)."""
+
+    points: np.ndarray  # [nPoints,3]
+    face_offsets: np.ndarray  # [nFaces+1]
+    face_verts: np.ndarray  # [sum face sizes]
+    owner: np.ndarray  # [nFaces]
+    neighbour: np.ndarray  # [nInternal]
+    cell_centres: np.ndarray  # [nCells,3]
+    patch_starts: np.ndarray  # [nPatches+1] face index ranges of the boundary patches
+    patch_names: tuple = PATCH_NAMES
+    dims: tuple = (0, 0, 0)
+    lo: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    hi: np.ndarray = field(default_factory=lambda: np.ones(3))
+
+    @property
+    def n_points(self) -> int:
+        return int(self.points.shape[0])
+
+    @property
+    def n_cells(self) -> int:
+        return int(self.cell_centres.shape[0])
+
+    @property
+    def n_faces(self) -> int:
+        return int(self.owner.shape[0])
+
+    @property
+    def n_internal(self) -> int:
+        return int(self.neighbour.shape[0])
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    """Vectorised SplitMix64 (public-domain reference constants)."""
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def uniform01(seed: int, n: int, stream: int = 0) -> np.ndarray:
+    """n reproducible doubles in [0,1) from (seed, stream, index) -- explicit host RNG so that the
+    oracle, the reference kernels and the product all see the same cloud."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(n, dtype=np.uint64)
+        key = _splitmix64(np.uint64(seed) ^ (np.uint64(stream) * np.uint64(0xD1342543DE82EF95)))
+        bits = _splitmix64(idx * np.uint64(0x2545F4914F6CDD1D) + key)
+    return (bits >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def box_mesh(nx: int, ny: int, nz: int, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), jitter: float = 0.0,
+             seed: int = 1591593751) -> PolyMesh:
+    """nx*ny*nz hex block in blockMesh ordering.  ``jitter`` (fraction of the local spacing, < 0.3)
+    displaces interior points pseudo-randomly (boundary points slide within their boundary plane)
+    so that tets are irregular and faces non-planar, like a real body-fitted mesh."""
+    lo = np.asarray(lo, dtype=np.float64)
+    hi = np.asarray(hi, dtype=np.float64)
+    npx, npy, npz = nx + 1, ny + 1, nz + 1
+    ii, jj, kk = np.meshgrid(np.arange(npx), np.arange(npy), np.arange(npz), indexing="ij")
+    # point id = i + npx*(j + npy*k)  -> order arrays as (k,j,i)
+    I = ii.transpose(2, 1, 0).reshape(-1)
+    J = jj.transpose(2, 1, 0).reshape(-1)
+    K = kk.transpose(2, 1, 0).reshape(-1)
+    h = (hi - lo) / np.array([nx, ny, nz], dtype=np.float64)
+    pts = np.empty((I.size, 3), dtype=np.float64)
+    pts[:, 0] = lo[0] + I * h[0]
+    pts[:, 1] = lo[1] + J * h[1]
+    pts[:, 2] = lo[2] + K * h[2]
+    if jitter > 0.0:
+        n = I.size
+        for ax, (idx, nmax) in enumerate(((I, nx), (J, ny), (K, nz))):
+            r = uniform01(seed, n, stream=101 + ax) * 2.0 - 1.0
+            interior = (idx > 0) & (idx < nmax)
+            pts[:, ax] += np.where(interior, r * jitter * h[ax], 0.0)
+
+    def pid(i, j, k):
+        return i + npx * (j + npy * k)
+
+    ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    CI = ci.transpose(2, 1, 0).reshape(-1).astype(np.int64)
+    CJ = cj.transpose(2, 1, 0).reshape(-1).astype(np.int64)
+    CK = ck.transpose(2, 1, 0).reshape(-1).astype(np.int64)
+    ncell = CI.size
+    cell_id = CI + nx * (CJ + ny * CK)
+    assert np.array_equal(cell_id, np.arange(ncell))
+    # the 8 corner point ids of every cell
+    corners = np.stack([pid(CI + o[0], CJ + o[1], CK + o[2]) for o in _HEX_OFFS], axis=1)  # [ncell,8]
+
+    # internal faces: for each cell ascending, faces towards +x, +y, +z neighbours (ascending nbr id)
+    has = [CI < nx - 1, CJ < ny - 1, CK < nz - 1]
+    nbr = [cell_id + 1, cell_id + nx, cell_id + nx * ny]
+    cyc = [_HEX_FACES["x+"], _HEX_FACES["y+"], _HEX_FACES["z+"]]
+    slot = np.stack(has, axis=1)  # [ncell,3]
+    order = np.cumsum(slot.reshape(-1)).reshape(ncell, 3) - 1  # face id of (cell, dir) where slot
+    n_internal = int(slot.sum())
+    int_verts = np.empty((n_internal, 4), dtype=np.int64)
+    int_owner = np.empty(n_internal, dtype=np.int64)
+    int_nbr = np.empty(n_internal, dtype=np.int64)
+    for d in range(3):
+        m = slot[:, d]
+        fid = order[m, d]
+        int_verts[fid] = corners[m][:, cyc[d]]
+        int_owner[fid] = cell_id[m]
+        int_nbr[fid] = nbr[d][m]
+
+    # boundary patches, each ordered by cell id
+    b_verts, b_owner, starts = [], [], [n_internal]
+    sel = {
+        "x-": CI == 0, "x+": CI == nx - 1, "y-": CJ == 0, "y+": CJ == ny - 1, "z-": CK == 0, "z+": CK == nz - 1,
+    }
+    for name in PATCH_NAMES:
+        m = sel[name]
+        b_verts.append(corners[m][:, _HEX_FACES[name]])
+        b_owner.append(cell_id[m])
+        starts.append(starts[-1] + int(m.sum()))
+    verts = np.concatenate([int_verts] + b_verts, axis=0)
+    owner = np.concatenate([int_owner] + b_owner, axis=0)
+    nfaces = verts.shape[0]
+    centres = pts[corners].mean(axis=1)
+    if jitter == 0.0:
+        centres[:, 0] = lo[0] + (CI + 0.5) * h[0]
+        centres[:, 1] = lo[1] + (CJ + 0.5) * h[1]
+        centres[:, 2] = lo[2] + (CK + 0.5) * h[2]
+    return PolyMesh(
+        points=np.ascontiguousarray(pts),
+        face_offsets=(np.arange(nfaces + 1, dtype=np.int64) * 4).astype(np.int32),
+        face_verts=np.ascontiguousarray(verts.reshape(-1).astype(np.int32)),
+        owner=owner.astype(np.int32),
+        neighbour=int_nbr.astype(np.int32),
+        cell_centres=np.ascontiguousarray(centres),
+        patch_starts=np.asarray(starts, dtype=np.int32),
+        dims=(nx, ny, nz),
+        lo=lo,
+        hi=hi,
+    )
+
+
+def channel_mesh(nx=400, ny=50, nz=50, jitter: float = 0.0) -> PolyMesh:
+    """BASELINE config 3/5 mesh: 4 x 1 x 1 channel, inlet x-, outlet x+, walls on +-y/+-z."""
+    return box_mesh(nx, ny, nz, lo=(0.0, 0.0, 0.0), hi=(4.0, 1.0, 1.0), jitter=jitter)
+
+
+def backward_step_mesh() -> PolyMesh:
+    """C1 stand-in for pitzDaily (12 225 hex cells, one cell thick): a 163 x 75 x 1 block scaled to the
+    pitzDaily bounding box; the real multi-block grading needs blockMesh (not available)."""
+    return box_mesh(163, 75, 1, lo=(-0.0206, -0.0254, -0.0005), hi=(0.29, 0.0254, 0.0005))
+
+
+# ------------------------------------------------------------------------------------------------
+# frozen velocity fields, evaluated at cell centres (fp64, [nCells,3])
+# ------------------------------------------------------------------------------------------------
+def field_uniform_vortex(x: np.ndarray, U0=(1.0, 0.0, 0.0), omega=2.0 * np.pi, R=0.2, centre=None) -> np.ndarray:
+    """U = U0 + Omega x (x-xc) inside radius R (solid body), decaying as R^2/r^2 outside (Rankine)."""
+    x = np.asarray(x, dtype=np.float64)
+    if centre is None:
+        centre = 0.5 * (x.min(axis=0) + x.max(axis=0))
+    dx = x[:, 0] - centre[0]
+    dy = x[:, 1] - centre[1]
+    r2 = dx * dx + dy * dy
+    s = np.where(r2 <= R * R, omega, omega * R * R / np.maximum(r2, 1e-300))
+    U = np.empty_like(x)
+    U[:, 0] = U0[0] - s * dy
+    U[:, 1] = U0[1] + s * dx
+    U[:, 2] = U0[2]
+    return U
+
+
+def field_channel(x: np.ndarray, t: float = 0.0, Umax=1.0, eps=0.05, lo=(0, 0, 0), hi=(4, 1, 1)) -> np.ndarray:
+    """Plane-Poiseuille-like profile with a small travelling sinusoidal perturbation (C3/C5)."""
+    x = np.asarray(x, dtype=np.float64)
+    Y = (x[:, 1] - lo[1]) / (hi[1] - lo[1])
+    Z = (x[:, 2] - lo[2]) / (hi[2] - lo[2])
+    prof = 16.0 * Y * (1 - Y) * Z * (1 - Z)
+    ph = 2.0 * np.pi * (x[:, 0] / (hi[0] - lo[0]) - t)
+    U = np.empty_like(x)
+    U[:, 0] = Umax * prof
+    U[:, 1] = eps * Umax * np.sin(ph) * np.sin(np.pi * Y)
+    U[:, 2] = eps * Umax * np.cos(ph) * np.sin(np.pi * Z)
+    return U
+
+
+def seed_box(n: int, lo, hi, seed: int = 1591593751) -> np.ndarray:
+    """Particle cloud [n,4] = (x,y,z,w=1) uniform in the seeding box (src/initCuda.H:50-62 keys)."""
+    lo = np.asarray(lo, dtype=np.float64)
+    hi = np.asarray(hi, dtype=np.float64)
+    p = np.empty((n, 4), dtype=np.float64)
+    for ax in range(3):
+        p[:, ax] = lo[ax] + uniform01(seed, n, stream=ax) * (hi[ax] - lo[ax])
+    p[:, 3] = 1.0
+    return p
