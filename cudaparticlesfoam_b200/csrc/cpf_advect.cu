@@ -1,0 +1,406 @@
+// cpf_advect.cu -- the fused particle sub-step kernel (sm_100a).
+//
+// One launch = nSub iterations of the loop body of /root/reference/src/advect.H:96-161 for every
+// particle, i.e. the reference's five kernels
+//   particleAdvectKernelTetVel (cuda/particles.cu:316-373)      S1
+//   particleBrownianMotion     (cuda/particles.cu:551-575)      S2
+//   particleLocator            (query/ConvexQuery.cu:135-216)   S3   | baryQueryDisp (query/RTQuery.cu:221-248)
+//   convexReflector            (query/ConvexQuery.cu:320-436)   S4   | RTreflection  (query/RTQuery.cu:109-186)
+//   particleMoveKernel         (cuda/particles.cu:659-704)      S5
+// fused, with the particle (position, flag, tet id) held in registers across the fused sub-steps:
+// one 256-bit load + one 32-bit load per particle per launch, the same back.  disp never touches
+// memory; vel is written only when the host can observe it (last sub-step of a call).
+#include "cpf_internal.h"
+
+namespace cpf {
+
+// ------------------------------------------------------------------------------------------------
+// random walk deviates
+// ------------------------------------------------------------------------------------------------
+template <int RNG> struct Rng;
+
+template <> struct Rng<CPF_RNG_NONE> {
+    CPF_DEV void open(const ParticleView &, long long, const StepParams &) {}
+    CPF_DEV bool draw(int, double &, double &, double &) { return false; }
+    CPF_DEV void close(const ParticleView &, long long) {}
+};
+
+// The reference's stream: cuRAND XORWOW, curand_init(1591593751, particle, 0), three successive
+// curand_normal_double per sub-step (cuda/particles.cu:537,565-567).  The state lives in registers
+// for the whole launch: 48 B in + 48 B out per particle per launch instead of per sub-step.
+template <> struct Rng<CPF_RNG_XORWOW> {
+    curandState_t st;
+    CPF_DEV void open(const ParticleView &pv, long long i, const StepParams &) { st = pv.rng[i]; }
+    CPF_DEV bool draw(int, double &a, double &b, double &c)
+    {
+        a = curand_normal_double(&st);
+        b = curand_normal_double(&st);
+        c = curand_normal_double(&st);
+        return true;
+    }
+    CPF_DEV void close(const ParticleView &pv, long long i) { pv.rng[i] = st; }
+};
+
+// Stateless counter-based stream: Philox4x32-10 keyed by the seed, counter = (particle id,
+// sub-step index); fp32 Box-Muller.  0 B of RNG traffic.  Statistical (not bit) parity with XORWOW.
+CPF_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+CPF_DEV void box_muller_f32(uint32_t x, uint32_t y, double &n0, double &n1)
+{
+    const float u1 = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    n0 = (double)(r * s);
+    n1 = (double)(r * c);
+}
+template <> struct Rng<CPF_RNG_PHILOX> {
+    uint32_t id, k0, k1;
+    unsigned long long step0;
+    CPF_DEV void open(const ParticleView &pv, long long i, const StepParams &sp)
+    {
+        id = (uint32_t)pv.pid[i];
+        k0 = (uint32_t)sp.seed; k1 = (uint32_t)(sp.seed >> 32);
+        step0 = sp.step0;
+    }
+    CPF_DEV bool draw(int s, double &a, double &b, double &c)
+    {
+        const unsigned long long st = step0 + (unsigned long long)s;
+        uint32_t o[4];
+        philox4x32_10(id, 0u, (uint32_t)st, (uint32_t)(st >> 32), k0, k1, o);
+        double d;
+        box_muller_f32(o[0], o[1], a, b);
+        box_muller_f32(o[2], o[3], c, d);
+        return true;
+    }
+    CPF_DEV void close(const ParticleView &, long long) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// exact sub-step tails (S3+S4+S5)
+// ------------------------------------------------------------------------------------------------
+struct Tally { unsigned hops, exact, refl, esc; };
+
+// Default build: convex line walk + reflector.  The reference's reflector re-walks the segment
+// from the start tet with bit-identical arithmetic (ConvexQuery.cu:343-397 vs :165-200), so the
+// locator's wall state IS the reflector's state after its first inner loop; we continue from it.
+CPF_DEV void tail_convex_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &tet, double &w, int reflect, Tally &ty)
+{
+    const D3 E0 = xadd(P, disp);
+    D3 E = E0, S = P;
+    int cur = tet, in_j = -1;
+    bool wall = false;
+    Tet T;
+    int4 v;
+    for (int i = 0; i < 50; ++i) {
+        T = load_tet(m, cur, v);
+        ty.hops++;
+        const int out = trace_exact(T, S, E, in_j);
+        if (out < 0) break;
+        const int link = link_at(T.link, out);
+        in_j = out;
+        if (link < 0) { wall = true; break; }
+        cur = link >> 2;
+        in_j = link & 3;
+    }
+    if (!wall) {
+        tet = cur;
+        P = xadd(P, disp); // S5
+        return;
+    }
+    if (!reflect) { // reflectWall == false: id stays -(tet+1), particle is moved, frozen next step
+        tet = -(tet + 1);
+        P = xadd(P, disp);
+        return;
+    }
+    // S4: convexReflector, up to 5 wall hits
+    D3 Phit = S;
+    int next = -1;
+    for (int j = 0; j < 5; ++j) {
+        if (j > 0) {
+            next = -1;
+            bool hitwall = false;
+            int i = 0;
+            for (; i < 50; ++i) {
+                T = load_tet(m, cur, v);
+                ty.hops++;
+                const int out = trace_exact(T, S, E, in_j);
+                if (out < 0) break;
+                const int link = link_at(T.link, out);
+                in_j = out;
+                if (link < 0) { hitwall = true; break; }
+                cur = link >> 2;
+                in_j = link & 3;
+            }
+            if (!hitwall) { next = cur; break; } // end point found (or 50-tet cap: next == cur)
+        }
+        Phit = S;
+        ty.refl++;
+        reflect_exact(T, Phit, E, vel);
+    }
+    const D3 nd = xsub(E, Phit);
+    tet = next;
+    P = xadd(Phit, nd); // p = P_hit (S4) then p += disp (S5)
+    (void)w;
+}
+
+// RTX=true build: barycentric point walk + RTreflection
+CPF_DEV int bary_search(const MeshView &m, D3 Q, int start, Tet &T, int &face_j, Tally &ty)
+{
+    int s = start;
+    face_j = -1;
+    int4 v;
+    for (int i = 0; i < 50; ++i) {
+        T = load_tet(m, s, v);
+        ty.hops++;
+        double w[4];
+        bary_exact(T, Q, w);
+        const double wmin = fmin(fmin(w[0], w[1]), fmin(w[2], w[3]));
+        if (wmin >= 0.0) break;
+        int k = 0;
+        if (w[1] < w[0]) k = 1;
+        if (w[2] < (k == 0 ? w[0] : w[1])) k = 2;
+        if (w[3] < (k == 0 ? w[0] : (k == 1 ? w[1] : w[2]))) k = 3;
+        face_j = (T.code >> (2 * k)) & 3u;
+        const int link = link_at(T.link, face_j);
+        if (link < 0) return -(s + 1);
+        s = link >> 2;
+    }
+    return s;
+}
+
+CPF_DEV void tail_bary_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &tet, int reflect, Tally &ty)
+{
+    Tet T;
+    int fj;
+    D3 R = xadd(P, disp);
+    int s = bary_search(m, R, tet, T, fj, ty);
+    if (s < 0 && reflect) {
+        int bd = -(s + 1);
+        for (int i = 0; i < 10; ++i) {
+            if (i > 0) {
+                s = bary_search(m, R, bd, T, fj, ty);
+                if (s >= 0) { bd = s; break; }
+                bd = -(s + 1);
+            }
+            // specularReflect (query/RTQuery.cu:92-107) on face fj of tet bd (= T)
+            D3 A;
+            const D3 n = face_normal_exact(T, fj, A);
+            double sp = xdot(xsub(R, A), n);
+            sp = __dadd_rn(sp, sp);
+            double sv = xdot(vel, n);
+            sv = __dadd_rn(sv, sv);
+            R = D3{ __fma_rn(-sp, n.x, R.x), __fma_rn(-sp, n.y, R.y), __fma_rn(-sp, n.z, R.z) };
+            vel = D3{ __fma_rn(-sv, n.x, vel.x), __fma_rn(-sv, n.y, vel.y), __fma_rn(-sv, n.z, vel.z) };
+            ty.refl++;
+        }
+        s = bd;
+        disp = xsub(R, P);
+    }
+    tet = s;
+    P = xadd(P, disp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused kernel
+// ------------------------------------------------------------------------------------------------
+template <int LOC, bool FILT, int RNG>
+__global__ void __launch_bounds__(128) k_substeps(const MeshView m, const ParticleView pv, const StepParams sp)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    Tally ty{ 0u, 0u, 0u, 0u };
+    unsigned nsteps = 0;
+    if (i < pv.n) {
+        double4 p4 = ld_stream4(pv.pos + i);
+        int tet = ld_stream_i(pv.tet + i);
+        D3 P{ p4.x, p4.y, p4.z };
+        double w = p4.w;
+        D3 vel{ 0.0, 0.0, 0.0 };
+        bool velValid = false;
+        Rng<RNG> rng;
+        const bool live = (w != 0.0);
+        if (live) rng.open(pv, i, sp);
+        for (int s = 0; s < sp.nSub; ++s) {
+            if (w == 0.0) break;
+            if (tet < 0) { w = 0.0; break; } // S1: left the domain -> frozen (particles.cu:334-338)
+            // ---- S1 velocity + Euler displacement: disp = (P + dt*vel) - P
+            const int4 v = ld_int4(m.tetv, tet);
+            const int cell = tet_cell(m, tet, v);
+            const double *uc = m.ucell + 3ll * cell;
+            vel = D3{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+            velValid = true;
+            D3 disp{ __dsub_rn(__fma_rn(sp.dt, vel.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, vel.y, P.y), P.y),
+                     __dsub_rn(__fma_rn(sp.dt, vel.z, P.z), P.z) };
+            // ---- S2 random walk: disp += xi * sqrt(2 D dt)
+            double x0, x1, x2;
+            if (rng.draw(s, x0, x1, x2)) {
+                disp.x = __fma_rn(x0, sp.randDisp, disp.x);
+                disp.y = __fma_rn(x1, sp.randDisp, disp.y);
+                disp.z = __fma_rn(x2, sp.randDisp, disp.z);
+            }
+            nsteps++;
+            // ---- S3..S5
+            if (LOC == CPF_LOCATOR_CONVEX) {
+                if (FILT) {
+                    int hops = 0;
+                    const int r = walk_filtered(m, tet, P, disp, hops);
+                    ty.hops += hops;
+                    if (r >= 0) {
+                        tet = r;
+                        P = xadd(P, disp);
+                        continue;
+                    }
+                }
+                ty.exact++;
+                tail_convex_exact(m, P, disp, vel, tet, w, sp.reflect, ty);
+            } else {
+                ty.exact++;
+                tail_bary_exact(m, P, disp, vel, tet, sp.reflect, ty);
+            }
+        }
+        if (live) {
+            rng.close(pv, i);
+            st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
+            st_stream_i(pv.tet + i, tet);
+            if (sp.writeVel && velValid) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
+        }
+    }
+    // statistics: warp reduce, one atomic per warp and counter
+    unsigned vals[5] = { ty.esc, ty.refl, ty.exact, ty.hops, nsteps };
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        unsigned x = __reduce_add_sync(0xffffffffu, vals[c]);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(sp.counters + c, (unsigned long long)x);
+    }
+}
+
+// src/initCuda.H:184-199: the one cudaAdvect right after seeding; its only lasting effect is to
+// deactivate particles whose initial location failed (tet < 0) and to fill vel for VTU 0.
+__global__ void __launch_bounds__(128) k_initial_advect(const MeshView m, const ParticleView pv)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pv.n) return;
+    double4 p4 = pv.pos[i];
+    if (p4.w == 0.0) return;
+    const int tet = pv.tet[i];
+    if (tet < 0) { p4.w = 0.0; pv.pos[i] = p4; return; }
+    const int4 v = ld_int4(m.tetv, tet);
+    const int cell = tet_cell(m, tet, v);
+    const double *uc = m.ucell + 3ll * cell;
+    pv.vel[i] = make_double4(uc[0], uc[1], uc[2], -1.0);
+}
+
+__global__ void k_init_rng(curandState_t *st, long long n, unsigned long long seed)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) curand_init(seed, (unsigned long long)i, 0ull, &st[i]); // particles.cu:537
+}
+
+template <int RNG> __global__ void k_debug_normals(const ParticleView pv, const StepParams sp, double *xi)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pv.n) return;
+    Rng<RNG> rng;
+    rng.open(pv, i, sp);
+    double a = 0, b = 0, c = 0;
+    rng.draw(0, a, b, c);
+    const long long o = pv.pid[i];
+    xi[3 * o] = a; xi[3 * o + 1] = b; xi[3 * o + 2] = c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+template <int LOC, bool FILT> static void launch_rng(cpf_context *ctx, const MeshView &m, const ParticleView &pv,
+                                                     const StepParams &sp, int rng, dim3 grid)
+{
+    switch (rng) {
+    case CPF_RNG_XORWOW: k_substeps<LOC, FILT, CPF_RNG_XORWOW><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
+    case CPF_RNG_PHILOX: k_substeps<LOC, FILT, CPF_RNG_PHILOX><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
+    default: k_substeps<LOC, FILT, CPF_RNG_NONE><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
+    }
+}
+
+int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
+{
+    if (ctx->n == 0 || nSub <= 0) return CPF_OK;
+    const MeshView m = mesh_view(ctx);
+    const ParticleView pv = particle_view(ctx);
+    StepParams sp;
+    sp.nSub = nSub;
+    sp.dt = dt;
+    sp.randDisp = sqrt((2.00 * ctx->cfg.diffusion_coeff) * dt);
+    sp.reflect = ctx->cfg.reflect_wall;
+    sp.writeVel = writeVel ? 1 : 0;
+    sp.seed = ctx->cfg.seed;
+    sp.step0 = ctx->step_index;
+    sp.counters = ctx->d_counters;
+    int rng = ctx->cfg.rng;
+    if (rng == CPF_RNG_XORWOW && !ctx->rng_ready) {
+        int rc = launch_init_rng(ctx);
+        if (rc) return rc;
+    }
+    const dim3 grid((unsigned)((ctx->n + 127) / 128));
+    if (ctx->cfg.locator == CPF_LOCATOR_BARY) launch_rng<CPF_LOCATOR_BARY, false>(ctx, m, pv, sp, rng, grid);
+    else if (ctx->cfg.path == CPF_PATH_EXACT) launch_rng<CPF_LOCATOR_CONVEX, false>(ctx, m, pv, sp, rng, grid);
+    else launch_rng<CPF_LOCATOR_CONVEX, true>(ctx, m, pv, sp, rng, grid);
+    ctx->launches++;
+    ctx->step_index += (unsigned long long)nSub;
+    CPF_CUDA(ctx, cudaGetLastError());
+    return CPF_OK;
+}
+
+int launch_initial_advect(cpf_context *ctx, double)
+{
+    if (ctx->n == 0) return CPF_OK;
+    k_initial_advect<<<(unsigned)((ctx->n + 127) / 128), 128, 0, ctx->stream>>>(mesh_view(ctx), particle_view(ctx));
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+    return CPF_OK;
+}
+
+int launch_init_rng(cpf_context *ctx)
+{
+    for (int b = 0; b < 2; ++b)
+        if (!ctx->d_rng[b]) CPF_CUDA(ctx, cudaMalloc(&ctx->d_rng[b], sizeof(curandState_t) * (size_t)ctx->n));
+    // states are indexed by ORIGINAL particle id; only valid before any sort or via pid scatter
+    if (ctx->permuted) return fail(ctx, CPF_ERR_INVALID, "cpf_init_rng must run before particles are sorted");
+    k_init_rng<<<(unsigned)((ctx->n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_rng[ctx->pcur], ctx->n, ctx->cfg.seed);
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+    ctx->rng_ready = true;
+    return CPF_OK;
+}
+
+int launch_debug_normals(cpf_context *ctx, double *d_xi)
+{
+    const ParticleView pv = particle_view(ctx);
+    StepParams sp{};
+    sp.seed = ctx->cfg.seed;
+    sp.step0 = ctx->step_index;
+    const unsigned grid = (unsigned)((ctx->n + 127) / 128);
+    if (ctx->cfg.rng == CPF_RNG_XORWOW) {
+        if (!ctx->rng_ready) { int rc = launch_init_rng(ctx); if (rc) return rc; }
+        k_debug_normals<CPF_RNG_XORWOW><<<grid, 128, 0, ctx->stream>>>(particle_view(ctx), sp, d_xi);
+    } else if (ctx->cfg.rng == CPF_RNG_PHILOX) {
+        k_debug_normals<CPF_RNG_PHILOX><<<grid, 128, 0, ctx->stream>>>(pv, sp, d_xi);
+    } else {
+        CPF_CUDA(ctx, cudaMemsetAsync(d_xi, 0, sizeof(double) * 3 * (size_t)ctx->n, ctx->stream));
+    }
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+    return CPF_OK;
+}
+
+} // namespace cpf

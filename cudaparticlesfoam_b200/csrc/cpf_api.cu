@@ -1,0 +1,585 @@
+// cpf_api.cu -- the C ABI of libcpf (include/cpf.h).  Host-side orchestration only; every entry
+// point validates, enqueues work on the context's stream and returns a status code.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "cpf_internal.h"
+
+using namespace cpf;
+
+namespace cpf {
+void release_mesh(cpf_context *ctx);
+
+ParticleView particle_view(const cpf_context *ctx)
+{
+    ParticleView pv;
+    const int a = ctx->pcur;
+    pv.pos = ctx->d_pos[a]; pv.tet = ctx->d_tet[a]; pv.pid = ctx->d_pid[a]; pv.vel = ctx->d_vel[a]; pv.rng = ctx->d_rng[a];
+    pv.n = ctx->n;
+    return pv;
+}
+
+int ensure_scratch(cpf_context *ctx, size_t bytes)
+{
+    if (bytes <= ctx->scratch_bytes) return CPF_OK;
+    if (ctx->d_scratch) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0; }
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return CPF_OK;
+}
+
+static void free_particles(cpf_context *ctx)
+{
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(ctx->d_pos[b]); cudaFree(ctx->d_tet[b]); cudaFree(ctx->d_pid[b]); cudaFree(ctx->d_vel[b]); cudaFree(ctx->d_rng[b]);
+        ctx->d_pos[b] = nullptr; ctx->d_tet[b] = nullptr; ctx->d_pid[b] = nullptr; ctx->d_vel[b] = nullptr; ctx->d_rng[b] = nullptr;
+    }
+    ctx->n = 0; ctx->pcur = 0; ctx->permuted = false; ctx->rng_ready = false; ctx->have_tets = false;
+}
+
+__global__ void k_iota_fill(long long n, int *pid0, int *tet0)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { pid0[i] = (int)i; tet0[i] = -1; }
+}
+
+static int alloc_particles(cpf_context *ctx, long long n)
+{
+    free_particles(ctx);
+    if (n <= 0) return CPF_OK;
+    if (n >= (1ll << 31)) return fail(ctx, CPF_ERR_INVALID, "more than 2^31 particles per GPU are not supported");
+    for (int b = 0; b < 2; ++b) {
+        CPF_CUDA(ctx, cudaMalloc(&ctx->d_pos[b], sizeof(double4) * (size_t)n));
+        CPF_CUDA(ctx, cudaMalloc(&ctx->d_tet[b], sizeof(int) * (size_t)n));
+        CPF_CUDA(ctx, cudaMalloc(&ctx->d_pid[b], sizeof(int) * (size_t)n));
+        CPF_CUDA(ctx, cudaMalloc(&ctx->d_vel[b], sizeof(double4) * (size_t)n));
+        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_vel[b], 0, sizeof(double4) * (size_t)n, ctx->stream));
+    }
+    ctx->n = n;
+    k_iota_fill<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->d_pid[0], ctx->d_tet[0]);
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+    return CPF_OK;
+}
+
+static inline unsigned long long splitmix64(unsigned long long x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    unsigned long long z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+} // namespace cpf
+
+static std::string g_create_error;
+
+extern "C" {
+
+int cpf_abi_version(void) { return CPF_ABI_VERSION; }
+
+void cpf_default_config(cpf_config *cfg)
+{
+    memset(cfg, 0, sizeof *cfg);
+    cfg->device = 0;
+    cfg->interp = CPF_INTERP_TET;       // src/initCuda.H:72
+    cfg->locator = CPF_LOCATOR_CONVEX;  // etc/bashrc:1 RTX=false -> -DConvexPoly
+    cfg->integrator = CPF_EULER;
+    cfg->rng = CPF_RNG_XORWOW;          // usingBrownianMotion = true, src/initCuda.H:66
+    cfg->reflect_wall = 1;              // src/initCuda.H:67
+    cfg->path = CPF_PATH_FILTERED;
+    cfg->sort_interval = 0;
+    cfg->fuse_substeps = 0;
+    cfg->dt = 1e-4;                     // src/initCuda.H:55
+    cfg->diffusion_coeff = 5.7e-6;      // src/initCuda.H:56
+    cfg->seed = 1591593751ull;          // cuda/particles.cu:544
+    cfg->save_interval = 10;            // src/initCuda.H:57
+}
+
+int cpf_create(const cpf_config *cfg, cpf_context **out)
+{
+    if (!out) return CPF_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libcpf has no CPU fallback";
+        return CPF_ERR_NO_DEVICE;
+    }
+    cpf_context *ctx = new (std::nothrow) cpf_context;
+    if (!ctx) return CPF_ERR_NOMEM;
+    if (cfg) ctx->cfg = *cfg; else cpf_default_config(&ctx->cfg);
+    ctx->device = ctx->cfg.device;
+    if (ctx->device < 0 || ctx->device >= ndev) { g_create_error = "bad device ordinal"; delete ctx; return CPF_ERR_INVALID; }
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * CNT_COUNT)) != cudaSuccess ||
+        (e = cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * CNT_COUNT)) != cudaSuccess) {
+        g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
+        delete ctx;
+        return CPF_ERR_CUDA;
+    }
+    *out = ctx;
+    return CPF_OK;
+}
+
+int cpf_destroy(cpf_context *ctx)
+{
+    if (!ctx) return CPF_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_particles(ctx);
+    release_mesh(ctx);
+    cudaFree(ctx->d_counters); cudaFree(ctx->d_sort_hist); cudaFree(ctx->d_scratch);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evCopy);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copyStream);
+    delete ctx;
+    return CPF_OK;
+}
+
+const char *cpf_last_error(const cpf_context *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int cpf_sync(cpf_context *ctx)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CPF_OK;
+}
+
+int cpf_set_config(cpf_context *ctx, const cpf_config *cfg)
+{
+    if (!ctx || !cfg) return CPF_ERR_INVALID;
+    if (cfg->device != ctx->cfg.device) return fail(ctx, CPF_ERR_INVALID, "the device cannot change after cpf_create");
+    ctx->cfg = *cfg;
+    return CPF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mesh
+// ---------------------------------------------------------------------------------------------
+static void bbox_of(cpf_context *ctx, long long n, const double *a, bool reset)
+{
+    if (reset) for (int k = 0; k < 3; ++k) { ctx->bbox_lo[k] = 1e300; ctx->bbox_hi[k] = -1e300; }
+    for (long long i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            ctx->bbox_lo[k] = std::min(ctx->bbox_lo[k], a[3 * i + k]);
+            ctx->bbox_hi[k] = std::max(ctx->bbox_hi[k], a[3 * i + k]);
+        }
+}
+
+static int upload_patch_kinds(cpf_context *ctx, int nPatches, const int *patchKind)
+{
+    ctx->nPatches = nPatches > 0 ? nPatches : 1;
+    std::vector<uint8_t> k((size_t)ctx->nPatches, (uint8_t)CPF_PATCH_REFLECT);
+    if (patchKind) for (int p = 0; p < nPatches; ++p) k[(size_t)p] = (uint8_t)patchKind[p];
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_patch_kind, k.size()));
+    CPF_CUDA(ctx, cudaMemcpy(ctx->d_patch_kind, k.data(), k.size(), cudaMemcpyHostToDevice));
+    return CPF_OK;
+}
+
+int cpf_mesh_upload_poly(cpf_context *ctx, int nPoints, const double *points, int nFaces, const int *faceOffsets,
+                         const int *faceVerts, const int *owner, int nInternal, const int *neighbour, int nCells,
+                         const double *cellCentres, const int *tetBasePt, int nPatches, const int *patchStart, const int *patchKind)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    if (!points || !faceOffsets || !faceVerts || !owner || (nInternal > 0 && !neighbour) || !cellCentres || nPoints <= 0 ||
+        nFaces <= 0 || nCells <= 0 || nInternal < 0 || nInternal > nFaces)
+        return fail(ctx, CPF_ERR_INVALID, "cpf_mesh_upload_poly: bad arguments");
+    cudaSetDevice(ctx->device);
+    // --- the glue's decomposition (src/initCuda.H:86-110): cell by cell, face by face of the
+    // cell (owned faces ascending, then neighbour faces ascending), one tet per face-fan triangle
+    std::vector<int> start((size_t)nCells + 1, 0);
+    for (int f = 0; f < nFaces; ++f) {
+        if (owner[f] < 0 || owner[f] >= nCells) return fail(ctx, CPF_ERR_INVALID, "owner[%d] out of range", f);
+        start[(size_t)owner[f] + 1]++;
+    }
+    for (int f = 0; f < nInternal; ++f) {
+        if (neighbour[f] < 0 || neighbour[f] >= nCells) return fail(ctx, CPF_ERR_INVALID, "neighbour[%d] out of range", f);
+        start[(size_t)neighbour[f] + 1]++;
+    }
+    for (int c = 0; c < nCells; ++c) start[(size_t)c + 1] += start[(size_t)c];
+    std::vector<int> cellFaces((size_t)start[(size_t)nCells]), fill((size_t)nCells, 0);
+    for (int f = 0; f < nFaces; ++f) { const int c = owner[f]; cellFaces[(size_t)(start[(size_t)c] + fill[(size_t)c]++)] = f; }
+    for (int f = 0; f < nInternal; ++f) { const int c = neighbour[f]; cellFaces[(size_t)(start[(size_t)c] + fill[(size_t)c]++)] = f; }
+    std::vector<int> facePatch;
+    if (nPatches > 0 && patchStart) {
+        facePatch.assign((size_t)nFaces, -1);
+        for (int p = 0; p < nPatches; ++p)
+            for (int f = patchStart[p]; f < patchStart[p + 1] && f < nFaces; ++f) facePatch[(size_t)f] = p;
+    }
+    long long nTets = 0;
+    for (int f = 0; f < nFaces; ++f) {
+        const int sz = faceOffsets[f + 1] - faceOffsets[f];
+        if (sz < 3) return fail(ctx, CPF_ERR_INVALID, "face %d has fewer than 3 points", f);
+        nTets += (long long)(sz - 2) * (f < nInternal ? 2 : 1);
+    }
+    std::vector<int> tets((size_t)nTets * 4), tetPatch((size_t)nTets, -1);
+    long long t = 0;
+    for (int c = 0; c < nCells; ++c)
+        for (int q = start[(size_t)c]; q < start[(size_t)c + 1]; ++q) {
+            const int f = cellFaces[(size_t)q];
+            const int *F = faceVerts + faceOffsets[f];
+            const int sz = faceOffsets[f + 1] - faceOffsets[f];
+            const int base = tetBasePt ? tetBasePt[f] : 0;
+            const bool own = owner[f] == c;
+            for (int tp = 1; tp <= sz - 2; ++tp) {
+                int pa = (tp + base) % sz, pb = (pa + 1) % sz;
+                if (!own) std::swap(pa, pb);
+                int *o = &tets[(size_t)t * 4];
+                o[0] = nPoints + c; o[1] = F[base]; o[2] = F[pa]; o[3] = F[pb];
+                if (!facePatch.empty()) tetPatch[(size_t)t] = facePatch[(size_t)f];
+                else tetPatch[(size_t)t] = f >= nInternal ? 0 : -1;
+                ++t;
+            }
+        }
+    // vertex array = [points..., cell centres...]  (src/initCuda.H:112-124)
+    std::vector<double> pos(((size_t)nPoints + (size_t)nCells) * 3);
+    memcpy(pos.data(), points, sizeof(double) * 3 * (size_t)nPoints);
+    memcpy(pos.data() + 3 * (size_t)nPoints, cellCentres, sizeof(double) * 3 * (size_t)nCells);
+    bbox_of(ctx, nPoints, points, true);
+    int rc = build_device_mesh(ctx, (long long)nPoints + nCells, pos.data(), nTets, tets.data(), nullptr, tetPatch.data(), nCells,
+                               nPoints, true);
+    if (rc) return rc;
+    return upload_patch_kinds(ctx, nPatches, patchKind);
+}
+
+int cpf_mesh_upload_tets(cpf_context *ctx, int nVerts, const double *positions, long long nTets, const int *tetVerts,
+                         const int *tetCell, int nCells)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    if (!positions || !tetVerts || nVerts <= 0 || nTets <= 0) return fail(ctx, CPF_ERR_INVALID, "cpf_mesh_upload_tets: bad arguments");
+    cudaSetDevice(ctx->device);
+    if (!tetCell) nCells = (int)nTets;
+    bbox_of(ctx, nVerts, positions, true);
+    int rc = build_device_mesh(ctx, nVerts, positions, nTets, tetVerts, tetCell, nullptr, nCells, 0, false);
+    if (rc) return rc;
+    return upload_patch_kinds(ctx, 1, nullptr);
+}
+
+int cpf_mesh_info(cpf_context *ctx, long long *nVerts, long long *nTets, long long *nCells, long long *nBoundaryFaces)
+{
+    if (!ctx || !ctx->have_mesh) return fail(ctx, CPF_ERR_INVALID, "no mesh uploaded");
+    if (nVerts) *nVerts = ctx->nVerts;
+    if (nTets) *nTets = ctx->nTets;
+    if (nCells) *nCells = ctx->nCells;
+    if (nBoundaryFaces) *nBoundaryFaces = ctx->nBoundaryFaces;
+    return CPF_OK;
+}
+
+int cpf_mesh_download_tets(cpf_context *ctx, int *tetVerts, int *tetCell)
+{
+    if (!ctx || !ctx->have_mesh) return fail(ctx, CPF_ERR_INVALID, "no mesh uploaded");
+    cudaSetDevice(ctx->device);
+    std::vector<int4> sv((size_t)ctx->nTets);
+    std::vector<uint16_t> code((size_t)ctx->nTets);
+    CPF_CUDA(ctx, cudaMemcpy(sv.data(), ctx->d_tetv, sizeof(int4) * sv.size(), cudaMemcpyDeviceToHost));
+    CPF_CUDA(ctx, cudaMemcpy(code.data(), ctx->d_tetcode, sizeof(uint16_t) * code.size(), cudaMemcpyDeviceToHost));
+    std::vector<int> cells;
+    if (tetCell && !ctx->cellFromVertex) {
+        CPF_CUDA(ctx, cudaMemcpy(tetCell, ctx->d_tetcell, sizeof(int) * (size_t)ctx->nTets, cudaMemcpyDeviceToHost));
+    }
+    for (long long t = 0; t < ctx->nTets; ++t) {
+        const int s[4] = { sv[(size_t)t].x, sv[(size_t)t].y, sv[(size_t)t].z, sv[(size_t)t].w };
+        if (tetVerts)
+            for (int k = 0; k < 4; ++k) tetVerts[4 * t + k] = s[(code[(size_t)t] >> (2 * k)) & 3];
+        if (tetCell && ctx->cellFromVertex) tetCell[t] = s[3] - ctx->nPoints;
+    }
+    return CPF_OK;
+}
+
+int cpf_mesh_download_neighbours(cpf_context *ctx, int *nbr)
+{
+    if (!ctx || !ctx->have_mesh || !nbr) return fail(ctx, CPF_ERR_INVALID, "no mesh uploaded");
+    cudaSetDevice(ctx->device);
+    std::vector<int4> l((size_t)ctx->nTets);
+    std::vector<uint16_t> code((size_t)ctx->nTets);
+    CPF_CUDA(ctx, cudaMemcpy(l.data(), ctx->d_tetl, sizeof(int4) * l.size(), cudaMemcpyDeviceToHost));
+    CPF_CUDA(ctx, cudaMemcpy(code.data(), ctx->d_tetcode, sizeof(uint16_t) * code.size(), cudaMemcpyDeviceToHost));
+    for (long long t = 0; t < ctx->nTets; ++t) {
+        const int lk[4] = { l[(size_t)t].x, l[(size_t)t].y, l[(size_t)t].z, l[(size_t)t].w };
+        for (int k = 0; k < 4; ++k) {
+            const int v = lk[(code[(size_t)t] >> (2 * k)) & 3];
+            nbr[4 * t + k] = v < 0 ? v : (v >> 2);
+        }
+    }
+    return CPF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// flow field
+// ---------------------------------------------------------------------------------------------
+int cpf_update_velocity(cpf_context *ctx, const double *U, int on_device)
+{
+    if (!ctx || !ctx->have_mesh || !U) return fail(ctx, CPF_ERR_INVALID, "cpf_update_velocity: no mesh or null field");
+    cudaSetDevice(ctx->device);
+    const size_t bytes = sizeof(double) * 3 * (size_t)ctx->nCells;
+    // double-buffered: sub-steps already enqueued keep reading the previous field
+    const int nb = 1 - ctx->ucur;
+    CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ucell[nb], U, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    ctx->ucur = nb;
+    return CPF_OK;
+}
+
+int cpf_update_vertex_velocity(cpf_context *ctx, const double *Uvert, int on_device)
+{
+    if (!ctx || !ctx->have_mesh || !Uvert) return fail(ctx, CPF_ERR_INVALID, "cpf_update_vertex_velocity: no mesh or null field");
+    cudaSetDevice(ctx->device);
+    const size_t bytes = sizeof(double) * 3 * (size_t)ctx->nVerts;
+    if (!ctx->d_uvert) CPF_CUDA(ctx, cudaMalloc(&ctx->d_uvert, bytes));
+    CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_uvert, Uvert, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    return CPF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// particles
+// ---------------------------------------------------------------------------------------------
+int cpf_set_particles(cpf_context *ctx, long long n, const double *xyzw)
+{
+    if (!ctx || n < 0 || (n > 0 && !xyzw)) return fail(ctx, CPF_ERR_INVALID, "cpf_set_particles: bad arguments");
+    cudaSetDevice(ctx->device);
+    int rc = alloc_particles(ctx, n);
+    if (rc) return rc;
+    if (n) CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_pos[0], xyzw, sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CPF_OK;
+}
+
+int cpf_seed_box(cpf_context *ctx, long long n, const double lo[3], const double hi[3], unsigned long long seed)
+{
+    if (!ctx || n < 0 || !lo || !hi) return fail(ctx, CPF_ERR_INVALID, "cpf_seed_box: bad arguments");
+    std::vector<double> p((size_t)n * 4);
+    for (int ax = 0; ax < 3; ++ax) {
+        const unsigned long long key = splitmix64(seed ^ ((unsigned long long)ax * 0xD1342543DE82EF95ull));
+        for (long long i = 0; i < n; ++i) {
+            const unsigned long long bits = splitmix64((unsigned long long)i * 0x2545F4914F6CDD1Dull + key);
+            const double u = (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+            p[(size_t)i * 4 + ax] = lo[ax] + u * (hi[ax] - lo[ax]); // lower + r*(upper-lower), particles.cu:88-91
+        }
+    }
+    for (long long i = 0; i < n; ++i) p[(size_t)i * 4 + 3] = 1.0;
+    return cpf_set_particles(ctx, n, p.data());
+}
+
+int cpf_set_tets(cpf_context *ctx, const int *tet)
+{
+    if (!ctx || !tet || ctx->n == 0) return fail(ctx, CPF_ERR_INVALID, "cpf_set_tets: no particles");
+    if (ctx->permuted) return fail(ctx, CPF_ERR_INVALID, "cpf_set_tets after a sort is not supported");
+    cudaSetDevice(ctx->device);
+    CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tet[ctx->pcur], tet, sizeof(int) * (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->have_tets = true;
+    return CPF_OK;
+}
+
+int cpf_locate_initial(cpf_context *ctx)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return locate_particles(ctx);
+}
+
+int cpf_init_rng(cpf_context *ctx)
+{
+    if (!ctx || ctx->n == 0) return fail(ctx, CPF_ERR_INVALID, "cpf_init_rng: no particles");
+    cudaSetDevice(ctx->device);
+    return launch_init_rng(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------
+// hot path
+// ---------------------------------------------------------------------------------------------
+int cpf_substeps(cpf_context *ctx, int n, double dt)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    if (!ctx->have_mesh || !ctx->have_tets) return fail(ctx, CPF_ERR_INVALID, "cpf_substeps: mesh and located particles are required");
+    if (ctx->cfg.integrator != CPF_EULER || ctx->cfg.interp != CPF_INTERP_TET)
+        return fail(ctx, CPF_ERR_INVALID, "integrator/interp combination not available in this build");
+    cudaSetDevice(ctx->device);
+    CPF_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    const int fuse = ctx->cfg.fuse_substeps > 0 ? ctx->cfg.fuse_substeps : 1;
+    int done = 0;
+    while (done < n) {
+        if (ctx->cfg.sort_interval > 0 && ctx->since_sort >= ctx->cfg.sort_interval) {
+            int rc = sort_particles_by_cell(ctx);
+            if (rc) return rc;
+        }
+        int k = std::min(fuse, n - done);
+        if (ctx->cfg.sort_interval > 0) k = std::min(k, std::max(1, ctx->cfg.sort_interval - ctx->since_sort));
+        int rc = launch_substeps(ctx, k, dt, done + k == n);
+        if (rc) return rc;
+        done += k;
+        ctx->since_sort += k;
+    }
+    CPF_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    return CPF_OK;
+}
+
+int cpf_advect(cpf_context *ctx, double deltaT, int *nCyclesOut)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    // src/advect.H:36-37
+    int nCycles = (int)std::max(std::ceil(deltaT / ctx->cfg.dt), 1.0);
+    const double cycleDt = deltaT / nCycles;
+    if (nCyclesOut) *nCyclesOut = nCycles;
+    return cpf_substeps(ctx, nCycles, cycleDt);
+}
+
+int cpf_initial_advect(cpf_context *ctx)
+{
+    if (!ctx || !ctx->have_mesh || !ctx->have_tets) return fail(ctx, CPF_ERR_INVALID, "cpf_initial_advect: mesh and located particles are required");
+    cudaSetDevice(ctx->device);
+    return launch_initial_advect(ctx, ctx->cfg.dt);
+}
+
+int cpf_sort_particles(cpf_context *ctx)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return sort_particles_by_cell(ctx);
+}
+
+int cpf_last_step_ms(cpf_context *ctx, float *ms)
+{
+    if (!ctx || !ms) return CPF_ERR_INVALID;
+    CPF_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    CPF_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return CPF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// results
+// ---------------------------------------------------------------------------------------------
+int cpf_download(cpf_context *ctx, double *xyzw, double *vel, int *tet)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    if (ctx->n == 0) return CPF_OK;
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)ctx->n;
+    const int a = ctx->pcur;
+    if (!ctx->permuted) {
+        if (xyzw) CPF_CUDA(ctx, cudaMemcpyAsync(xyzw, ctx->d_pos[a], sizeof(double4) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (vel) CPF_CUDA(ctx, cudaMemcpyAsync(vel, ctx->d_vel[a], sizeof(double4) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (tet) CPF_CUDA(ctx, cudaMemcpyAsync(tet, ctx->d_tet[a], sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        int rc = ensure_scratch(ctx, n * (2 * sizeof(double4) + sizeof(int)));
+        if (rc) return rc;
+        double4 *dp = (double4 *)ctx->d_scratch, *dv = dp + n;
+        int *dt = (int *)(dv + n);
+        rc = gather_original_order(ctx, xyzw ? dp : nullptr, vel ? dv : nullptr, tet ? dt : nullptr);
+        if (rc) return rc;
+        if (xyzw) CPF_CUDA(ctx, cudaMemcpyAsync(xyzw, dp, sizeof(double4) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (vel) CPF_CUDA(ctx, cudaMemcpyAsync(vel, dv, sizeof(double4) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (tet) CPF_CUDA(ctx, cudaMemcpyAsync(tet, dt, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CPF_OK;
+}
+
+int cpf_download_cells(cpf_context *ctx, int *cell)
+{
+    if (!ctx || !cell || !ctx->have_mesh) return fail(ctx, CPF_ERR_INVALID, "cpf_download_cells: bad arguments");
+    std::vector<int> tet((size_t)ctx->n);
+    int rc = cpf_download(ctx, nullptr, nullptr, tet.data());
+    if (rc) return rc;
+    std::vector<int> tv((size_t)ctx->nTets * 4), tc((size_t)ctx->nTets);
+    rc = cpf_mesh_download_tets(ctx, tv.data(), tc.data());
+    if (rc) return rc;
+    for (long long i = 0; i < ctx->n; ++i) cell[i] = tet[(size_t)i] >= 0 ? tc[(size_t)tet[(size_t)i]] : -1;
+    return CPF_OK;
+}
+
+int cpf_stats_get(cpf_context *ctx, cpf_stats *out)
+{
+    if (!ctx || !out) return CPF_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return reduce_stats(ctx, out);
+}
+
+long long cpf_num_particles(cpf_context *ctx) { return ctx ? ctx->n : 0; }
+
+int cpf_device_pointers(cpf_context *ctx, void **pos4, void **tet, void **ucell)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    if (pos4) *pos4 = ctx->d_pos[ctx->pcur];
+    if (tet) *tet = ctx->d_tet[ctx->pcur];
+    if (ucell) *ucell = ctx->d_ucell[ctx->ucur];
+    return CPF_OK;
+}
+
+int cpf_debug_next_normals(cpf_context *ctx, double *xi)
+{
+    if (!ctx || !xi || ctx->n == 0) return fail(ctx, CPF_ERR_INVALID, "cpf_debug_next_normals: bad arguments");
+    cudaSetDevice(ctx->device);
+    double *d = nullptr;
+    CPF_CUDA(ctx, cudaMalloc(&d, sizeof(double) * 3 * (size_t)ctx->n));
+    int rc = launch_debug_normals(ctx, d);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(xi, d, sizeof(double) * 3 * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, CPF_ERR_CUDA, "download of normals failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
+long long cpf_launch_count(cpf_context *ctx) { return ctx ? ctx->launches : 0; }
+
+// writeParticles2VTU (cuda/utils.cpp:144-283): same file name, arrays and ASCII layout so existing
+// ParaView states keep working.  ParticleTetID carries the barycentric-mode id array of the
+// reference (unused in the default build, Appendix A.9) -- both arrays hold the current tet here.
+int cpf_write_vtu(cpf_context *ctx, const char *dir, unsigned step)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    const long long n = ctx->n;
+    std::vector<double> p((size_t)n * 4), v((size_t)n * 4);
+    std::vector<int> tet((size_t)n);
+    int rc = cpf_download(ctx, p.data(), v.data(), tet.data());
+    if (rc) return rc;
+    char name[1200];
+    snprintf(name, sizeof name, "%s%sparticle_%04u.vtu", dir ? dir : "", (dir && *dir) ? "/" : "", step);
+    FILE *fp = fopen(name, "w");
+    if (!fp) return fail(ctx, CPF_ERR_INVALID, "cannot open %s", name);
+    fprintf(fp, "<VTKFile type='UnstructuredGrid' version='1.0' byte_order='LittleEndian' header_type='UInt64'>\n<UnstructuredGrid>\n");
+    fprintf(fp, "<Piece NumberOfCells='%lld' NumberOfPoints='%lld'>\n<Points>\n", n, n);
+    fprintf(fp, "<DataArray NumberOfComponents='3' type='Float64' Name='Position' format='ascii'>\n");
+    for (long long i = 0; i < n; ++i) fprintf(fp, "%.15lf %.15lf %.15lf\n", p[4 * i], p[4 * i + 1], p[4 * i + 2]);
+    fprintf(fp, "</DataArray>\n</Points>\n<PointData>\n");
+    fprintf(fp, "<DataArray NumberOfComponents='1' type='Int32' Name='ParticleType' format='ascii'>\n");
+    for (long long i = 0; i < n; ++i) fprintf(fp, "%d\n", (int)p[4 * i + 3]);
+    fprintf(fp, "</DataArray>\n<DataArray NumberOfComponents='1' type='Int32' Name='ParticleID' format='ascii'>\n");
+    for (long long i = 0; i < n; ++i) fprintf(fp, "%lld\n", i);
+    fprintf(fp, "</DataArray>\n<DataArray NumberOfComponents='1' type='Int32' Name='ParticleTetID' format='ascii'>\n");
+    for (long long i = 0; i < n; ++i) fprintf(fp, "%d\n", tet[(size_t)i]);
+    fprintf(fp, "</DataArray>\n<DataArray NumberOfComponents='1' type='Int32' Name='ConvexTetID' format='ascii'>\n");
+    for (long long i = 0; i < n; ++i) fprintf(fp, "%d\n", tet[(size_t)i]);
+    fprintf(fp, "</DataArray>\n<DataArray NumberOfComponents='3' type='Float32' Name='vels' format='ascii'>\n");
+    double totalKE = 0.0;
+    for (long long i = 0; i < n; ++i) {
+        if (std::isnan(v[4 * i])) fprintf(fp, "%lf %lf %lf\n", 0.0, 0.0, 0.0);
+        else fprintf(fp, "%lf %lf %lf\n", v[4 * i], v[4 * i + 1], v[4 * i + 2]);
+    }
+    fprintf(fp, "</DataArray>\n<DataArray NumberOfComponents='1' type='Float32' Name='KEs' format='ascii'>\n");
+    for (long long i = 0; i < n; ++i) {
+        const double ke = 0.5 * (v[4 * i] * v[4 * i] + v[4 * i + 1] * v[4 * i + 1] + v[4 * i + 2] * v[4 * i + 2]);
+        fprintf(fp, "%lf\n", ke);
+        totalKE += ke;
+    }
+    fprintf(fp, "</DataArray>\n</PointData>\n<Cells>\n<DataArray type='Int32' Name='connectivity' format='ascii'>\n");
+    for (long long i = 0; i < n; ++i) fprintf(fp, "%lld\n", i);
+    fprintf(fp, "</DataArray>\n<DataArray type='Int32' Name='offsets' format='ascii'>\n");
+    for (long long i = 0; i < n; ++i) fprintf(fp, "%lld\n", i + 1);
+    fprintf(fp, "</DataArray>\n<DataArray type='UInt8' Name='types' format='ascii'>\n");
+    for (long long i = 0; i < n; ++i) fprintf(fp, "1\n");
+    fprintf(fp, "</DataArray>\n</Cells>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+    fclose(fp);
+    printf("#adv: System Kinetic Energy=%lf\n", totalKE);
+    return CPF_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,130 @@
+// cpf_internal.h -- shared declarations of libcpf's translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cpf.h"
+#include "cpf_geom.cuh"
+
+namespace cpf {
+
+enum Counter { CNT_ESCAPED = 0, CNT_REFLECT, CNT_EXACT, CNT_HOPS, CNT_SUBSTEPS, CNT_LOST, CNT_COUNT = 8 };
+
+struct ParticleView {
+    double4 *pos;        // [n] x,y,z,w (w != 0 => active), reference layout (cuda/common.h:26)
+    int *tet;            // [n]
+    int *pid;            // [n] original particle index (identity until the first sort)
+    double4 *vel;        // [n] vx,vy,vz,-1 (written on the last fused sub-step when requested)
+    curandState_t *rng;  // [n] XORWOW states (CPF_RNG_XORWOW)
+    long long n;
+};
+
+struct StepParams {
+    int nSub;
+    double dt;
+    double randDisp;     // sqrt(2*D*dt), cuda/particles.cu:564
+    int reflect;
+    int writeVel;
+    unsigned long long seed;
+    unsigned long long step0; // global sub-step index of the first fused sub-step (Philox counter)
+    unsigned long long *counters;
+};
+
+// BVH over tets for initial / lost-particle location (cpf_locate.cu)
+struct BvhLevel { float4 *lo; float4 *hi; long long n; };
+
+} // namespace cpf
+
+struct cpf_context {
+    cpf_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evCopy = nullptr;
+    std::string err;
+    float last_ms = 0.f;
+    long long launches = 0;
+
+    // mesh
+    bool have_mesh = false;
+    long long nVerts = 0, nTets = 0, nCells = 0, nBoundaryFaces = 0;
+    int nPoints = 0, nPatches = 0;
+    bool cellFromVertex = false;
+    double4 *d_vpos = nullptr;
+    int4 *d_tetv = nullptr;      // sorted ids
+    int4 *d_tetl = nullptr;      // links
+    uint16_t *d_tetcode = nullptr;
+    int *d_tetcell = nullptr;
+    double *d_ucell[2] = { nullptr, nullptr }; // double-buffered cell field, solver layout [nCells][3]
+    int ucur = 0;
+    double *d_uvert = nullptr;
+    uint8_t *d_patch_kind = nullptr;
+    double guard = 1e-7, hmin = 0.0;
+    double bbox_lo[3] = { 0, 0, 0 }, bbox_hi[3] = { 0, 0, 0 };
+    double *h_pinned = nullptr;
+    size_t pinned_bytes = 0;
+
+    // BVH (sorted tet order + 8-ary implicit tree of float boxes)
+    int *d_bvh_tet = nullptr;                 // [nTets] tet ids in Morton order
+    std::vector<cpf::BvhLevel> bvh;           // level 0 = groups of 8 tets
+    float4 *d_bvh_top_lo = nullptr, *d_bvh_top_hi = nullptr; // concatenated top levels (staged in smem)
+    int bvh_top_first_level = 0, bvh_top_nodes = 0;
+    std::vector<int> bvh_top_offsets;
+
+    // particles (double-buffered for sort-by-cell)
+    long long n = 0;
+    double4 *d_pos[2] = { nullptr, nullptr };
+    int *d_tet[2] = { nullptr, nullptr };
+    int *d_pid[2] = { nullptr, nullptr };
+    double4 *d_vel[2] = { nullptr, nullptr };
+    curandState_t *d_rng[2] = { nullptr, nullptr };
+    int pcur = 0;
+    bool permuted = false;
+    bool rng_ready = false;
+    bool have_tets = false;
+    unsigned long long step_index = 0; // global sub-step counter
+    int since_sort = 0;
+    int *d_sort_hist = nullptr;
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+
+    unsigned long long *d_counters = nullptr;
+};
+
+namespace cpf {
+
+int fail(cpf_context *ctx, int code, const char *fmt, ...);
+#define CPF_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return cpf::fail(ctx, CPF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                                    \
+    } while (0)
+
+MeshView mesh_view(const cpf_context *ctx);
+ParticleView particle_view(const cpf_context *ctx);
+int ensure_scratch(cpf_context *ctx, size_t bytes);
+
+// cpf_mesh.cu
+int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, long long nTets, const int *tetVerts,
+                      const int *tetCell, const int *tetPatch, long long nCells, int nPoints, bool cellFromVertex);
+// cpf_locate.cu
+int build_bvh(cpf_context *ctx);
+void free_bvh(cpf_context *ctx);
+int locate_particles(cpf_context *ctx);
+// cpf_advect.cu
+int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel);
+int launch_initial_advect(cpf_context *ctx, double dt);
+int launch_debug_normals(cpf_context *ctx, double *d_xi);
+int launch_init_rng(cpf_context *ctx);
+// cpf_sort.cu
+int sort_particles_by_cell(cpf_context *ctx);
+int gather_original_order(cpf_context *ctx, double4 *d_pos_out, double4 *d_vel_out, int *d_tet_out);
+int reduce_stats(cpf_context *ctx, cpf_stats *out);
+
+} // namespace cpf

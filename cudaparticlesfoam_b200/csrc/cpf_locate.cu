@@ -1,0 +1,254 @@
+// cpf_locate.cu -- initial / lost-particle point location with a hand-written BVH.
+//
+// Replaces the reference's init-time seeding: OptiX shared-face triangle BVH + fp32 ray cast
+// (third_party/RTXAdvect/optix/OptixTetQuery.cpp:53-108,143-271, optix/optixQueryKernel.cu:63-124)
+// followed by the fp64 narrow phase baryQuery (query/RTQuery.cu:189-218, 295-310).
+//
+// Structure: tets sorted along a 63-bit Morton curve of their centroids; an implicit 8-ary tree of
+// float boxes (rounded outward) over that order, level 0 = groups of 8 tets.  The top levels
+// (<= 2048-node level and everything above it) are staged in shared memory by every CTA; the lower
+// levels and the candidate tets come through L2.  A particle is assigned the LOWEST tet id whose
+// four reference barycentric coordinates (cuda/DeviceTetMesh.cuh:108-156) are all >= 0 -- the same
+// answer as a brute-force scan, independent of traversal order; from a containing tet the
+// reference's narrow phase returns immediately, so no further walk is needed.
+#include <cub/cub.cuh>
+
+#include "cpf_internal.h"
+
+namespace cpf {
+
+CPF_DEV unsigned long long spread21(unsigned long long x)
+{
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(long long nTets, const int4 *__restrict__ tetv, const double4 *__restrict__ vpos, double3 lo,
+                         double3 inv, unsigned long long *__restrict__ keys, int *__restrict__ ids)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTets) return;
+    const int4 v = tetv[t];
+    const D3 a = ld_vertex(vpos, v.x), b = ld_vertex(vpos, v.y), c = ld_vertex(vpos, v.z), d = ld_vertex(vpos, v.w);
+    const double cx = 0.25 * (a.x + b.x + c.x + d.x), cy = 0.25 * (a.y + b.y + c.y + d.y), cz = 0.25 * (a.z + b.z + c.z + d.z);
+    const double s = 2097151.0;
+    const unsigned long long ix = (unsigned long long)fmin(fmax((cx - lo.x) * inv.x * s, 0.0), s);
+    const unsigned long long iy = (unsigned long long)fmin(fmax((cy - lo.y) * inv.y * s, 0.0), s);
+    const unsigned long long iz = (unsigned long long)fmin(fmax((cz - lo.z) * inv.z * s, 0.0), s);
+    keys[t] = spread21(ix) | (spread21(iy) << 1) | (spread21(iz) << 2);
+    ids[t] = (int)t;
+}
+
+__global__ void k_bvh_leaves(long long nGroups, long long nTets, const int *__restrict__ order, const int4 *__restrict__ tetv,
+                             const double4 *__restrict__ vpos, float4 *__restrict__ blo, float4 *__restrict__ bhi)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nGroups) return;
+    double lx = 1e300, ly = 1e300, lz = 1e300, hx = -1e300, hy = -1e300, hz = -1e300;
+    for (int q = 0; q < 8; ++q) {
+        const long long i = 8 * g + q;
+        if (i >= nTets) break;
+        const int4 v = tetv[order[i]];
+        const int ids[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const D3 p = ld_vertex(vpos, ids[k]);
+            lx = fmin(lx, p.x); ly = fmin(ly, p.y); lz = fmin(lz, p.z);
+            hx = fmax(hx, p.x); hy = fmax(hy, p.y); hz = fmax(hz, p.z);
+        }
+    }
+    blo[g] = make_float4(__double2float_rd(lx), __double2float_rd(ly), __double2float_rd(lz), 0.f);
+    bhi[g] = make_float4(__double2float_ru(hx), __double2float_ru(hy), __double2float_ru(hz), 0.f);
+}
+
+__global__ void k_bvh_up(long long nParents, long long nChildren, const float4 *__restrict__ clo, const float4 *__restrict__ chi,
+                         float4 *__restrict__ plo, float4 *__restrict__ phi)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nParents) return;
+    float4 lo = make_float4(3e38f, 3e38f, 3e38f, 0.f), hi = make_float4(-3e38f, -3e38f, -3e38f, 0.f);
+    for (int q = 0; q < 8; ++q) {
+        const long long i = 8 * g + q;
+        if (i >= nChildren) break;
+        const float4 a = clo[i], b = chi[i];
+        lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
+        hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
+    }
+    plo[g] = lo; phi[g] = hi;
+}
+
+#define CPF_BVH_MAX_LEVELS 12
+struct BvhView {
+    const float4 *lo[CPF_BVH_MAX_LEVELS];
+    const float4 *hi[CPF_BVH_MAX_LEVELS];
+    long long n[CPF_BVH_MAX_LEVELS];
+    int nLevels;
+    int topFirst;                       // first level staged in shared memory
+    int topOffset[CPF_BVH_MAX_LEVELS];  // offset of each staged level in the smem arrays
+    int topNodes;
+    const float4 *topLo, *topHi;
+    const int *order;
+    long long nTets;
+};
+
+CPF_DEV bool in_box(const float4 lo, const float4 hi, D3 P)
+{
+    return P.x >= (double)lo.x && P.x <= (double)hi.x && P.y >= (double)lo.y && P.y <= (double)hi.y && P.z >= (double)lo.z &&
+           P.z <= (double)hi.z;
+}
+
+__global__ void __launch_bounds__(128) k_locate(const MeshView m, const BvhView bv, const ParticleView pv)
+{
+    extern __shared__ float4 smem[];
+    float4 *sLo = smem, *sHi = smem + bv.topNodes;
+    for (int q = threadIdx.x; q < bv.topNodes; q += blockDim.x) { sLo[q] = bv.topLo[q]; sHi[q] = bv.topHi[q]; }
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pv.n) return;
+    const double4 p4 = pv.pos[i];
+    if (p4.w == 0.0) { pv.tet[i] = -1; return; }
+    const D3 P{ p4.x, p4.y, p4.z };
+    int best = 0x7fffffff;
+    int stack[72];
+    int sp = 0;
+    const int root = bv.nLevels - 1;
+    stack[sp++] = (root << 26) | 0;
+    while (sp > 0) {
+        const int e = stack[--sp];
+        const int L = e >> 26;
+        const long long g = e & 0x3ffffff;
+        float4 lo, hi;
+        if (L >= bv.topFirst) { lo = sLo[bv.topOffset[L] + g]; hi = sHi[bv.topOffset[L] + g]; }
+        else { lo = __ldg(bv.lo[L] + g); hi = __ldg(bv.hi[L] + g); }
+        if (!in_box(lo, hi, P)) continue;
+        if (L > 0) {
+            const long long nc = bv.n[L - 1];
+            for (int q = 7; q >= 0; --q) {
+                const long long c = 8 * g + q;
+                if (c < nc && sp < 72) stack[sp++] = ((L - 1) << 26) | (int)c;
+            }
+        } else {
+            for (int q = 0; q < 8; ++q) {
+                const long long k = 8 * g + q;
+                if (k >= bv.nTets) break;
+                const int t = __ldg(bv.order + k);
+                if (t >= best) continue;
+                int4 v;
+                const Tet T = load_tet(m, t, v);
+                // cheap reject on the tet's own box before the exact test
+                const double lx = fmin(fmin(T.P[0].x, T.P[1].x), fmin(T.P[2].x, T.P[3].x)), hx = fmax(fmax(T.P[0].x, T.P[1].x), fmax(T.P[2].x, T.P[3].x));
+                if (P.x < lx || P.x > hx) continue;
+                const double ly = fmin(fmin(T.P[0].y, T.P[1].y), fmin(T.P[2].y, T.P[3].y)), hy = fmax(fmax(T.P[0].y, T.P[1].y), fmax(T.P[2].y, T.P[3].y));
+                if (P.y < ly || P.y > hy) continue;
+                const double lz = fmin(fmin(T.P[0].z, T.P[1].z), fmin(T.P[2].z, T.P[3].z)), hz = fmax(fmax(T.P[0].z, T.P[1].z), fmax(T.P[2].z, T.P[3].z));
+                if (P.z < lz || P.z > hz) continue;
+                double w[4];
+                bary_exact(T, P, w);
+                if (w[0] >= 0.0 && w[1] >= 0.0 && w[2] >= 0.0 && w[3] >= 0.0) best = t;
+            }
+        }
+    }
+    pv.tet[i] = (best == 0x7fffffff) ? -1 : best;
+}
+
+void free_bvh(cpf_context *ctx)
+{
+    cudaFree(ctx->d_bvh_tet); ctx->d_bvh_tet = nullptr;
+    for (auto &l : ctx->bvh) { cudaFree(l.lo); cudaFree(l.hi); }
+    ctx->bvh.clear();
+    cudaFree(ctx->d_bvh_top_lo); cudaFree(ctx->d_bvh_top_hi);
+    ctx->d_bvh_top_lo = ctx->d_bvh_top_hi = nullptr;
+    ctx->bvh_top_offsets.clear();
+}
+
+int build_bvh(cpf_context *ctx)
+{
+    free_bvh(ctx);
+    cudaStream_t st = ctx->stream;
+    const long long nT = ctx->nTets;
+    unsigned long long *d_k = nullptr, *d_k2 = nullptr;
+    int *d_id = nullptr;
+    CPF_CUDA(ctx, cudaMalloc(&d_k, sizeof(unsigned long long) * (size_t)nT));
+    CPF_CUDA(ctx, cudaMalloc(&d_k2, sizeof(unsigned long long) * (size_t)nT));
+    CPF_CUDA(ctx, cudaMalloc(&d_id, sizeof(int) * (size_t)nT));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_bvh_tet, sizeof(int) * (size_t)nT));
+    double3 lo = make_double3(ctx->bbox_lo[0], ctx->bbox_lo[1], ctx->bbox_lo[2]);
+    double3 inv;
+    inv.x = 1.0 / fmax(ctx->bbox_hi[0] - ctx->bbox_lo[0], 1e-300);
+    inv.y = 1.0 / fmax(ctx->bbox_hi[1] - ctx->bbox_lo[1], 1e-300);
+    inv.z = 1.0 / fmax(ctx->bbox_hi[2] - ctx->bbox_lo[2], 1e-300);
+    k_morton<<<(unsigned)((nT + 255) / 256), 256, 0, st>>>(nT, ctx->d_tetv, ctx->d_vpos, lo, inv, d_k, d_id);
+    size_t tmpBytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, d_k, d_k2, d_id, ctx->d_bvh_tet, nT, 0, 63, st);
+    void *d_tmp = nullptr;
+    CPF_CUDA(ctx, cudaMalloc(&d_tmp, tmpBytes));
+    CPF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k, d_k2, d_id, ctx->d_bvh_tet, nT, 0, 63, st));
+    ctx->launches += 5;
+
+    long long n = (nT + 7) / 8;
+    BvhLevel L0{ nullptr, nullptr, n };
+    CPF_CUDA(ctx, cudaMalloc(&L0.lo, sizeof(float4) * (size_t)n));
+    CPF_CUDA(ctx, cudaMalloc(&L0.hi, sizeof(float4) * (size_t)n));
+    k_bvh_leaves<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, nT, ctx->d_bvh_tet, ctx->d_tetv, ctx->d_vpos, L0.lo, L0.hi);
+    ctx->launches++;
+    ctx->bvh.push_back(L0);
+    while (n > 1) {
+        const long long np = (n + 7) / 8;
+        BvhLevel L{ nullptr, nullptr, np };
+        CPF_CUDA(ctx, cudaMalloc(&L.lo, sizeof(float4) * (size_t)np));
+        CPF_CUDA(ctx, cudaMalloc(&L.hi, sizeof(float4) * (size_t)np));
+        const BvhLevel &c = ctx->bvh.back();
+        k_bvh_up<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(np, n, c.lo, c.hi, L.lo, L.hi);
+        ctx->launches++;
+        ctx->bvh.push_back(L);
+        n = np;
+    }
+    if ((int)ctx->bvh.size() > CPF_BVH_MAX_LEVELS) return fail(ctx, CPF_ERR_INVALID, "BVH too deep");
+    // top levels (first level with <= 2048 nodes and everything above) -> one contiguous array
+    int first = 0;
+    while (first < (int)ctx->bvh.size() - 1 && ctx->bvh[first].n > 2048) ++first;
+    ctx->bvh_top_first_level = first;
+    ctx->bvh_top_offsets.assign(ctx->bvh.size(), 0);
+    int total = 0;
+    for (int l = first; l < (int)ctx->bvh.size(); ++l) { ctx->bvh_top_offsets[l] = total; total += (int)ctx->bvh[l].n; }
+    ctx->bvh_top_nodes = total;
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_bvh_top_lo, sizeof(float4) * (size_t)total));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_bvh_top_hi, sizeof(float4) * (size_t)total));
+    for (int l = first; l < (int)ctx->bvh.size(); ++l) {
+        CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_bvh_top_lo + ctx->bvh_top_offsets[l], ctx->bvh[l].lo, sizeof(float4) * (size_t)ctx->bvh[l].n,
+                                      cudaMemcpyDeviceToDevice, st));
+        CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_bvh_top_hi + ctx->bvh_top_offsets[l], ctx->bvh[l].hi, sizeof(float4) * (size_t)ctx->bvh[l].n,
+                                      cudaMemcpyDeviceToDevice, st));
+    }
+    CPF_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(d_k); cudaFree(d_k2); cudaFree(d_id); cudaFree(d_tmp);
+    return CPF_OK;
+}
+
+int locate_particles(cpf_context *ctx)
+{
+    if (!ctx->have_mesh) return fail(ctx, CPF_ERR_INVALID, "no mesh uploaded");
+    if (ctx->n == 0) return CPF_OK;
+    BvhView bv{};
+    bv.nLevels = (int)ctx->bvh.size();
+    for (int l = 0; l < bv.nLevels; ++l) { bv.lo[l] = ctx->bvh[l].lo; bv.hi[l] = ctx->bvh[l].hi; bv.n[l] = ctx->bvh[l].n; bv.topOffset[l] = ctx->bvh_top_offsets[l]; }
+    bv.topFirst = ctx->bvh_top_first_level;
+    bv.topNodes = ctx->bvh_top_nodes;
+    bv.topLo = ctx->d_bvh_top_lo; bv.topHi = ctx->d_bvh_top_hi;
+    bv.order = ctx->d_bvh_tet;
+    bv.nTets = ctx->nTets;
+    const size_t smem = sizeof(float4) * 2 * (size_t)bv.topNodes;
+    CPF_CUDA(ctx, cudaFuncSetAttribute(k_locate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_locate<<<(unsigned)((ctx->n + 127) / 128), 128, smem, ctx->stream>>>(mesh_view(ctx), bv, particle_view(ctx));
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+    ctx->have_tets = true;
+    return CPF_OK;
+}
+
+} // namespace cpf

@@ -1,0 +1,290 @@
+// cpf_mesh.cu -- device mesh builder.
+//
+// Replaces, for the hot path, the reference's host-side mesh preparation:
+//   * tet decomposition in the glue            /root/reference/src/initCuda.H:86-110
+//   * HostTetMesh::getBoundaryMesh/add1Facet   third_party/RTXAdvect/cuda/HostTetMesh.h:265-430
+//     (std::map with a 3x20-bit key: minutes and GBs at 1M cells, wrong past 2^20 vertices)
+//   * DeviceTetMesh::upload                    third_party/RTXAdvect/cuda/DeviceTetMesh.cuh:59-72
+// Here the face topology is built ON THE DEVICE: every tet emits its four ascending vertex
+// triples, one 64-bit radix sort on the two smallest ids groups candidate partners, and a
+// neighbourhood scan matches the third id.  The result is a 32+2 byte tet record
+// (sorted vertex ids, neighbour links, orientation code) instead of the reference's
+// tetfacets -> facets -> positions -> faceinfos four-level gather (400 B per visited tet).
+#include <cub/cub.cuh>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "cpf_internal.h"
+
+namespace cpf {
+
+enum MeshFlag { MF_REPEATED_VERTEX = 1, MF_BAD_VOLUME = 2, MF_ZERO_DET = 4, MF_NONMANIFOLD = 8, MF_ORIENTATION = 16, MF_OPEN_FACE = 32 };
+
+struct FaceEntry { int c; int tf; }; // third vertex id, (tet<<2 | sorted face slot)
+
+// One thread per tet: validate, sort the vertex ids, derive perm/flip code, emit 4 face keys.
+__global__ void k_prepare_tets(long long nTets, const int4 *__restrict__ tetref, const double4 *__restrict__ vpos,
+                               int4 *__restrict__ tetv, uint16_t *__restrict__ tetcode, unsigned long long *__restrict__ keys,
+                               int *__restrict__ entryIdx, FaceEntry *__restrict__ entries, unsigned *__restrict__ flags,
+                               unsigned long long *__restrict__ hminBits, int bits)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTets) return;
+    const int4 r = tetref[t];
+    int id[4] = { r.x, r.y, r.z, r.w };
+    unsigned f = 0;
+    if (id[0] == id[1] || id[0] == id[2] || id[0] == id[3] || id[1] == id[2] || id[1] == id[3] || id[2] == id[3]) f |= MF_REPEATED_VERTEX;
+    const D3 A = ld_vertex(vpos, id[0]), B = ld_vertex(vpos, id[1]), C = ld_vertex(vpos, id[2]), D = ld_vertex(vpos, id[3]);
+    // HostTetMesh.h:334-343 volume sign test: double arithmetic without contraction, narrowed to float
+    {
+        const D3 e1 = xsub(B, A), e2 = xsub(C, A), e3 = xsub(D, A);
+        const double cx = __dsub_rn(__dmul_rn(e1.y, e2.z), __dmul_rn(e2.y, e1.z));
+        const double cy = __dsub_rn(__dmul_rn(e1.z, e2.x), __dmul_rn(e2.z, e1.x));
+        const double cz = __dsub_rn(__dmul_rn(e1.x, e2.y), __dmul_rn(e2.x, e1.y));
+        const float vol = (float)__dadd_rn(__dadd_rn(__dmul_rn(e3.x, cx), __dmul_rn(e3.y, cy)), __dmul_rn(e3.z, cz));
+        if (!(vol > 0.f)) f |= MF_BAD_VOLUME; // zero (dropped by the reference) or inverted (swapped by it)
+    }
+    const double det = xdet(A, B, C, D); // particles.cu:348 den == 0 -> particle frozen
+    if (det == 0.0) f |= MF_ZERO_DET;
+    // rank of each reference vertex among the four ids
+    int rank[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int rk = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rk += (id[q] < id[k]) ? 1 : 0;
+        rank[k] = rk;
+    }
+    int s[4] = { 0, 0, 0, 0 };
+    unsigned code = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!(f & MF_REPEATED_VERTEX)) s[rank[k]] = id[k];
+        code |= (unsigned)rank[k] << (2 * k);
+    }
+    // Gmsh face order of the reference (HostTetMesh.h:351-358): face k is opposite vertex k.
+    // `front` = parity of the sort of (v0,v1,v2) as add1Facet performs it (:272-275);
+    // the reference negates the normal when this tet is the face's `back`, i.e. when !front.
+    const int fk[4][3] = { { 1, 2, 3 }, { 2, 0, 3 }, { 0, 1, 3 }, { 0, 2, 1 } };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int a = id[fk[k][0]], b = id[fk[k][1]], c = id[fk[k][2]];
+        int front = 0;
+        if (a > c) { int x = a; a = c; c = x; front ^= 1; }
+        if (b > c) { int x = b; b = c; c = x; front ^= 1; }
+        if (a > b) { int x = a; a = b; b = x; front ^= 1; }
+        const int j = rank[k];
+        if (!front) code |= 1u << (8 + j);
+        const long long e = 4 * t + j;
+        keys[e] = ((unsigned long long)(unsigned)a << bits) | (unsigned)b;
+        entryIdx[e] = (int)e;
+        entries[e] = FaceEntry{ c, (int)((t << 2) | j) };
+    }
+    tetv[t] = make_int4(s[0], s[1], s[2], s[3]);
+    tetcode[t] = (uint16_t)code;
+    if (f) atomicOr(flags, f);
+    else {
+        // smallest height = |det| / (largest face normal length): feeds the filter's guard band
+        const D3 n0 = xcross(xsub(C, B), xsub(D, B)), n1 = xcross(xsub(C, A), xsub(D, A)), n2 = xcross(xsub(B, A), xsub(D, A)),
+                 n3 = xcross(xsub(B, A), xsub(C, A));
+        const double m = fmax(fmax(xdot(n0, n0), xdot(n1, n1)), fmax(xdot(n2, n2), xdot(n3, n3)));
+        const double h = fabs(det) / sqrt(m);
+        atomicMin(hminBits, (unsigned long long)__double_as_longlong(h));
+    }
+}
+
+// One thread per sorted face entry: find the other tet with the same (a,b,c).
+__global__ void k_link_faces(long long nEntries, const unsigned long long *__restrict__ keys, const int *__restrict__ order,
+                             const FaceEntry *__restrict__ entries, const uint16_t *__restrict__ tetcode,
+                             const int *__restrict__ tetPatch, int *__restrict__ links, unsigned *__restrict__ flags,
+                             unsigned long long *__restrict__ nBoundary)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nEntries) return;
+    const unsigned long long key = keys[i];
+    const FaceEntry me = entries[order[i]];
+    int partner = -1, count = 0;
+    for (long long q = i - 1; q >= 0 && keys[q] == key; --q) {
+        const FaceEntry o = entries[order[q]];
+        if (o.c == me.c) { partner = o.tf; count++; }
+    }
+    for (long long q = i + 1; q < nEntries && keys[q] == key; ++q) {
+        const FaceEntry o = entries[order[q]];
+        if (o.c == me.c) { partner = o.tf; count++; }
+    }
+    const int t = me.tf >> 2, j = me.tf & 3;
+    const unsigned code = tetcode[t];
+    int link;
+    if (count == 0) {
+        int patch = 0;
+        if (tetPatch) {
+            // only the face opposite reference vertex 0 (the cell centre) can lie on a patch
+            if ((int)(code & 3u) == j && tetPatch[t] >= 0) patch = tetPatch[t];
+            else atomicOr(flags, (unsigned)MF_OPEN_FACE);
+        }
+        link = -(patch + 1);
+        atomicAdd(nBoundary, 1ull);
+    } else {
+        if (count > 1) atomicOr(flags, (unsigned)MF_NONMANIFOLD);
+        const unsigned ocode = tetcode[partner >> 2];
+        if (((code >> (8 + j)) & 1u) == ((ocode >> (8 + (partner & 3))) & 1u)) atomicOr(flags, (unsigned)MF_ORIENTATION);
+        link = partner;
+    }
+    links[4ll * t + j] = link;
+}
+
+__global__ void k_pack_positions(long long n, const double *__restrict__ xyz, double4 *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0);
+}
+
+int fail(cpf_context *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+static void free_mesh(cpf_context *ctx)
+{
+    cudaFree(ctx->d_vpos); cudaFree(ctx->d_tetv); cudaFree(ctx->d_tetl); cudaFree(ctx->d_tetcode); cudaFree(ctx->d_tetcell);
+    cudaFree(ctx->d_ucell[0]); cudaFree(ctx->d_ucell[1]); cudaFree(ctx->d_uvert); cudaFree(ctx->d_patch_kind);
+    ctx->d_vpos = nullptr; ctx->d_tetv = nullptr; ctx->d_tetl = nullptr; ctx->d_tetcode = nullptr; ctx->d_tetcell = nullptr;
+    ctx->d_ucell[0] = ctx->d_ucell[1] = nullptr; ctx->d_uvert = nullptr; ctx->d_patch_kind = nullptr;
+    free_bvh(ctx);
+    ctx->have_mesh = false;
+}
+
+int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, long long nTets, const int *tetVerts,
+                      const int *tetCell, const int *tetPatch, long long nCells, int nPoints, bool cellFromVertex)
+{
+    if (nVerts <= 0 || nTets <= 0 || nCells <= 0) return fail(ctx, CPF_ERR_INVALID, "empty mesh");
+    if (nTets >= (1ll << 29)) return fail(ctx, CPF_ERR_INVALID, "more than 2^29 tets per GPU are not supported");
+    free_mesh(ctx);
+    cudaStream_t st = ctx->stream;
+    ctx->nVerts = nVerts; ctx->nTets = nTets; ctx->nCells = nCells; ctx->nPoints = nPoints;
+    ctx->cellFromVertex = cellFromVertex;
+
+    // -- raw uploads (async from the caller's buffers; pageable memory falls back to staged copies)
+    double *d_xyz = nullptr;
+    int4 *d_tetref = nullptr;
+    int *d_tetPatch = nullptr;
+    CPF_CUDA(ctx, cudaMalloc(&d_xyz, sizeof(double) * 3 * (size_t)nVerts));
+    CPF_CUDA(ctx, cudaMalloc(&d_tetref, sizeof(int4) * (size_t)nTets));
+    CPF_CUDA(ctx, cudaMemcpyAsync(d_xyz, pos, sizeof(double) * 3 * (size_t)nVerts, cudaMemcpyHostToDevice, st));
+    CPF_CUDA(ctx, cudaMemcpyAsync(d_tetref, tetVerts, sizeof(int4) * (size_t)nTets, cudaMemcpyHostToDevice, st));
+    if (tetPatch) {
+        CPF_CUDA(ctx, cudaMalloc(&d_tetPatch, sizeof(int) * (size_t)nTets));
+        CPF_CUDA(ctx, cudaMemcpyAsync(d_tetPatch, tetPatch, sizeof(int) * (size_t)nTets, cudaMemcpyHostToDevice, st));
+    }
+    if (!cellFromVertex) {
+        CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetcell, sizeof(int) * (size_t)nTets));
+        if (tetCell) CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tetcell, tetCell, sizeof(int) * (size_t)nTets, cudaMemcpyHostToDevice, st));
+        else {
+            std::vector<int> iota((size_t)nTets);
+            for (long long t = 0; t < nTets; ++t) iota[(size_t)t] = (int)t;
+            CPF_CUDA(ctx, cudaMemcpy(ctx->d_tetcell, iota.data(), sizeof(int) * (size_t)nTets, cudaMemcpyHostToDevice));
+        }
+    }
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_vpos, sizeof(double4) * (size_t)nVerts));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetv, sizeof(int4) * (size_t)nTets));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetl, sizeof(int4) * (size_t)nTets));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetcode, sizeof(uint16_t) * (size_t)nTets));
+    for (int b = 0; b < 2; ++b) {
+        CPF_CUDA(ctx, cudaMalloc(&ctx->d_ucell[b], sizeof(double) * 3 * (size_t)nCells));
+        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_ucell[b], 0, sizeof(double) * 3 * (size_t)nCells, st));
+    }
+    ctx->ucur = 0;
+    k_pack_positions<<<(unsigned)((nVerts + 255) / 256), 256, 0, st>>>(nVerts, d_xyz, ctx->d_vpos);
+    ctx->launches++;
+
+    // -- per-tet preparation + face keys
+    const long long nE = 4 * nTets;
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr, *d_hmin = nullptr, *d_nb = nullptr;
+    int *d_idx = nullptr, *d_idx2 = nullptr;
+    FaceEntry *d_entries = nullptr;
+    unsigned *d_flags = nullptr;
+    CPF_CUDA(ctx, cudaMalloc(&d_keys, sizeof(unsigned long long) * (size_t)nE));
+    CPF_CUDA(ctx, cudaMalloc(&d_keys2, sizeof(unsigned long long) * (size_t)nE));
+    CPF_CUDA(ctx, cudaMalloc(&d_idx, sizeof(int) * (size_t)nE));
+    CPF_CUDA(ctx, cudaMalloc(&d_idx2, sizeof(int) * (size_t)nE));
+    CPF_CUDA(ctx, cudaMalloc(&d_entries, sizeof(FaceEntry) * (size_t)nE));
+    CPF_CUDA(ctx, cudaMalloc(&d_flags, sizeof(unsigned)));
+    CPF_CUDA(ctx, cudaMalloc(&d_hmin, sizeof(unsigned long long)));
+    CPF_CUDA(ctx, cudaMalloc(&d_nb, sizeof(unsigned long long)));
+    CPF_CUDA(ctx, cudaMemsetAsync(d_flags, 0, sizeof(unsigned), st));
+    CPF_CUDA(ctx, cudaMemsetAsync(d_nb, 0, sizeof(unsigned long long), st));
+    CPF_CUDA(ctx, cudaMemsetAsync(d_hmin, 0x7f, sizeof(unsigned long long), st)); // huge positive double
+    int bits = 1;
+    while ((1ll << bits) < nVerts) ++bits;
+    k_prepare_tets<<<(unsigned)((nTets + 127) / 128), 128, 0, st>>>(nTets, d_tetref, ctx->d_vpos, ctx->d_tetv, ctx->d_tetcode,
+                                                                   d_keys, d_idx, d_entries, d_flags, d_hmin, bits);
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+
+    // -- one radix sort on (smallest, second smallest) vertex id, 2*bits significant key bits
+    size_t tmpBytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, d_keys, d_keys2, d_idx, d_idx2, (long long)nE, 0, 2 * bits, st);
+    void *d_tmp = nullptr;
+    CPF_CUDA(ctx, cudaMalloc(&d_tmp, tmpBytes));
+    CPF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_keys, d_keys2, d_idx, d_idx2, (long long)nE, 0, 2 * bits, st));
+    ctx->launches += 4;
+
+    k_link_faces<<<(unsigned)((nE + 127) / 128), 128, 0, st>>>(nE, d_keys2, d_idx2, d_entries, ctx->d_tetcode, d_tetPatch,
+                                                              (int *)ctx->d_tetl, d_flags, d_nb);
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+
+    unsigned flags = 0;
+    unsigned long long hbits = 0, nb = 0;
+    CPF_CUDA(ctx, cudaMemcpyAsync(&flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost, st));
+    CPF_CUDA(ctx, cudaMemcpyAsync(&hbits, d_hmin, sizeof hbits, cudaMemcpyDeviceToHost, st));
+    CPF_CUDA(ctx, cudaMemcpyAsync(&nb, d_nb, sizeof nb, cudaMemcpyDeviceToHost, st));
+    CPF_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(d_xyz); cudaFree(d_tetref); cudaFree(d_tetPatch); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx);
+    cudaFree(d_idx2); cudaFree(d_entries); cudaFree(d_flags); cudaFree(d_hmin); cudaFree(d_nb); cudaFree(d_tmp);
+    if (flags) {
+        free_mesh(ctx);
+        return fail(ctx, CPF_ERR_MESH,
+                    "invalid tet mesh:%s%s%s%s%s%s", (flags & MF_REPEATED_VERTEX) ? " repeated vertex in a tet;" : "",
+                    (flags & MF_BAD_VOLUME) ? " zero or negative tet volume (orient tets so that det(A,B,C,D) > 0);" : "",
+                    (flags & MF_ZERO_DET) ? " degenerate tet (det == 0);" : "",
+                    (flags & MF_NONMANIFOLD) ? " face shared by more than two tets;" : "",
+                    (flags & MF_ORIENTATION) ? " inconsistent face orientation;" : "",
+                    (flags & MF_OPEN_FACE) ? " interior tet face without a neighbour;" : "");
+    }
+    double hmin;
+    memcpy(&hmin, &hbits, sizeof hmin);
+    ctx->hmin = hmin;
+    ctx->nBoundaryFaces = (long long)nb;
+    // guard band of the filtered path in barycentric units: at least 100x the reference's absolute
+    // 1e-13 tolerance measured against the smallest tet height, never below 1e-7
+    double g = 1e-11 / hmin;
+    ctx->guard = g > 1e-7 ? g : 1e-7;
+    ctx->have_mesh = true;
+    return build_bvh(ctx);
+}
+
+MeshView mesh_view(const cpf_context *ctx)
+{
+    MeshView m;
+    m.vpos = ctx->d_vpos; m.tetv = ctx->d_tetv; m.tetl = ctx->d_tetl; m.tetcode = ctx->d_tetcode;
+    m.tetcell = ctx->cellFromVertex ? nullptr : ctx->d_tetcell;
+    m.ucell = ctx->d_ucell[ctx->ucur];
+    m.uvert = ctx->d_uvert;
+    m.patch_kind = ctx->d_patch_kind;
+    m.nPoints = ctx->nPoints; m.nTets = ctx->nTets; m.nCells = (int)ctx->nCells;
+    m.guard = ctx->guard;
+    return m;
+}
+
+void release_mesh(cpf_context *ctx) { free_mesh(ctx); }
+
+} // namespace cpf

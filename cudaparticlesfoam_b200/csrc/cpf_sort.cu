@@ -1,0 +1,144 @@
+// cpf_sort.cu -- sort-by-cell (locality), original-order gather for downloads, statistics.
+//
+// The reference never reorders particles (thread i == particle i forever,
+// third_party/RTXAdvect/query/ConvexQuery.cu:146), so neighbouring threads gather unrelated tets.
+// Here particles are periodically counting-sorted by the cell that contains them; `pid` carries the
+// original index so that every download is returned in the reference's order.
+#include <cub/cub.cuh>
+
+#include "cpf_internal.h"
+
+namespace cpf {
+
+CPF_DEV int sort_key(const MeshView &m, int tet)
+{
+    if (tet < 0) return m.nCells; // frozen / lost particles go last
+    const int4 v = ld_int4(m.tetv, tet);
+    return tet_cell(m, tet, v);
+}
+
+__global__ void k_hist(const MeshView m, const int *__restrict__ tet, long long n, int *__restrict__ hist)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(hist + sort_key(m, tet[i]), 1);
+}
+
+__global__ void k_scatter(const MeshView m, long long n, int *__restrict__ cursor, const double4 *__restrict__ pos,
+                          const int *__restrict__ tet, const int *__restrict__ pid, const double4 *__restrict__ vel,
+                          const curandState_t *__restrict__ rng, double4 *__restrict__ pos2, int *__restrict__ tet2,
+                          int *__restrict__ pid2, double4 *__restrict__ vel2, curandState_t *__restrict__ rng2)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = tet[i];
+    const int dst = atomicAdd(cursor + sort_key(m, t), 1);
+    pos2[dst] = pos[i];
+    tet2[dst] = t;
+    pid2[dst] = pid[i];
+    vel2[dst] = vel[i];
+    if (rng) rng2[dst] = rng[i];
+}
+
+int sort_particles_by_cell(cpf_context *ctx)
+{
+    if (ctx->n == 0 || !ctx->have_mesh || !ctx->have_tets) return CPF_OK;
+    cudaStream_t st = ctx->stream;
+    const long long n = ctx->n;
+    const int nb = (int)ctx->nCells + 1;
+    if (!ctx->d_sort_hist) CPF_CUDA(ctx, cudaMalloc(&ctx->d_sort_hist, sizeof(int) * (size_t)(ctx->nCells + 2)));
+    CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_sort_hist, 0, sizeof(int) * (size_t)nb, st));
+    const MeshView m = mesh_view(ctx);
+    const int a = ctx->pcur, b = 1 - a;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    k_hist<<<grid, 256, 0, st>>>(m, ctx->d_tet[a], n, ctx->d_sort_hist);
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->d_sort_hist, ctx->d_sort_hist, nb, st);
+    int rc = ensure_scratch(ctx, tmp);
+    if (rc) return rc;
+    CPF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->d_scratch, tmp, ctx->d_sort_hist, ctx->d_sort_hist, nb, st));
+    const bool useRng = ctx->rng_ready && ctx->d_rng[a] && ctx->d_rng[b];
+    k_scatter<<<grid, 256, 0, st>>>(m, n, ctx->d_sort_hist, ctx->d_pos[a], ctx->d_tet[a], ctx->d_pid[a], ctx->d_vel[a],
+                                    useRng ? ctx->d_rng[a] : nullptr, ctx->d_pos[b], ctx->d_tet[b], ctx->d_pid[b], ctx->d_vel[b],
+                                    useRng ? ctx->d_rng[b] : nullptr);
+    ctx->launches += 4;
+    CPF_CUDA(ctx, cudaGetLastError());
+    ctx->pcur = b;
+    ctx->permuted = true;
+    ctx->since_sort = 0;
+    return CPF_OK;
+}
+
+__global__ void k_gather(long long n, const int *__restrict__ pid, const double4 *__restrict__ pos, const double4 *__restrict__ vel,
+                         const int *__restrict__ tet, double4 *__restrict__ pos_o, double4 *__restrict__ vel_o, int *__restrict__ tet_o)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long o = pid[i];
+    if (pos_o) pos_o[o] = pos[i];
+    if (vel_o) vel_o[o] = vel[i];
+    if (tet_o) tet_o[o] = tet[i];
+}
+
+int gather_original_order(cpf_context *ctx, double4 *d_pos_out, double4 *d_vel_out, int *d_tet_out)
+{
+    const int a = ctx->pcur;
+    k_gather<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n, ctx->d_pid[a], ctx->d_pos[a], ctx->d_vel[a], ctx->d_tet[a],
+                                                                        d_pos_out, d_vel_out, d_tet_out);
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+    return CPF_OK;
+}
+
+// cudaReportParticles (cuda/particles.cu:763-775) + kinetic energy (cuda/utils.cpp:253-258)
+__global__ void k_stats(long long n, const double4 *__restrict__ pos, const int *__restrict__ tet, const double4 *__restrict__ vel,
+                        unsigned long long *__restrict__ out_counts, double *__restrict__ out_ke)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned active = 0, neg = 0;
+    double ke = 0.0;
+    if (i < n) {
+        active = pos[i].w != 0.0;
+        neg = tet[i] < 0;
+        const double4 v = vel[i];
+        ke = 0.5 * (v.x * v.x + v.y * v.y + v.z * v.z);
+    }
+    active = __reduce_add_sync(0xffffffffu, active);
+    neg = __reduce_add_sync(0xffffffffu, neg);
+    for (int o = 16; o > 0; o >>= 1) ke += __shfl_down_sync(0xffffffffu, ke, o);
+    if ((threadIdx.x & 31) == 0) {
+        if (active) atomicAdd(out_counts, (unsigned long long)active);
+        if (neg) atomicAdd(out_counts + 1, (unsigned long long)neg);
+        atomicAdd(out_ke, ke);
+    }
+}
+
+int reduce_stats(cpf_context *ctx, cpf_stats *out)
+{
+    memset(out, 0, sizeof *out);
+    out->n_particles = ctx->n;
+    int rc = ensure_scratch(ctx, 64);
+    if (rc) return rc;
+    unsigned long long *d_c = (unsigned long long *)ctx->d_scratch;
+    double *d_ke = (double *)(d_c + 2);
+    CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 64, ctx->stream));
+    if (ctx->n) {
+        const int a = ctx->pcur;
+        k_stats<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n, ctx->d_pos[a], ctx->d_tet[a], ctx->d_vel[a], d_c, d_ke);
+        ctx->launches++;
+    }
+    unsigned long long h[3] = { 0, 0, 0 }, cnt[CNT_COUNT] = { 0 };
+    CPF_CUDA(ctx, cudaMemcpyAsync(h, d_c, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CPF_CUDA(ctx, cudaMemcpyAsync(cnt, ctx->d_counters, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->n_active = (long long)h[0];
+    out->n_negative_tet = (long long)h[1];
+    memcpy(&out->kinetic_energy, &h[2], sizeof(double));
+    out->n_escaped = (long long)cnt[CNT_ESCAPED];
+    out->n_reflections = (long long)cnt[CNT_REFLECT];
+    out->n_exact = (long long)cnt[CNT_EXACT];
+    out->n_hops = (long long)cnt[CNT_HOPS];
+    out->n_substeps = (long long)cnt[CNT_SUBSTEPS];
+    return CPF_OK;
+}
+
+} // namespace cpf

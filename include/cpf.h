@@ -1,0 +1,180 @@
+/*
+ * cpf.h -- C ABI of libcpf: B200-native particle advection on OpenFOAM tet-decomposed meshes.
+ *
+ * This is the drop-in boundary for the hot path of simzero/cudaParticlesFoam: everything the
+ * solvers reach through src/initCuda.H and src/advect.H (textually included into main()) and that
+ * today crosses into libcudaParticleAdvection.so as C++ free functions in namespace advect
+ * (third_party/RTXAdvect/cuda/common.h:32-102, query/ConvexQuery.h:33-46, query/RTQuery.h:34-63).
+ * Each entry point below names the reference interface it replaces (paths relative to
+ * /root/reference).  extern "C", plain pointers and sizes only; the library owns all device memory
+ * behind the handle; host buffers are borrowed for the duration of a call; every call returns an
+ * int status (0 = CPF_OK) and never exits or throws (the reference's cudaCheck calls exit(),
+ * third_party/RTXAdvect/cuda/cudaHelpers.cuh:32-40).
+ */
+#ifndef CPF_H
+#define CPF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPF_ABI_VERSION 1
+
+typedef struct cpf_context cpf_context;
+
+enum cpf_status {
+    CPF_OK = 0,
+    CPF_ERR_INVALID = 1,      /* bad argument / call order                                      */
+    CPF_ERR_CUDA = 2,         /* CUDA runtime error (message via cpf_last_error)                 */
+    CPF_ERR_MESH = 3,         /* degenerate / inverted / non-manifold tet mesh                   */
+    CPF_ERR_NOMEM = 4,
+    CPF_ERR_NO_DEVICE = 5     /* no CUDA device: there is NO CPU fallback                        */
+};
+
+/* src/initCuda.H:72 VelocityInterpMethod ("TetVelocity" is what the glue uses;
+ * "VertexVelocity" = cuda/particles.cu:244-313, barycentric interpolation of per-vertex values,
+ * i.e. OpenFOAM cellPoint-style interpolation over [points..., cell centres...]) */
+enum cpf_interp { CPF_INTERP_TET = 0, CPF_INTERP_VERTEX = 1 };
+/* -DConvexPoly (default build, etc/bashrc:1 RTX=false) vs RTX=true build */
+enum cpf_locator { CPF_LOCATOR_CONVEX = 0, CPF_LOCATOR_BARY = 1 };
+/* time integration: the reference wires Euler only (cuda/particles.cu:358); RK2/RK4 are extensions */
+enum cpf_integrator { CPF_EULER = 0, CPF_RK2 = 1, CPF_RK4 = 4 };
+/* random walk generator: XORWOW = the reference's cuRAND stream (cuda/particles.cu:524-575),
+ * PHILOX = stateless counter-based stream (0 B of state traffic), NONE = usingBrownianMotion=false */
+enum cpf_rng { CPF_RNG_NONE = 0, CPF_RNG_XORWOW = 1, CPF_RNG_PHILOX = 2 };
+/* per-patch boundary action; the reference reflects on every boundary (query/RTQuery.cu:165-166) */
+enum cpf_patch_kind { CPF_PATCH_REFLECT = 0, CPF_PATCH_ESCAPE = 1 };
+/* arithmetic policy of the locate step */
+enum cpf_path {
+    CPF_PATH_FILTERED = 0,    /* fast filtered predicates, exact reference arithmetic on demand   */
+    CPF_PATH_EXACT = 1        /* reference arithmetic for every particle (cross-check mode)       */
+};
+
+/* Mirrors the dictionary keys and hard-coded switches of src/initCuda.H:50-72. */
+typedef struct cpf_config {
+    int device;               /* CUDA device ordinal                                             */
+    int interp;               /* enum cpf_interp        (default CPF_INTERP_TET)                  */
+    int locator;              /* enum cpf_locator       (default CPF_LOCATOR_CONVEX)              */
+    int integrator;           /* enum cpf_integrator    (default CPF_EULER)                       */
+    int rng;                  /* enum cpf_rng           (default CPF_RNG_XORWOW, as the glue)     */
+    int reflect_wall;         /* src/initCuda.H:67 reflectWall (default 1)                        */
+    int path;                 /* enum cpf_path          (default CPF_PATH_FILTERED)               */
+    int sort_interval;        /* re-sort particles by cell every N sub-steps (0 = never)          */
+    int fuse_substeps;        /* max sub-steps fused into one launch (0 = library default)        */
+    double dt;                /* "dt" Lagrangian step (default 1e-4)                              */
+    double diffusion_coeff;   /* "diffusionCoeff" (default 5.7e-6)                                */
+    unsigned long long seed;  /* RNG seed (default 1591593751, cuda/particles.cu:544)             */
+    int save_interval;        /* "saveInterval" (default 10)                                      */
+    int reserved[7];
+} cpf_config;
+
+/* Counters gathered per GPU ("particle statistics come back by gather"). */
+typedef struct cpf_stats {
+    long long n_particles;
+    long long n_active;       /* w != 0                                                          */
+    long long n_negative_tet; /* what cudaReportParticles counts (cuda/particles.cu:763-775)      */
+    long long n_escaped;      /* left through an ESCAPE patch (cumulative)                        */
+    long long n_reflections;  /* wall hits handled (cumulative)                                   */
+    long long n_exact;        /* particle-sub-steps that took the exact path (cumulative)         */
+    long long n_hops;         /* tets visited by the locator (cumulative)                         */
+    long long n_substeps;     /* particle-sub-steps executed (cumulative)                         */
+    double kinetic_energy;    /* sum 0.5*|vel|^2, as printed by writeParticles2VTU (utils.cpp:258) */
+    double reserved[3];
+} cpf_stats;
+
+/* -- lifecycle ------------------------------------------------------------------------------ */
+int cpf_abi_version(void);
+void cpf_default_config(cpf_config *cfg);
+/* replaces the ~35 locals + cudaMalloc block of src/initCuda.H:33-72, 141-150 */
+int cpf_create(const cpf_config *cfg, cpf_context **out);
+int cpf_destroy(cpf_context *ctx);
+const char *cpf_last_error(const cpf_context *ctx); /* ctx may be NULL: last create() failure */
+int cpf_sync(cpf_context *ctx);
+int cpf_set_config(cpf_context *ctx, const cpf_config *cfg); /* run-time switches only */
+
+/* -- mesh upload ---------------------------------------------------------------------------- */
+/* Replaces src/initCuda.H:76-130: tet decomposition of the fvMesh (polyMeshTetDecomposition::
+ * cellTetIndices / tetIndices::faceTriIs), HostTetMesh::getBoundaryMesh (cuda/HostTetMesh.h:
+ * 307-430), DeviceTetMesh::upload (cuda/DeviceTetMesh.cuh:59-72) and the OptiX BVH build.
+ * Arrays are OpenFOAM's: points[nPoints][3], faces as CSR, owner[nFaces], neighbour[nInternal],
+ * cellCentres[nCells][3] (mesh.C()), tetBasePt[nFaces] (mesh.tetBasePtIs(), NULL => 0),
+ * patchStart[nPatches+1] face ranges of the boundary patches, patchKind[nPatches] (NULL => all
+ * reflect).  Vertex ids of the device tet mesh are [points..., nPoints + cell]. */
+int cpf_mesh_upload_poly(cpf_context *ctx, int nPoints, const double *points, int nFaces,
+                         const int *faceOffsets, const int *faceVerts, const int *owner, int nInternal,
+                         const int *neighbour, int nCells, const double *cellCentres, const int *tetBasePt,
+                         int nPatches, const int *patchStart, const int *patchKind);
+/* Same for an explicit tet list (HostTetMesh{positions,indices}); tetCell may be NULL (tet == cell). */
+int cpf_mesh_upload_tets(cpf_context *ctx, int nVerts, const double *positions, long long nTets,
+                         const int *tetVerts, const int *tetCell, int nCells);
+int cpf_mesh_info(cpf_context *ctx, long long *nVerts, long long *nTets, long long *nCells,
+                  long long *nBoundaryFaces);
+/* debug/parity: tet table in upload order */
+int cpf_mesh_download_tets(cpf_context *ctx, int *tetVerts /*[nTets][4]*/, int *tetCell /*[nTets]*/);
+/* debug/parity: per tet and reference face slot k (opposite vertex k): neighbour tet, or
+ * -(patch+1) on the boundary -- the information content of tetfacets+faceInfos */
+int cpf_mesh_download_neighbours(cpf_context *ctx, int *nbr /*[nTets][4]*/);
+
+/* -- flow field ----------------------------------------------------------------------------- */
+/* Replaces the host 12x expansion + cudaUpdateVelocity of src/advect.H:44-57 and
+ * cuda/particles.cu:733-749.  U is the solver's cell field [nCells][3] (fp64).  on_device != 0:
+ * U is a device pointer (e.g. the NCCL broadcast buffer) and is consumed in place on the
+ * library's stream. */
+int cpf_update_velocity(cpf_context *ctx, const double *U, int on_device);
+/* CPF_INTERP_VERTEX: explicit per-vertex field [nVerts][3] (points then centres); if never
+ * called the library interpolates point values from the cell field (inverse-distance weights). */
+int cpf_update_vertex_velocity(cpf_context *ctx, const double *Uvert, int on_device);
+
+/* -- particles ------------------------------------------------------------------------------ */
+/* cudaInitParticles (cuda/particles.cu:100-108) with an explicit, reproducible host-side stream */
+int cpf_seed_box(cpf_context *ctx, long long n, const double lo[3], const double hi[3],
+                 unsigned long long seed);
+/* cudaInitParticles(fileName) analogue: xyzw[n][4] = (x,y,z,active) */
+int cpf_set_particles(cpf_context *ctx, long long n, const double *xyzw);
+/* optional: caller-supplied start tets (skips cpf_locate_initial) */
+int cpf_set_tets(cpf_context *ctx, const int *tet);
+/* replaces RTQuery(OptixQuery&,...) = OptiX ray cast + baryQuery (query/RTQuery.cu:295-310):
+ * BVH point location, lowest containing tet id, -1 outside */
+int cpf_locate_initial(cpf_context *ctx);
+/* initRandomGenerator (cuda/particles.cu:541-548) */
+int cpf_init_rng(cpf_context *ctx);
+
+/* -- the hot path --------------------------------------------------------------------------- */
+/* One body of src/advect.H:33-184 without the velocity refresh: nCycles = max(ceil(deltaT/dt),1)
+ * sub-steps of {cudaAdvect, cudaBrownianMotion, convexTetQuery|RTQuery, convexWallReflect|
+ * RTWallReflect, cudaMoveParticles}, fused.  Asynchronous; *nCyclesOut may be NULL. */
+int cpf_advect(cpf_context *ctx, double deltaT, int *nCyclesOut);
+/* exactly n sub-steps of size dt (the loop body at src/advect.H:86-184) */
+int cpf_substeps(cpf_context *ctx, int n, double dt);
+/* the initial cudaAdvect of src/initCuda.H:184-199 (deactivates out-of-domain particles) */
+int cpf_initial_advect(cpf_context *ctx);
+/* force a sort-by-cell now */
+int cpf_sort_particles(cpf_context *ctx);
+/* last kernel timing: milliseconds of the most recent cpf_advect/cpf_substeps on the device */
+int cpf_last_step_ms(cpf_context *ctx, float *ms);
+
+/* -- results -------------------------------------------------------------------------------- */
+/* replaces the D2H copies of writeParticles2VTU (cuda/utils.cpp:144-170); any pointer may be
+ * NULL; arrays are in ORIGINAL particle order: xyzw[n][4], vel[n][4], tet[n] */
+int cpf_download(cpf_context *ctx, double *xyzw, double *vel, int *tet);
+int cpf_download_cells(cpf_context *ctx, int *cell);
+/* cudaReportParticles + the kinetic-energy print of writeParticles2VTU */
+int cpf_stats_get(cpf_context *ctx, cpf_stats *out);
+/* writeParticles2VTU (cuda/utils.cpp:144-283): particle_%04d.vtu in `dir` */
+int cpf_write_vtu(cpf_context *ctx, const char *dir, unsigned step);
+long long cpf_num_particles(cpf_context *ctx);
+/* raw device pointers (for torch / NCCL plumbing); valid until the next set/seed/sort call */
+int cpf_device_pointers(cpf_context *ctx, void **pos4, void **tet, void **ucell);
+/* parity tooling: the normal deviates the next sub-step will use, [n][3], original order;
+ * does not advance the stream */
+int cpf_debug_next_normals(cpf_context *ctx, double *xi);
+/* number of kernels the library launched since create (bench.py gpu_launches) */
+long long cpf_launch_count(cpf_context *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPF_H */

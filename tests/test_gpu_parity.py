@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on identical
+seeded inputs.  Bit-exact for tet ids and (fp64) positions/velocities -- the stated tolerance of the
+north star (1e-6 relative) is met with margin 0."""
+import numpy as np
+import pytest
+
+from conftest import make_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _tracker(**kw):
+    from cudaparticlesfoam_b200 import api
+
+    kw.setdefault("rng", api.RNG_NONE)
+    return api.ParticleTracker(**kw)
+
+
+def _assert_same_state(p, v, t, cl, what=""):
+    bad = np.flatnonzero(t != cl.tet)
+    assert bad.size == 0, f"{what}: {bad.size} tet ids differ, first {bad[:5]}: {t[bad[:5]]} vs {cl.tet[bad[:5]]}"
+    assert np.array_equal(p.view(np.uint64), cl.p.view(np.uint64)), f"{what}: positions not bit-identical"
+    if v is not None:
+        live = cl.p[:, 3] != 0
+        assert np.array_equal(v[live, :3].view(np.uint64), cl.vel[live, :3].view(np.uint64)), f"{what}: velocities differ"
+
+
+def test_mesh_builder_matches_oracle(synth, orc):
+    """A1+A2: tets and neighbour information equal the oracle's decomposition and face tables."""
+    pm, mesh, U, p = make_case(synth, orc, dims=(9, 7, 5), jitter=0.25)
+    tr = _tracker()
+    tr.upload_poly(pm)
+    tv, tc = tr.download_tets()
+    assert np.array_equal(tv, mesh.idx) and np.array_equal(tc, mesh.tet_cell)
+    nb = tr.download_neighbours()
+    # oracle neighbour across reference face slot k
+    f = mesh.tetfacets
+    front, back = mesh.finfo[f, 0], mesh.finfo[f, 1]
+    me = np.arange(mesh.n_tets)[:, None]
+    other = np.where(back == me, front, back)
+    assert np.array_equal(nb >= 0, other >= 0)
+    assert np.array_equal(nb[nb >= 0], other[other >= 0])
+    info = tr.mesh_info()
+    assert info["n_boundary_faces"] == mesh.n_boundary and info["n_tets"] == mesh.n_tets
+    # boundary links carry the patch of the polyMesh face
+    npatch = len(pm.patch_starts) - 1
+    assert set(np.unique(-nb[nb < 0] - 1)) == set(range(npatch))
+    tr.close()
+
+
+def test_invalid_meshes_are_rejected(synth, orc):
+    from cudaparticlesfoam_b200 import api
+
+    pm, mesh, U, p = make_case(synth, orc, dims=(3, 3, 3), jitter=0.0)
+    tr = _tracker()
+    bad = mesh.idx.copy()
+    bad[5, [1, 2]] = bad[5, [2, 1]]  # inverted tet
+    with pytest.raises(api.CpfError) as e:
+        tr.upload_tets(mesh.pos, bad, mesh.tet_cell, pm.n_cells)
+    assert e.value.code == 3
+    tr.upload_tets(mesh.pos, mesh.idx, mesh.tet_cell, pm.n_cells)  # the handle is still usable
+    tr.close()
+
+
+def test_initial_location_matches_brute_force(synth, orc):
+    """A4: BVH location == lowest containing tet id (brute force), outside -> -1."""
+    pm, mesh, U, p = make_case(synth, orc, dims=(10, 9, 8), jitter=0.2, n=20000, margin=-0.05)
+    # put some particles exactly on mesh vertices / faces / cell centres (documented tie class:
+    # both sides return the lowest id, so even these must agree)
+    p[:200, :3] = mesh.pos[:200]
+    p[200:400, :3] = 0.5 * (mesh.pos[mesh.idx[:200, 1]] + mesh.pos[mesh.idx[:200, 2]])
+    tr = _tracker()
+    tr.upload_poly(pm)
+    tr.set_particles(p)
+    tr.locate_initial()
+    _, _, t = tr.download(pos=False, vel=False)
+    ref = orc.locate_brute(mesh, p)
+    assert (ref < 0).sum() > 100
+    assert np.array_equal(t, ref)
+    tr.close()
+
+
+@pytest.mark.parametrize("path", [1, 0], ids=["exact", "filtered"])
+@pytest.mark.parametrize("jitter", [0.0, 0.2])
+def test_convex_substeps_bit_exact(synth, orc, path, jitter):
+    """A5+A7+A8+A9 fused (default ConvexPoly build, no random walk): 60 sub-steps with reflections."""
+    pm, mesh, U, p = make_case(synth, orc, dims=(12, 10, 8), jitter=jitter, n=30000)
+    Utet = orc.expand_velocity(mesh, U)
+    tet0 = orc.locate_brute(mesh, p)
+    cl = orc.Cloud.make(p, tet0)
+    tr = _tracker(path=path)
+    tr.upload_poly(pm)
+    tr.update_velocity(U)
+    tr.set_particles(p)
+    tr.locate_initial()
+    dt = 0.02
+    for chunk in (1, 7, 52):
+        orc.substeps(mesh, cl, Utet, chunk, dt)
+        tr.substeps(chunk, dt)
+        pp, vv, tt = tr.download()
+        _assert_same_state(pp, vv, tt, cl, f"after chunk {chunk}")
+    st = tr.stats()
+    assert st["n_reflections"] > 0, "the case must exercise wall reflection"
+    assert st["n_active"] == int((cl.p[:, 3] != 0).sum())
+    if path == 0:
+        assert st["n_exact"] < 0.2 * st["n_substeps"], "the filtered path should rarely need exact arithmetic"
+    tr.close()
+
+
+def test_filtered_path_handles_degenerate_starts(synth, orc):
+    """Particles sitting exactly on vertices, edges, faces and cell centres must take the exact
+    path and still reproduce the oracle bit for bit."""
+    pm, mesh, U, p = make_case(synth, orc, dims=(6, 6, 6), jitter=0.0, n=6000, field=(0.3, 0.2, 0.1))
+    k = 1500
+    p[:k, :3] = mesh.pos[np.arange(k) % mesh.pos.shape[0]]                      # vertices (incl. centres)
+    a = mesh.pos[mesh.idx[:k, 1]]; b = mesh.pos[mesh.idx[:k, 2]]; c = mesh.pos[mesh.idx[:k, 3]]
+    p[k:2 * k, :3] = 0.5 * (a + b)                                              # edge midpoints
+    p[2 * k:3 * k, :3] = (a + b + c) / 3.0                                      # face centroids
+    tet0 = orc.locate_brute(mesh, p)
+    Utet = orc.expand_velocity(mesh, U)
+    cl = orc.Cloud.make(p, tet0)
+    tr = _tracker(path=0)
+    tr.upload_poly(pm)
+    tr.update_velocity(U)
+    tr.set_particles(p)
+    tr.set_tets(tet0)
+    orc.substeps(mesh, cl, Utet, 25, 0.05)
+    tr.substeps(25, 0.05)
+    pp, vv, tt = tr.download()
+    _assert_same_state(pp, vv, tt, cl, "degenerate starts")
+    tr.close()
+
+
+def test_fused_and_sorted_runs_equal_plain_run(synth, orc):
+    """Fusing sub-steps into one launch and re-sorting particles by cell must not change a bit."""
+    pm, mesh, U, p = make_case(synth, orc, dims=(10, 10, 10), jitter=0.15, n=20000, field="channel")
+    Utet = orc.expand_velocity(mesh, U)
+    tet0 = orc.locate_brute(mesh, p)
+    cl = orc.Cloud.make(p, tet0)
+    orc.substeps(mesh, cl, Utet, 40, 0.03)
+    for kw in (dict(fuse_substeps=8), dict(sort_interval=5), dict(fuse_substeps=4, sort_interval=6)):
+        tr = _tracker(**kw)
+        tr.upload_poly(pm)
+        tr.update_velocity(U)
+        tr.set_particles(p)
+        tr.locate_initial()
+        tr.substeps(40, 0.03)
+        pp, vv, tt = tr.download()
+        _assert_same_state(pp, vv, tt, cl, str(kw))
+        tr.close()
+
+
+def test_bary_mode_bit_exact(synth, orc):
+    """A7'+A8' (RTX=true build): barycentric walk + RTreflection."""
+    pm, mesh, U, p = make_case(synth, orc, dims=(10, 8, 6), jitter=0.2, n=20000)
+    Utet = orc.expand_velocity(mesh, U)
+    tet0 = orc.locate_brute(mesh, p)
+    cl = orc.Cloud.make(p, tet0)
+    from cudaparticlesfoam_b200 import api
+
+    tr = _tracker(locator=api.LOCATOR_BARY)
+    tr.upload_poly(pm)
+    tr.update_velocity(U)
+    tr.set_particles(p)
+    tr.locate_initial()
+    orc.substeps(mesh, cl, Utet, 50, 0.02, convex=False)
+    tr.substeps(50, 0.02)
+    pp, vv, tt = tr.download()
+    _assert_same_state(pp, vv, tt, cl, "bary mode")
+    assert tr.stats()["n_reflections"] > 0
+    tr.close()
+
+
+@pytest.mark.parametrize("rng", [1, 2], ids=["xorwow", "philox"])
+def test_random_walk_matches_oracle_given_the_deviates(synth, orc, rng):
+    """A6: disp += sqrt(2 D dt) * xi.  The deviates are read back from the library and fed to the
+    oracle, so the comparison stays bit-exact for either generator."""
+    pm, mesh, U, p = make_case(synth, orc, dims=(8, 8, 8), jitter=0.2, n=10000, field="channel")
+    Utet = orc.expand_velocity(mesh, U)
+    tet0 = orc.locate_brute(mesh, p)
+    cl = orc.Cloud.make(p, tet0)
+    tr = _tracker(rng=rng, diffusion_coeff=2e-3, sort_interval=4)
+    tr.upload_poly(pm)
+    tr.update_velocity(U)
+    tr.set_particles(p)
+    tr.locate_initial()
+    dt = 0.02
+    xs = []
+    for s in range(12):
+        xi = tr.next_normals()
+        xs.append(xi)
+        orc.substeps(mesh, cl, Utet, 1, dt, xi=xi[None], D=2e-3)
+        tr.substeps(1, dt)
+    pp, vv, tt = tr.download()
+    _assert_same_state(pp, vv, tt, cl, "random walk")
+    x = np.concatenate(xs).ravel()
+    assert abs(x.mean()) < 0.02 and abs(x.std() - 1.0) < 0.02, "deviates must be standard normal"
+    tr.close()
+
+
+def test_velocity_refresh_and_advect_cycle_count(synth, orc):
+    """A10 + src/advect.H:36-37: nCycles = max(ceil(deltaT/dt),1), cycleDt = deltaT/nCycles, new
+    cell field picked up by the next call."""
+    pm, mesh, U, p = make_case(synth, orc, dims=(8, 8, 8), jitter=0.1, n=8000)
+    tet0 = orc.locate_brute(mesh, p)
+    cl = orc.Cloud.make(p, tet0)
+    tr = _tracker(dt=3e-3)
+    tr.init_cuda(pm, U, particles=p)
+    t = 0.0
+    for step in range(4):
+        Ut = synth.field_uniform_vortex(pm.cell_centres, R=0.3, omega=2 * np.pi * (1 + 0.3 * step))
+        n = tr.advect(Ut, 0.01)
+        assert n == 4
+        orc.substeps(mesh, cl, orc.expand_velocity(mesh, Ut), 4, 0.01 / 4)
+    pp, vv, tt = tr.download()
+    _assert_same_state(pp, vv, tt, cl, "coupled refresh")
+    tr.close()
+
+
+def test_empty_and_inactive_inputs(synth, orc):
+    pm, mesh, U, p = make_case(synth, orc, dims=(4, 4, 4), jitter=0.0, n=64)
+    tr = _tracker()
+    tr.upload_poly(pm)
+    tr.update_velocity(U)
+    tr.set_particles(np.zeros((0, 4)))
+    tr.locate_initial()
+    tr.substeps(3, 0.01)
+    assert tr.stats()["n_particles"] == 0
+    # outside / inactive particles are frozen exactly like the reference does (w := 0, never moved)
+    p[:10, 0] += 5.0
+    p[10:20, 3] = 0.0
+    tr.set_particles(p)
+    tr.locate_initial()
+    tr.substeps(5, 0.01)
+    pp, _, tt = tr.download()
+    assert np.all(tt[:10] == -1) and np.all(pp[:10, 3] == 0) and np.array_equal(pp[:20, :3], p[:20, :3])
+    assert np.all(pp[20:, 3] == 1)
+    tr.close()
