@@ -397,6 +397,7 @@ int cpf_init_rng(cpf_context *ctx)
 int cpf_substeps(cpf_context *ctx, int n, double dt)
 {
     if (!ctx) return CPF_ERR_INVALID;
+    if (ctx->n == 0 || n <= 0) return CPF_OK;
     if (!ctx->have_mesh || !ctx->have_tets) return fail(ctx, CPF_ERR_INVALID, "cpf_substeps: mesh and located particles are required");
     if (ctx->cfg.integrator != CPF_EULER || ctx->cfg.interp != CPF_INTERP_TET)
         return fail(ctx, CPF_ERR_INVALID, "integrator/interp combination not available in this build");

@@ -272,13 +272,17 @@ static inline void s1_advect_vertvel(double *p, int tet, double *vel, double *di
     double wA = ref_det(P, B, C, D) * rden;
     double wB = ref_det(A, P, C, D) * rden;
     double wC = ref_det(A, B, P, D) * rden;
-    double wD = ref_det(A, B, C, P) * rden;
+    /* det(A,B,C,P): nvcc reuses cross(B-A,C-A) from `den` and emits this dot with the x product
+     * rounded first (PTX of particleAdvectKernel): fma(c.z,r.z, fma(c.y,r.y, c.x*r.x)) */
+    v3 cr = ref_cross(v3_sub(B, A), v3_sub(C, A));
+    v3 rr = v3_sub(P, A);
+    double wD = fma(cr.z, rr.z, fma(cr.y, rr.y, cr.x * rr.x)) * rden;
     v3 uA = ld3(Uvert, ix[0]), uB = ld3(Uvert, ix[1]), uC = ld3(Uvert, ix[2]), uD = ld3(Uvert, ix[3]);
-    /* wA*velA + wB*velB + wC*velC + wD*velD, left to right: fma(wD,uD, fma(wC,uC, fma(wB,uB, wA*uA))) */
+    /* wA*velA + wB*velB + wC*velC + wD*velD -> fma(wD,uD, fma(wC,uC, fma(wA,uA, wB*uB))) */
     v3 v;
-    v.x = fma(wD, uD.x, fma(wC, uC.x, fma(wB, uB.x, wA * uA.x)));
-    v.y = fma(wD, uD.y, fma(wC, uC.y, fma(wB, uB.y, wA * uA.y)));
-    v.z = fma(wD, uD.z, fma(wC, uC.z, fma(wB, uB.z, wA * uA.z)));
+    v.x = fma(wD, uD.x, fma(wC, uC.x, fma(wA, uA.x, wB * uB.x)));
+    v.y = fma(wD, uD.y, fma(wC, uC.y, fma(wA, uA.y, wB * uB.y)));
+    v.z = fma(wD, uD.z, fma(wC, uC.z, fma(wA, uA.z, wB * uB.z)));
     disp[0] = fma(dt, v.x, p[0]) - p[0];
     disp[1] = fma(dt, v.y, p[1]) - p[1];
     disp[2] = fma(dt, v.z, p[2]) - p[2];

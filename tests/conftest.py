@@ -55,6 +55,8 @@ def make_case(synth, orc, dims=(8, 7, 6), jitter=0.2, n=4000, field="vortex", se
     mesh = orc.tet_mesh_from_poly(pm)
     if field == "vortex":
         U = synth.field_uniform_vortex(pm.cell_centres, R=0.3)
+    elif field == "swirl":
+        U = synth.field_uniform_vortex(pm.cell_centres, U0=(0.0, 0.0, 0.0), R=0.3)
     elif field == "channel":
         U = synth.field_channel(pm.cell_centres, lo=pm.lo, hi=pm.hi)
     else:

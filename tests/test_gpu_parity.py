@@ -102,8 +102,28 @@ def test_convex_substeps_bit_exact(synth, orc, path, jitter):
     st = tr.stats()
     assert st["n_reflections"] > 0, "the case must exercise wall reflection"
     assert st["n_active"] == int((cl.p[:, 3] != 0).sum())
-    if path == 0:
-        assert st["n_exact"] < 0.2 * st["n_substeps"], "the filtered path should rarely need exact arithmetic"
+    tr.close()
+
+
+def test_filtered_path_rarely_needs_exact_arithmetic(synth, orc):
+    """Closed swirling flow (few wall contacts): the guard-band filter must let almost every
+    particle-sub-step through the cheap path, and still match the oracle bit for bit."""
+    pm, mesh, U, p = make_case(synth, orc, dims=(12, 12, 6), jitter=0.2, n=40000, field="swirl", margin=0.1)
+    Utet = orc.expand_velocity(mesh, U)
+    tet0 = orc.locate_brute(mesh, p)
+    cl = orc.Cloud.make(p, tet0)
+    tr = _tracker(path=0)
+    tr.upload_poly(pm)
+    tr.update_velocity(U)
+    tr.set_particles(p)
+    tr.locate_initial()
+    orc.substeps(mesh, cl, Utet, 30, 0.02)
+    tr.substeps(30, 0.02)
+    pp, vv, tt = tr.download()
+    _assert_same_state(pp, vv, tt, cl, "swirl")
+    st = tr.stats()
+    assert st["n_hops"] > 1.5 * st["n_substeps"], "the case must cross tets"
+    assert st["n_exact"] < 0.01 * st["n_substeps"], (st["n_exact"], st["n_substeps"])
     tr.close()
 
 
