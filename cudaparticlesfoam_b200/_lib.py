@@ -37,6 +37,9 @@ SYMBOLS = {
     "cpf_destroy": (C.c_int, [_vp]),
     "cpf_last_error": (C.c_char_p, [_vp]),
     "cpf_sync": (C.c_int, [_vp]),
+    "cpf_set_stream": (C.c_int, [_vp, _vp]),
+    "cpf_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "cpf_profile_read": (C.c_int, [_vp, _ip, _dp, _dp]),
     "cpf_set_config": (C.c_int, [_vp, C.POINTER(CpfConfig)]),
     "cpf_mesh_upload_poly": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _ip, _ip, _ip, C.c_int, _ip, C.c_int, _dp, _ip, C.c_int, _ip, _ip]),
     "cpf_mesh_upload_tets": (C.c_int, [_vp, C.c_int, _dp, _ll, _ip, _ip, C.c_int]),

@@ -246,5 +246,16 @@ class ParticleTracker:
         self._chk(self.lib.cpf_device_pointers(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def set_stream(self, cuda_stream: int | None):
+        self._chk(self.lib.cpf_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def profile(self, enable: bool):
+        self._chk(self.lib.cpf_profile_enable(self.h, int(enable)))
+
+    def profile_read(self):
+        n, tot, mx = C.c_int(), C.c_double(), C.c_double()
+        self._chk(self.lib.cpf_profile_read(self.h, C.byref(n), C.byref(tot), C.byref(mx)))
+        return n.value, tot.value, mx.value
+
     def launch_count(self) -> int:
         return int(self.lib.cpf_launch_count(self.h))

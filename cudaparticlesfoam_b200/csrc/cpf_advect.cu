@@ -352,9 +352,23 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
         if (rc) return rc;
     }
     const dim3 grid((unsigned)((ctx->n + 127) / 128));
+    if (ctx->profiling) {
+        if (ctx->profUsed + 2 > ctx->profEvents.size()) {
+            cudaEvent_t a, b;
+            CPF_CUDA(ctx, cudaEventCreate(&a));
+            CPF_CUDA(ctx, cudaEventCreate(&b));
+            ctx->profEvents.push_back(a);
+            ctx->profEvents.push_back(b);
+        }
+        CPF_CUDA(ctx, cudaEventRecord(ctx->profEvents[ctx->profUsed], ctx->stream));
+    }
     if (ctx->cfg.locator == CPF_LOCATOR_BARY) launch_rng<CPF_LOCATOR_BARY, false>(ctx, m, pv, sp, rng, grid);
     else if (ctx->cfg.path == CPF_PATH_EXACT) launch_rng<CPF_LOCATOR_CONVEX, false>(ctx, m, pv, sp, rng, grid);
     else launch_rng<CPF_LOCATOR_CONVEX, true>(ctx, m, pv, sp, rng, grid);
+    if (ctx->profiling) {
+        CPF_CUDA(ctx, cudaEventRecord(ctx->profEvents[ctx->profUsed + 1], ctx->stream));
+        ctx->profUsed += 2;
+    }
     ctx->launches++;
     ctx->step_index += (unsigned long long)nSub;
     CPF_CUDA(ctx, cudaGetLastError());

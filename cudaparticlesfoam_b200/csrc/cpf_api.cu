@@ -114,7 +114,7 @@ int cpf_create(const cpf_config *cfg, cpf_context **out)
     if (cfg) ctx->cfg = *cfg; else cpf_default_config(&ctx->cfg);
     ctx->device = ctx->cfg.device;
     if (ctx->device < 0 || ctx->device >= ndev) { g_create_error = "bad device ordinal"; delete ctx; return CPF_ERR_INVALID; }
-    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming)) != cudaSuccess ||
@@ -124,7 +124,44 @@ int cpf_create(const cpf_config *cfg, cpf_context **out)
         delete ctx;
         return CPF_ERR_CUDA;
     }
+    ctx->stream = ctx->ownStream;
     *out = ctx;
+    return CPF_OK;
+}
+
+int cpf_set_stream(cpf_context *ctx, void *cuda_stream)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->ownStream;
+    return CPF_OK;
+}
+
+int cpf_profile_enable(cpf_context *ctx, int enable)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    ctx->profiling = enable != 0;
+    ctx->profUsed = 0;
+    return CPF_OK;
+}
+
+int cpf_profile_read(cpf_context *ctx, int *nLaunches, double *total_ms, double *max_ms)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double tot = 0.0, mx = 0.0;
+    for (size_t q = 0; q + 1 < ctx->profUsed; q += 2) {
+        float ms = 0.f;
+        CPF_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->profEvents[q], ctx->profEvents[q + 1]));
+        tot += ms;
+        if (ms > mx) mx = ms;
+    }
+    if (nLaunches) *nLaunches = (int)(ctx->profUsed / 2);
+    if (total_ms) *total_ms = tot;
+    if (max_ms) *max_ms = mx;
+    ctx->profUsed = 0;
     return CPF_OK;
 }
 
@@ -138,7 +175,8 @@ int cpf_destroy(cpf_context *ctx)
     cudaFree(ctx->d_counters); cudaFree(ctx->d_sort_hist); cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evCopy);
-    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copyStream);
+    for (cudaEvent_t ev : ctx->profEvents) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->ownStream); cudaStreamDestroy(ctx->copyStream);
     delete ctx;
     return CPF_OK;
 }

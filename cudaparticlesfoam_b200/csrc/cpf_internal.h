@@ -42,8 +42,12 @@ struct BvhLevel { float4 *lo; float4 *hi; long long n; };
 struct cpf_context {
     cpf_config cfg;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream in use (private or caller-owned)
+    cudaStream_t ownStream = nullptr;   // the context's private stream
     cudaStream_t copyStream = nullptr;
+    bool profiling = false;
+    std::vector<cudaEvent_t> profEvents; // pairs
+    size_t profUsed = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evCopy = nullptr;
     std::string err;
     float last_ms = 0.f;

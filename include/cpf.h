@@ -93,6 +93,11 @@ int cpf_create(const cpf_config *cfg, cpf_context **out);
 int cpf_destroy(cpf_context *ctx);
 const char *cpf_last_error(const cpf_context *ctx); /* ctx may be NULL: last create() failure */
 int cpf_sync(cpf_context *ctx);
+/* Run all work of this context on a caller-owned CUDA stream (cudaStream_t), e.g. the stream the
+ * host issues its NCCL collectives on, so the velocity broadcast and its first consumer kernel are
+ * ordered without host synchronisation.  NULL restores the context's private stream.  The
+ * reference runs everything on the default stream with a device-wide sync after every kernel. */
+int cpf_set_stream(cpf_context *ctx, void *cuda_stream);
 int cpf_set_config(cpf_context *ctx, const cpf_config *cfg); /* run-time switches only */
 
 /* -- mesh upload ---------------------------------------------------------------------------- */
@@ -171,6 +176,11 @@ int cpf_device_pointers(cpf_context *ctx, void **pos4, void **tet, void **ucell)
 /* parity tooling: the normal deviates the next sub-step will use, [n][3], original order;
  * does not advance the stream */
 int cpf_debug_next_normals(cpf_context *ctx, double *xi);
+/* Device timing of the fused sub-step kernel: while enabled, a CUDA-event pair brackets every
+ * launch on the launching stream; cpf_profile_read returns and resets the totals (replaces the
+ * commented-out Adv/Dfs/Qry/Rft/Mov breakdown of src/advect.H:186-203). */
+int cpf_profile_enable(cpf_context *ctx, int enable);
+int cpf_profile_read(cpf_context *ctx, int *nLaunches, double *total_ms, double *max_ms);
 /* number of kernels the library launched since create (bench.py gpu_launches) */
 long long cpf_launch_count(cpf_context *ctx);
 
