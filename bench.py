@@ -139,7 +139,10 @@ def run_ours(args, w, rank, world, local_rank):
     pm, p, fields = build_inputs(w, rank)
     tr = api.ParticleTracker(device=local_rank, rng=api.RNG_PHILOX if w["D"] > 0 else api.RNG_NONE, diffusion_coeff=w["D"], dt=w["dt"],
                              sort_interval=args.sort_interval, fuse_substeps=args.fuse, path=api.PATH_EXACT if args.exact else api.PATH_FILTERED)
-    stream = torch.cuda.current_stream()
+    # one explicit non-default stream shared by torch (copies, NCCL, timing events) and the library
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     tr.set_stream(stream.cuda_stream)
     t0 = time.time()
     tr.upload_poly(pm)
