@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcpf.so")
+LIB_PATH = os.environ.get("CPF_LIB", os.path.join(_HERE, "libcpf.so"))  # CPF_LIB: experiment builds only
 
 
 class CpfConfig(C.Structure):

@@ -12,6 +12,15 @@
 // memory; vel is written only when the host can observe it (last sub-step of a call).
 #include "cpf_internal.h"
 
+#ifndef CPF_MIN_BLOCKS
+#define CPF_MIN_BLOCKS 4
+#endif
+#ifdef CPF_TAIL_NOINLINE
+#define CPF_TAIL __device__ __noinline__
+#else
+#define CPF_TAIL __device__ __forceinline__
+#endif
+
 namespace cpf {
 
 // ------------------------------------------------------------------------------------------------
@@ -59,11 +68,11 @@ CPF_DEV void box_muller_f32(uint32_t x, uint32_t y, double &n0, double &n1)
 {
     const float u1 = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
     const float u2 = ((float)(y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float r = sqrtf(-2.0f * logf(u1));
-    float s, c;
-    sincospif(2.0f * u2, &s, &c);
-    n0 = (double)(r * s);
-    n1 = (double)(r * c);
+    // MUFU-based: lg2/sin/cos/sqrt approximations (abs. error ~1e-6) are ample for a random walk
+    const float r = __fsqrt_rn(-2.0f * __logf(u1));
+    const float ang = 6.283185307179586f * u2;
+    n0 = (double)(r * __sinf(ang));
+    n1 = (double)(r * __cosf(ang));
 }
 template <> struct Rng<CPF_RNG_PHILOX> {
     uint32_t id, k0, k1;
@@ -95,7 +104,7 @@ struct Tally { unsigned hops, exact, refl, esc; };
 // Default build: convex line walk + reflector.  The reference's reflector re-walks the segment
 // from the start tet with bit-identical arithmetic (ConvexQuery.cu:343-397 vs :165-200), so the
 // locator's wall state IS the reflector's state after its first inner loop; we continue from it.
-CPF_DEV void tail_convex_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &tet, double &w, int reflect, Tally &ty)
+CPF_TAIL void tail_convex_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &tet, double &w, int reflect, Tally &ty)
 {
     const D3 E0 = xadd(P, disp);
     D3 E = E0, S = P;
@@ -180,7 +189,7 @@ CPF_DEV int bary_search(const MeshView &m, D3 Q, int start, Tet &T, int &face_j,
     return s;
 }
 
-CPF_DEV void tail_bary_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &tet, int reflect, Tally &ty)
+CPF_TAIL void tail_bary_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &tet, int reflect, Tally &ty)
 {
     Tet T;
     int fj;
@@ -216,7 +225,7 @@ CPF_DEV void tail_bary_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &te
 // the fused kernel
 // ------------------------------------------------------------------------------------------------
 template <int LOC, bool FILT, int RNG>
-__global__ void __launch_bounds__(128) k_substeps(const MeshView m, const ParticleView pv, const StepParams sp)
+__global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_substeps(const MeshView m, const ParticleView pv, const StepParams sp)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     Tally ty{ 0u, 0u, 0u, 0u };
@@ -230,13 +239,19 @@ __global__ void __launch_bounds__(128) k_substeps(const MeshView m, const Partic
         bool velValid = false;
         Rng<RNG> rng;
         const bool live = (w != 0.0);
-        if (live) rng.open(pv, i, sp);
+        WalkState ws;
+        bool wsValid = false;
+        if (live) {
+            rng.open(pv, i, sp);
+            if (FILT && tet >= 0) { ws_load(m, tet, ws); wsValid = true; }
+        }
         for (int s = 0; s < sp.nSub; ++s) {
             if (w == 0.0) break;
             if (tet < 0) { w = 0.0; break; } // S1: left the domain -> frozen (particles.cu:334-338)
             // ---- S1 velocity + Euler displacement: disp = (P + dt*vel) - P
-            const int4 v = ld_int4(m.tetv, tet);
-            const int cell = tet_cell(m, tet, v);
+            int cell;
+            if (FILT && wsValid && !m.tetcell) cell = ws.cell;
+            else cell = tet_cell(m, tet, ld_int4(m.tetv, tet));
             const double *uc = m.ucell + 3ll * cell;
             vel = D3{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
             velValid = true;
@@ -253,14 +268,14 @@ __global__ void __launch_bounds__(128) k_substeps(const MeshView m, const Partic
             // ---- S3..S5
             if (LOC == CPF_LOCATOR_CONVEX) {
                 if (FILT) {
-                    int hops = 0;
-                    const int r = walk_filtered(m, tet, P, disp, hops);
-                    ty.hops += hops;
+                    if (!wsValid) { ws_load(m, tet, ws); wsValid = true; }
+                    const int r = walk_filtered(m, ws, tet, P, disp, ty.hops);
                     if (r >= 0) {
                         tet = r;
                         P = xadd(P, disp);
                         continue;
                     }
+                    wsValid = false; // geometry registers are stale after a refused walk
                 }
                 ty.exact++;
                 tail_convex_exact(m, P, disp, vel, tet, w, sp.reflect, ty);

@@ -335,9 +335,10 @@ int cpf_mesh_download_neighbours(cpf_context *ctx, int *nbr)
 {
     if (!ctx || !ctx->have_mesh || !nbr) return fail(ctx, CPF_ERR_INVALID, "no mesh uploaded");
     cudaSetDevice(ctx->device);
-    std::vector<int4> l((size_t)ctx->nTets);
+    std::vector<int4> l2((size_t)ctx->nTets * 2), l((size_t)ctx->nTets);
     std::vector<uint16_t> code((size_t)ctx->nTets);
-    CPF_CUDA(ctx, cudaMemcpy(l.data(), ctx->d_tetl, sizeof(int4) * l.size(), cudaMemcpyDeviceToHost));
+    CPF_CUDA(ctx, cudaMemcpy(l2.data(), ctx->d_tetrec, sizeof(int4) * l2.size(), cudaMemcpyDeviceToHost));
+    for (size_t t = 0; t < l.size(); ++t) l[t] = l2[2 * t];
     CPF_CUDA(ctx, cudaMemcpy(code.data(), ctx->d_tetcode, sizeof(uint16_t) * code.size(), cudaMemcpyDeviceToHost));
     for (long long t = 0; t < ctx->nTets; ++t) {
         const int lk[4] = { l[(size_t)t].x, l[(size_t)t].y, l[(size_t)t].z, l[(size_t)t].w };

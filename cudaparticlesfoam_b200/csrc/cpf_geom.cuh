@@ -93,7 +93,7 @@ struct Tet {
 struct MeshView {
     const double4 *__restrict__ vpos; // [nVerts]
     const int4 *__restrict__ tetv;    // [nTets] sorted vertex ids
-    const int4 *__restrict__ tetl;    // [nTets] links
+    const int4 *__restrict__ tetrec;  // [nTets][2] {links, apex ids} (32 B, one 256-bit load)
     const uint16_t *__restrict__ tetcode;
     const int *__restrict__ tetcell;  // [nTets] or nullptr (cell = max vertex id - nPoints)
     const double *__restrict__ ucell; // [nCells][3]
@@ -112,7 +112,7 @@ CPF_DEV Tet load_tet(const MeshView &m, int t, int4 &vout)
 {
     Tet T;
     int4 v = ld_int4(m.tetv, t);
-    T.link = ld_int4(m.tetl, t);
+    T.link = ld_int4(m.tetrec, 2 * t);
     T.code = m.tetcode[t];
     T.P[0] = ld_vertex(m.vpos, v.x);
     T.P[1] = ld_vertex(m.vpos, v.y);
@@ -211,73 +211,161 @@ CPF_DEV void bary_exact(const Tet &T, D3 P, double w[4])
 }
 
 // ------------------------------------------------------------------------------------------------
-// FILTERED policy: walk the ORIGINAL segment P0 -> P0+d through the mesh with un-normalised
-// plane functions a_j + t*b_j (>= 0 inside), one approximate division per crossing, and refuse
-// (return -1) whenever any decision the reference takes is within the guard band:
-//   C1 entry/start point within guard of another face      C2 end point within guard of a face
-//   C3 exit point within guard of another face (edge/vertex grazing, ties of dT)
-//   a wall is reached, no consistent exit, or the reference's 50-tet cap is approached.
+// FILTERED policy.
+//
+// The walk carries the current tet's geometry in registers (WalkState): four vertex ids + positions
+// and, per register slot, the link and the "apex" vertex id of the neighbour across the face
+// opposite that slot.  Crossing a face replaces exactly one vertex, so a hop costs ONE memory round
+// (the neighbour's 32-byte record and its single new vertex, issued together) instead of the
+// reference's four dependent gathers, and a particle that stays in its tet costs no mesh load at
+// all when sub-steps are fused.
+//
+// Decisions use un-normalised plane functions a_j + t*b_j (>= 0 inside) of the ORIGINAL segment
+// P0 -> P0+d, and the walk refuses (CPF_NEED_EXACT) whenever a decision of the reference could
+// depend on rounding:
+//   C1 start/entry point within the guard band of another face
+//   C2 end point within the guard band of any face plane of the visited tet
+//   C3 exit point within the guard band of another face (edge/vertex grazing, ties of dT)
+//   a wall is reached, no consistent exit exists, or the reference's 50-tet cap is approached.
 // ------------------------------------------------------------------------------------------------
 #define CPF_NEED_EXACT (-1)
 
-CPF_DEV int walk_filtered(const MeshView &m, int tet0, D3 P0, D3 d, int &hops)
+// Register roles: slot 0 holds the vertex that entered last (the "apex": the entry face is the one
+// opposite slot 0), slots 1..3 the three vertices shared with the previous tet.  ord[q] is the slot
+// of role q's vertex in the tet's stored record (ascending vertex ids), so links and apex ids are
+// picked from the raw record on demand instead of being permuted on every hop.
+struct WalkState {
+    D3 X[4];
+    int4 link, apex; // raw record of the current tet (ascending-id order)
+    int ord[4];
+    int cell;
+};
+
+CPF_DEV void ld_rec(const int4 *__restrict__ rec, int t, int4 &link, int4 &apex)
 {
-    int cur = tet0, in_j = -1;
+    asm("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(link.x), "=r"(link.y), "=r"(link.z), "=r"(link.w), "=r"(apex.x), "=r"(apex.y), "=r"(apex.z), "=r"(apex.w)
+        : "l"(rec + 2ll * t));
+}
+
+CPF_DEV int sel4(int a, int b, int c, int d, int k)
+{
+    const int lo = (k & 1) ? b : a, hi = (k & 1) ? d : c;
+    return (k & 2) ? hi : lo;
+}
+CPF_DEV double dsel(bool c, double a, double b) { return c ? a : b; }
+
+// cold start: tet id -> full geometry (two dependent rounds: ids, then positions)
+CPF_DEV void ws_load(const MeshView &m, int tet, WalkState &ws)
+{
+    const int4 v = ld_int4(m.tetv, tet);
+    ld_rec(m.tetrec, tet, ws.link, ws.apex);
+    ws.X[0] = ld_vertex(m.vpos, v.x); ws.X[1] = ld_vertex(m.vpos, v.y);
+    ws.X[2] = ld_vertex(m.vpos, v.z); ws.X[3] = ld_vertex(m.vpos, v.w);
+    ws.ord[0] = 0; ws.ord[1] = 1; ws.ord[2] = 2; ws.ord[3] = 3;
+    ws.cell = m.tetcell ? 0 : v.w - m.nPoints;
+}
+
+// cross the face opposite role s (es = its record slot, link >= 0): one memory round
+CPF_DEV int ws_hop(const MeshView &m, WalkState &ws, int s, int es, int link)
+{
+    const int nid = sel4(ws.apex.x, ws.apex.y, ws.apex.z, ws.apex.w, es);
+    const int tet = link >> 2;
+    const int inj = link & 3; // record slot of the new apex inside the neighbour
+    ld_rec(m.tetrec, tet, ws.link, ws.apex);
+    const D3 Xn = ld_vertex(m.vpos, nid);
+    // kept vertices keep their relative id order: slot o of the old record -> (o minus the removed
+    // slot) -> (plus the inserted apex slot) in the neighbour's record
+    int no[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k = ws.ord[q] - (ws.ord[q] > es ? 1 : 0);
+        no[q] = k + (k >= inj ? 1 : 0);
+    }
+    // the previous apex (role 0) becomes one of the shared three: it takes the role that left
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+        const bool mv = (q == s);
+        ws.X[q].x = dsel(mv, ws.X[0].x, ws.X[q].x);
+        ws.X[q].y = dsel(mv, ws.X[0].y, ws.X[q].y);
+        ws.X[q].z = dsel(mv, ws.X[0].z, ws.X[q].z);
+        ws.ord[q] = mv ? no[0] : no[q];
+    }
+    ws.X[0] = Xn;
+    ws.ord[0] = inj;
+    if (!m.tetcell && nid >= m.nPoints) ws.cell = nid - m.nPoints; // a cell-centre vertex entered
+    return tet;
+}
+
+// ~2^-20 seed + two Newton steps: a few ulp, no branches (the IEEE division's slow path and its
+// divergence are not needed for a filtered decision)
+CPF_DEV double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
+// Walks from the tet held in ws (containing P0) along d.  Returns the final tet id (ws then holds
+// its geometry) or CPF_NEED_EXACT (ws is left somewhere along the way and must be reloaded).
+CPF_DEV int walk_filtered(const MeshView &m, WalkState &ws, int tet0, D3 P0, D3 d, unsigned &hops)
+{
+    int cur = tet0;
+    bool first = true; // the first tet has no entry face; afterwards it is the face opposite role 0
     double t_in = 0.0;
     for (int it = 0; it < 48; ++it) {
-        const int4 v = ld_int4(m.tetv, cur);
-        const int4 l = ld_int4(m.tetl, cur);
-        const D3 S0 = ld_vertex(m.vpos, v.x), S1 = ld_vertex(m.vpos, v.y), S2 = ld_vertex(m.vpos, v.z),
-                 S3 = ld_vertex(m.vpos, v.w);
         hops++;
-        const D3 e1{ S1.x - S0.x, S1.y - S0.y, S1.z - S0.z };
-        const D3 e2{ S2.x - S0.x, S2.y - S0.y, S2.z - S0.z };
-        const D3 e3{ S3.x - S0.x, S3.y - S0.y, S3.z - S0.z };
+        const D3 e1{ ws.X[1].x - ws.X[0].x, ws.X[1].y - ws.X[0].y, ws.X[1].z - ws.X[0].z };
+        const D3 e2{ ws.X[2].x - ws.X[0].x, ws.X[2].y - ws.X[0].y, ws.X[2].z - ws.X[0].z };
+        const D3 e3{ ws.X[3].x - ws.X[0].x, ws.X[3].y - ws.X[0].y, ws.X[3].z - ws.X[0].z };
         const D3 n1{ e2.y * e3.z - e2.z * e3.y, e2.z * e3.x - e2.x * e3.z, e2.x * e3.y - e2.y * e3.x };
         const D3 n2{ e3.y * e1.z - e3.z * e1.y, e3.z * e1.x - e3.x * e1.z, e3.x * e1.y - e3.y * e1.x };
         const D3 n3{ e1.y * e2.z - e1.z * e2.y, e1.z * e2.x - e1.x * e2.z, e1.x * e2.y - e1.y * e2.x };
-        double V6 = e1.x * n1.x + e1.y * n1.y + e1.z * n1.z;
-        const double sg = V6 < 0.0 ? -1.0 : 1.0;
-        const D3 r{ P0.x - S0.x, P0.y - S0.y, P0.z - S0.z };
+        const double V6s = e1.x * n1.x + e1.y * n1.y + e1.z * n1.z;
+        const double sg = V6s < 0.0 ? -1.0 : 1.0; // orientation: make "inside" positive
+        const D3 r{ P0.x - ws.X[0].x, P0.y - ws.X[0].y, P0.z - ws.X[0].z };
         double a[4], b[4];
         a[1] = sg * (r.x * n1.x + r.y * n1.y + r.z * n1.z);
         a[2] = sg * (r.x * n2.x + r.y * n2.y + r.z * n2.z);
         a[3] = sg * (r.x * n3.x + r.y * n3.y + r.z * n3.z);
-        V6 *= sg;
-        a[0] = V6 - a[1] - a[2] - a[3];
         b[1] = sg * (d.x * n1.x + d.y * n1.y + d.z * n1.z);
         b[2] = sg * (d.x * n2.x + d.y * n2.y + d.z * n2.z);
         b[3] = sg * (d.x * n3.x + d.y * n3.y + d.z * n3.z);
+        const double V6 = fabs(V6s);
+        a[0] = V6 - a[1] - a[2] - a[3];
         b[0] = -(b[1] + b[2] + b[3]);
         const double g = m.guard * V6;
         bool bad = false, allin = true;
-        double best = 2.0;
+        double as = 0.0, nbs = 1.0; // best exit so far: t = as/nbs
         int js = -1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const double e = a[j] + b[j];
-            if (j != in_j && fma(t_in, b[j], a[j]) < g) bad = true; // C1
-            if (fabs(e) < g) bad = true;                            // C2
-            if (e < 0.0) {
-                allin = false;
-                if (j != in_j && b[j] < 0.0) {
-                    const double t = a[j] / (-b[j]);
-                    if (t < best) { best = t; js = j; }
-                }
-            }
+            const bool notin = (j != 0) | first;
+            bad |= notin & (fma(t_in, b[j], a[j]) < g); // C1
+            bad |= fabs(e) < g;                         // C2
+            allin &= (e > 0.0);
+            const double nb = -b[j];
+            const bool cand = notin & (nb > 0.0) & (e < 0.0);
+            const bool better = cand & ((js < 0) | (a[j] * nbs < as * nb)); // t_j < t_best, no division
+            as = dsel(better, a[j], as);
+            nbs = dsel(better, nb, nbs);
+            js = better ? j : js;
         }
         if (bad) return CPF_NEED_EXACT;
         if (allin) return cur;
         if (js < 0) return CPF_NEED_EXACT;
+        const double t = as * fast_rcp(nbs);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j != js && fma(best, b[j], a[j]) < g) bad = true; // C3
-        if (bad || !(best - t_in >= 1e-9 * (1.0 - t_in)) || best > 1.0) return CPF_NEED_EXACT;
-        const int link = link_at(l, js);
-        if (link < 0) return CPF_NEED_EXACT; // wall: reflection / escape needs the exact hit point
-        cur = link >> 2;
-        in_j = link & 3;
-        t_in = best;
+        for (int j = 0; j < 4; ++j) bad |= (j != js) & (fma(t, b[j], a[j]) < g); // C3
+        const int es = sel4(ws.ord[0], ws.ord[1], ws.ord[2], ws.ord[3], js);
+        const int link = sel4(ws.link.x, ws.link.y, ws.link.z, ws.link.w, es);
+        if (bad | !(t - t_in >= 1e-9 * (1.0 - t_in)) | !(t <= 1.0) | (link < 0)) return CPF_NEED_EXACT; // incl. walls
+        cur = ws_hop(m, ws, js, es, link);
+        first = false;
+        t_in = t;
     }
     return CPF_NEED_EXACT;
 }

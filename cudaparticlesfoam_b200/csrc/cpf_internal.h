@@ -60,7 +60,7 @@ struct cpf_context {
     bool cellFromVertex = false;
     double4 *d_vpos = nullptr;
     int4 *d_tetv = nullptr;      // sorted ids
-    int4 *d_tetl = nullptr;      // links
+    int4 *d_tetrec = nullptr;    // [nTets][2]: {links, apex vertex id of the neighbour across each face}
     uint16_t *d_tetcode = nullptr;
     int *d_tetcell = nullptr;
     double *d_ucell[2] = { nullptr, nullptr }; // double-buffered cell field, solver layout [nCells][3]

@@ -98,8 +98,8 @@ __global__ void k_prepare_tets(long long nTets, const int4 *__restrict__ tetref,
 // One thread per sorted face entry: find the other tet with the same (a,b,c).
 __global__ void k_link_faces(long long nEntries, const unsigned long long *__restrict__ keys, const int *__restrict__ order,
                              const FaceEntry *__restrict__ entries, const uint16_t *__restrict__ tetcode,
-                             const int *__restrict__ tetPatch, int *__restrict__ links, unsigned *__restrict__ flags,
-                             unsigned long long *__restrict__ nBoundary)
+                             const int *__restrict__ tetPatch, const int4 *__restrict__ tetv, int *__restrict__ rec,
+                             unsigned *__restrict__ flags, unsigned long long *__restrict__ nBoundary)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nEntries) return;
@@ -116,7 +116,7 @@ __global__ void k_link_faces(long long nEntries, const unsigned long long *__res
     }
     const int t = me.tf >> 2, j = me.tf & 3;
     const unsigned code = tetcode[t];
-    int link;
+    int link, apex = -1;
     if (count == 0) {
         int patch = 0;
         if (tetPatch) {
@@ -131,8 +131,14 @@ __global__ void k_link_faces(long long nEntries, const unsigned long long *__res
         const unsigned ocode = tetcode[partner >> 2];
         if (((code >> (8 + j)) & 1u) == ((ocode >> (8 + (partner & 3))) & 1u)) atomicOr(flags, (unsigned)MF_ORIENTATION);
         link = partner;
+        // the one vertex of the neighbour that is not on the shared face: lets the walk fetch the
+        // next tet's record and its single new vertex in ONE memory round
+        const int4 ov = tetv[partner >> 2];
+        const int oj = partner & 3;
+        apex = oj == 0 ? ov.x : (oj == 1 ? ov.y : (oj == 2 ? ov.z : ov.w));
     }
-    links[4ll * t + j] = link;
+    rec[8ll * t + j] = link;
+    rec[8ll * t + 4 + j] = apex;
 }
 
 __global__ void k_pack_positions(long long n, const double *__restrict__ xyz, double4 *__restrict__ out)
@@ -154,9 +160,9 @@ int fail(cpf_context *ctx, int code, const char *fmt, ...)
 
 static void free_mesh(cpf_context *ctx)
 {
-    cudaFree(ctx->d_vpos); cudaFree(ctx->d_tetv); cudaFree(ctx->d_tetl); cudaFree(ctx->d_tetcode); cudaFree(ctx->d_tetcell);
+    cudaFree(ctx->d_vpos); cudaFree(ctx->d_tetv); cudaFree(ctx->d_tetrec); cudaFree(ctx->d_tetcode); cudaFree(ctx->d_tetcell);
     cudaFree(ctx->d_ucell[0]); cudaFree(ctx->d_ucell[1]); cudaFree(ctx->d_uvert); cudaFree(ctx->d_patch_kind);
-    ctx->d_vpos = nullptr; ctx->d_tetv = nullptr; ctx->d_tetl = nullptr; ctx->d_tetcode = nullptr; ctx->d_tetcell = nullptr;
+    ctx->d_vpos = nullptr; ctx->d_tetv = nullptr; ctx->d_tetrec = nullptr; ctx->d_tetcode = nullptr; ctx->d_tetcell = nullptr;
     ctx->d_ucell[0] = ctx->d_ucell[1] = nullptr; ctx->d_uvert = nullptr; ctx->d_patch_kind = nullptr;
     free_bvh(ctx);
     ctx->have_mesh = false;
@@ -195,7 +201,7 @@ int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, lon
     }
     CPF_CUDA(ctx, cudaMalloc(&ctx->d_vpos, sizeof(double4) * (size_t)nVerts));
     CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetv, sizeof(int4) * (size_t)nTets));
-    CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetl, sizeof(int4) * (size_t)nTets));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetrec, sizeof(int4) * 2 * (size_t)nTets));
     CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetcode, sizeof(uint16_t) * (size_t)nTets));
     for (int b = 0; b < 2; ++b) {
         CPF_CUDA(ctx, cudaMalloc(&ctx->d_ucell[b], sizeof(double) * 3 * (size_t)nCells));
@@ -238,7 +244,7 @@ int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, lon
     ctx->launches += 4;
 
     k_link_faces<<<(unsigned)((nE + 127) / 128), 128, 0, st>>>(nE, d_keys2, d_idx2, d_entries, ctx->d_tetcode, d_tetPatch,
-                                                              (int *)ctx->d_tetl, d_flags, d_nb);
+                                                              ctx->d_tetv, (int *)ctx->d_tetrec, d_flags, d_nb);
     ctx->launches++;
     CPF_CUDA(ctx, cudaGetLastError());
 
@@ -275,7 +281,7 @@ int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, lon
 MeshView mesh_view(const cpf_context *ctx)
 {
     MeshView m;
-    m.vpos = ctx->d_vpos; m.tetv = ctx->d_tetv; m.tetl = ctx->d_tetl; m.tetcode = ctx->d_tetcode;
+    m.vpos = ctx->d_vpos; m.tetv = ctx->d_tetv; m.tetrec = ctx->d_tetrec; m.tetcode = ctx->d_tetcode;
     m.tetcell = ctx->cellFromVertex ? nullptr : ctx->d_tetcell;
     m.ucell = ctx->d_ucell[ctx->ucur];
     m.uvert = ctx->d_uvert;
