@@ -10,10 +10,15 @@
 // fused, with the particle (position, flag, tet id) held in registers across the fused sub-steps:
 // one 256-bit load + one 32-bit load per particle per launch, the same back.  disp never touches
 // memory; vel is written only when the host can observe it (last sub-step of a call).
+#include <algorithm>
+
 #include "cpf_internal.h"
 
 #ifndef CPF_MIN_BLOCKS
 #define CPF_MIN_BLOCKS 4
+#endif
+#ifndef CPF_FAST_MIN_BLOCKS
+#define CPF_FAST_MIN_BLOCKS 5
 #endif
 #ifdef CPF_TAIL_NOINLINE
 #define CPF_TAIL __device__ __noinline__
@@ -224,13 +229,22 @@ CPF_TAIL void tail_bary_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &t
 // ------------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------------
-template <int LOC, bool FILT, int RNG>
+// QUEUED: the particles to process (and the sub-step each resumes at) come from the deferral queue
+// filled by k_fast; otherwise thread i handles particle i from sub-step 0.
+template <int LOC, bool FILT, int RNG, bool QUEUED>
 __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_substeps(const MeshView m, const ParticleView pv, const StepParams sp)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     Tally ty{ 0u, 0u, 0u, 0u };
     unsigned nsteps = 0;
-    if (i < pv.n) {
+    const long long nQueued = QUEUED ? (long long)*sp.queueCount : 0;
+    // QUEUED launches use a small fixed grid and stride over the queue
+    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; QUEUED ? slot < nQueued : true;
+         slot += (long long)gridDim.x * blockDim.x) {
+    long long i = slot;
+    int s0 = 0;
+    bool have = i < pv.n;
+    if (QUEUED) { const int2 q = sp.queue[slot]; i = q.x; s0 = q.y; have = true; }
+    if (have) {
         double4 p4 = ld_stream4(pv.pos + i);
         int tet = ld_stream_i(pv.tet + i);
         D3 P{ p4.x, p4.y, p4.z };
@@ -245,7 +259,7 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_substeps(const MeshView
             rng.open(pv, i, sp);
             if (FILT && tet >= 0) { ws_load(m, tet, ws); wsValid = true; }
         }
-        for (int s = 0; s < sp.nSub; ++s) {
+        for (int s = s0; s < sp.nSub; ++s) {
             if (w == 0.0) break;
             if (tet < 0) { w = 0.0; break; } // S1: left the domain -> frozen (particles.cu:334-338)
             // ---- S1 velocity + Euler displacement: disp = (P + dt*vel) - P
@@ -291,6 +305,8 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_substeps(const MeshView
             if (sp.writeVel && velValid) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
         }
     }
+    if (!QUEUED) break;
+    }
     // statistics: warp reduce, one atomic per warp and counter
     unsigned vals[5] = { ty.esc, ty.refl, ty.exact, ty.hops, nsteps };
 #pragma unroll
@@ -298,6 +314,74 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_substeps(const MeshView
         unsigned x = __reduce_add_sync(0xffffffffu, vals[c]);
         if ((threadIdx.x & 31) == 0 && x) atomicAdd(sp.counters + c, (unsigned long long)x);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fast: the lean main kernel of the filtered policy.  Same sub-step loop, but it contains no
+// exact-arithmetic code at all: the first sub-step whose walk is refused is NOT executed -- the
+// particle is written back as it was at the start of that sub-step and (particle, sub-step) is
+// appended to the deferral queue with one warp-aggregated atomic.  k_substeps<.., QUEUED> then
+// finishes the queued particles (exact path inline).  Keeping the rare exact path out of this
+// kernel is what lets it run at a higher occupancy (registers) and without its divergence.
+// ------------------------------------------------------------------------------------------------
+template <int RNG>
+__global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned hops = 0, nsteps = 0;
+    int deferAt = -1;
+    if (i < pv.n) {
+        const double4 p4 = ld_stream4(pv.pos + i);
+        int tet = ld_stream_i(pv.tet + i);
+        D3 P{ p4.x, p4.y, p4.z };
+        double w = p4.w;
+        int lastCell = -1;
+        if (w != 0.0) {
+            Rng<RNG> rng;
+            rng.open(pv, i, sp);
+            WalkState ws;
+            if (tet >= 0) ws_load(m, tet, ws);
+            for (int s = 0; s < sp.nSub; ++s) {
+                if (tet < 0) { w = 0.0; break; } // S1: left the domain -> frozen (particles.cu:334-338)
+                const int cell = m.tetcell ? __ldg(m.tetcell + tet) : ws.cell;
+                const double *uc = m.ucell + 3ll * cell;
+                const D3 vel{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+                D3 disp{ __dsub_rn(__fma_rn(sp.dt, vel.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, vel.y, P.y), P.y),
+                         __dsub_rn(__fma_rn(sp.dt, vel.z, P.z), P.z) };
+                double x0, x1, x2;
+                if (rng.draw(s, x0, x1, x2)) {
+                    disp.x = __fma_rn(x0, sp.randDisp, disp.x);
+                    disp.y = __fma_rn(x1, sp.randDisp, disp.y);
+                    disp.z = __fma_rn(x2, sp.randDisp, disp.z);
+                }
+                const int r = walk_filtered(m, ws, tet, P, disp, hops);
+                if (r < 0) { deferAt = s; break; }
+                tet = r;
+                P = xadd(P, disp);
+                lastCell = cell;
+                nsteps++;
+            }
+            st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
+            st_stream_i(pv.tet + i, tet);
+            if (sp.writeVel && lastCell >= 0 && deferAt < 0) {
+                const double *uc = m.ucell + 3ll * lastCell;
+                st_stream4(pv.vel + i, make_double4(__ldg(uc), __ldg(uc + 1), __ldg(uc + 2), -1.0));
+            }
+        }
+    }
+    // deferral queue: one atomic per warp
+    const unsigned mask = __ballot_sync(0xffffffffu, deferAt >= 0);
+    if (mask) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = (int)atomicAdd(sp.queueCount, (unsigned)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (deferAt >= 0) sp.queue[base + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
+    }
+    unsigned x = __reduce_add_sync(0xffffffffu, hops);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(sp.counters + CNT_HOPS, (unsigned long long)x);
+    x = __reduce_add_sync(0xffffffffu, nsteps);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(sp.counters + CNT_SUBSTEPS, (unsigned long long)x);
 }
 
 // src/initCuda.H:184-199: the one cudaAdvect right after seeding; its only lasting effect is to
@@ -341,9 +425,9 @@ template <int LOC, bool FILT> static void launch_rng(cpf_context *ctx, const Mes
                                                      const StepParams &sp, int rng, dim3 grid)
 {
     switch (rng) {
-    case CPF_RNG_XORWOW: k_substeps<LOC, FILT, CPF_RNG_XORWOW><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
-    case CPF_RNG_PHILOX: k_substeps<LOC, FILT, CPF_RNG_PHILOX><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
-    default: k_substeps<LOC, FILT, CPF_RNG_NONE><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
+    case CPF_RNG_XORWOW: k_substeps<LOC, FILT, CPF_RNG_XORWOW, false><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
+    case CPF_RNG_PHILOX: k_substeps<LOC, FILT, CPF_RNG_PHILOX, false><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
+    default: k_substeps<LOC, FILT, CPF_RNG_NONE, false><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
     }
 }
 
@@ -377,9 +461,24 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
         }
         CPF_CUDA(ctx, cudaEventRecord(ctx->profEvents[ctx->profUsed], ctx->stream));
     }
+    sp.queue = ctx->d_queue;
+    sp.queueCount = ctx->d_queue_count;
     if (ctx->cfg.locator == CPF_LOCATOR_BARY) launch_rng<CPF_LOCATOR_BARY, false>(ctx, m, pv, sp, rng, grid);
     else if (ctx->cfg.path == CPF_PATH_EXACT) launch_rng<CPF_LOCATOR_CONVEX, false>(ctx, m, pv, sp, rng, grid);
-    else launch_rng<CPF_LOCATOR_CONVEX, true>(ctx, m, pv, sp, rng, grid);
+    else if (rng == CPF_RNG_XORWOW) launch_rng<CPF_LOCATOR_CONVEX, true>(ctx, m, pv, sp, rng, grid); // stateful stream: no deferral
+    else {
+        // two-kernel filtered policy: lean fast kernel + queued finisher
+        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned), ctx->stream));
+        const dim3 qgrid(std::min<unsigned>(grid.x, 148u * 8u)); // the finisher strides over the queue
+        if (rng == CPF_RNG_PHILOX) {
+            k_fast<CPF_RNG_PHILOX><<<grid, 128, 0, ctx->stream>>>(m, pv, sp);
+            k_substeps<CPF_LOCATOR_CONVEX, true, CPF_RNG_PHILOX, true><<<qgrid, 128, 0, ctx->stream>>>(m, pv, sp);
+        } else {
+            k_fast<CPF_RNG_NONE><<<grid, 128, 0, ctx->stream>>>(m, pv, sp);
+            k_substeps<CPF_LOCATOR_CONVEX, true, CPF_RNG_NONE, true><<<qgrid, 128, 0, ctx->stream>>>(m, pv, sp);
+        }
+        ctx->launches++;
+    }
     if (ctx->profiling) {
         CPF_CUDA(ctx, cudaEventRecord(ctx->profEvents[ctx->profUsed + 1], ctx->stream));
         ctx->profUsed += 2;

@@ -32,6 +32,8 @@ struct StepParams {
     unsigned long long seed;
     unsigned long long step0; // global sub-step index of the first fused sub-step (Philox counter)
     unsigned long long *counters;
+    int2 *queue;            // deferral queue: (particle slot, sub-step to resume at)
+    unsigned *queueCount;
 };
 
 // BVH over tets for initial / lost-particle location (cpf_locate.cu)
@@ -97,6 +99,8 @@ struct cpf_context {
     size_t scratch_bytes = 0;
 
     unsigned long long *d_counters = nullptr;
+    int2 *d_queue = nullptr;          // [n] deferral queue of the two-kernel filtered policy
+    unsigned *d_queue_count = nullptr;
 };
 
 namespace cpf {
