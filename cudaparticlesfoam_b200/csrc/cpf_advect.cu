@@ -17,6 +17,9 @@
 #ifndef CPF_MIN_BLOCKS
 #define CPF_MIN_BLOCKS 4
 #endif
+#ifndef CPF_MAX_ROUNDS
+#define CPF_MAX_ROUNDS 3 /* exact<->fast ping-pong rounds before the exact finisher */
+#endif
 #ifndef CPF_FAST_MIN_BLOCKS
 #define CPF_FAST_MIN_BLOCKS 5
 #endif
@@ -227,161 +230,190 @@ CPF_TAIL void tail_bary_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &t
 }
 
 // ------------------------------------------------------------------------------------------------
-// the fused kernel
+// kernels
 // ------------------------------------------------------------------------------------------------
-// QUEUED: the particles to process (and the sub-step each resumes at) come from the deferral queue
-// filled by k_fast; otherwise thread i handles particle i from sub-step 0.
-template <int LOC, bool FILT, int RNG, bool QUEUED>
-__global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_substeps(const MeshView m, const ParticleView pv, const StepParams sp)
+// S1 + S2 of one sub-step: vel = U[cell]; disp = (P + dt*vel) - P (+ random walk)
+template <int RNG>
+CPF_DEV D3 displacement(const MeshView &m, const StepParams &sp, Rng<RNG> &rng, int s, int cell, const D3 &P, D3 &vel)
+{
+    const double *uc = m.ucell + 3ll * cell;
+    vel = D3{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+    D3 disp{ __dsub_rn(__fma_rn(sp.dt, vel.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, vel.y, P.y), P.y),
+             __dsub_rn(__fma_rn(sp.dt, vel.z, P.z), P.z) };
+    double x0, x1, x2;
+    if (rng.draw(s, x0, x1, x2)) {
+        disp.x = __fma_rn(x0, sp.randDisp, disp.x);
+        disp.y = __fma_rn(x1, sp.randDisp, disp.y);
+        disp.z = __fma_rn(x2, sp.randDisp, disp.z);
+    }
+    return disp;
+}
+
+CPF_DEV void flush_counters(const StepParams &sp, unsigned refl, unsigned exact, unsigned hops, unsigned nsteps)
+{
+    unsigned vals[5] = { 0u, refl, exact, hops, nsteps };
+#pragma unroll
+    for (int c = 1; c < 5; ++c) {
+        unsigned x = __reduce_add_sync(0xffffffffu, vals[c]);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(sp.counters + c, (unsigned long long)x);
+    }
+}
+
+// k_exact<LOC,RNG,QMODE>: sub-steps entirely in the reference's arithmetic.
+//   QMODE 0: thread i = particle i, all nSub sub-steps (CPF_PATH_EXACT cross-check mode, RTX build)
+//   QMODE 1: one sub-step per entry of the deferral queue; the entry is advanced to s+1 in place
+//   QMODE 2: entries of the deferral queue, all their remaining sub-steps (last round)
+template <int LOC, int RNG, int QMODE>
+__global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact(const MeshView m, const ParticleView pv, const StepParams sp)
 {
     Tally ty{ 0u, 0u, 0u, 0u };
     unsigned nsteps = 0;
-    const long long nQueued = QUEUED ? (long long)*sp.queueCount : 0;
-    // QUEUED launches use a small fixed grid and stride over the queue
-    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; QUEUED ? slot < nQueued : true;
-         slot += (long long)gridDim.x * blockDim.x) {
-    long long i = slot;
-    int s0 = 0;
-    bool have = i < pv.n;
-    if (QUEUED) { const int2 q = sp.queue[slot]; i = q.x; s0 = q.y; have = true; }
-    if (have) {
+    const long long total = QMODE ? (long long)*sp.countIn : pv.n;
+    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
+        long long i = slot;
+        int s0 = 0;
+        if (QMODE) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y; }
+        const int s1 = (QMODE == 1) ? min(s0 + 1, sp.nSub) : sp.nSub;
+        if (s0 >= s1) continue;
         double4 p4 = ld_stream4(pv.pos + i);
         int tet = ld_stream_i(pv.tet + i);
         D3 P{ p4.x, p4.y, p4.z };
         double w = p4.w;
+        if (w == 0.0) continue;
         D3 vel{ 0.0, 0.0, 0.0 };
         bool velValid = false;
         Rng<RNG> rng;
-        const bool live = (w != 0.0);
-        WalkState ws;
-        bool wsValid = false;
-        if (live) {
-            rng.open(pv, i, sp);
-            if (FILT && tet >= 0) { ws_load(m, tet, ws); wsValid = true; }
-        }
-        for (int s = s0; s < sp.nSub; ++s) {
+        rng.open(pv, i, sp);
+        for (int s = s0; s < s1; ++s) {
             if (w == 0.0) break;
             if (tet < 0) { w = 0.0; break; } // S1: left the domain -> frozen (particles.cu:334-338)
-            // ---- S1 velocity + Euler displacement: disp = (P + dt*vel) - P
-            int cell;
-            if (FILT && wsValid && !m.tetcell) cell = ws.cell;
-            else cell = tet_cell(m, tet, ld_int4(m.tetv, tet));
-            const double *uc = m.ucell + 3ll * cell;
-            vel = D3{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+            const int cell = tet_cell(m, tet, ld_int4(m.tetv, tet));
+            const D3 disp = displacement<RNG>(m, sp, rng, s, cell, P, vel);
             velValid = true;
-            D3 disp{ __dsub_rn(__fma_rn(sp.dt, vel.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, vel.y, P.y), P.y),
-                     __dsub_rn(__fma_rn(sp.dt, vel.z, P.z), P.z) };
-            // ---- S2 random walk: disp += xi * sqrt(2 D dt)
-            double x0, x1, x2;
-            if (rng.draw(s, x0, x1, x2)) {
-                disp.x = __fma_rn(x0, sp.randDisp, disp.x);
-                disp.y = __fma_rn(x1, sp.randDisp, disp.y);
-                disp.z = __fma_rn(x2, sp.randDisp, disp.z);
-            }
             nsteps++;
-            // ---- S3..S5
-            if (LOC == CPF_LOCATOR_CONVEX) {
-                if (FILT) {
-                    if (!wsValid) { ws_load(m, tet, ws); wsValid = true; }
-                    const int r = walk_filtered(m, ws, tet, P, disp, ty.hops);
-                    if (r >= 0) {
-                        tet = r;
-                        P = xadd(P, disp);
-                        continue;
-                    }
-                    wsValid = false; // geometry registers are stale after a refused walk
+            ty.exact++;
+            if (LOC == CPF_LOCATOR_CONVEX) tail_convex_exact(m, P, disp, vel, tet, w, sp.reflect, ty);
+            else tail_bary_exact(m, P, disp, vel, tet, sp.reflect, ty);
+        }
+        rng.close(pv, i);
+        st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
+        st_stream_i(pv.tet + i, tet);
+        if (sp.writeVel && velValid && s1 == sp.nSub) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
+        if (QMODE == 1) sp.queueIn[slot].y = s1;
+    }
+    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps);
+}
+
+// k_fast<RNG,QMODE>: the main kernel of the filtered policy (default ConvexPoly build).
+// fp32 guarded walk only -- no exact-arithmetic code, hence few registers and a high occupancy.
+// The first sub-step whose walk is refused is NOT executed: the particle is written back as it was
+// at the start of that sub-step and (particle, sub-step) is appended to the output queue with one
+// warp-aggregated atomic.  k_exact<..,1> performs that one sub-step exactly and this kernel, in
+// queue mode, resumes the particle.
+//   QMODE 0: thread i = particle i from sub-step 0      QMODE 2: entries of the input queue
+template <int RNG, int QMODE>
+__global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
+{
+    unsigned hops = 0, nsteps = 0;
+    const long long total = QMODE ? (long long)*sp.countIn : pv.n;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride) { // warp-uniform trip count
+        const long long slot = base + threadIdx.x;
+        int deferAt = -1;
+        long long i = slot;
+        int s0 = 0;
+        bool have = slot < total;
+        if (QMODE && have) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y; have = s0 < sp.nSub; }
+        if (have) {
+            const double4 p4 = ld_stream4(pv.pos + i);
+            int tet = ld_stream_i(pv.tet + i);
+            D3 P{ p4.x, p4.y, p4.z };
+            double w = p4.w;
+            if (w != 0.0) {
+                Rng<RNG> rng;
+                rng.open(pv, i, sp);
+                Fast32 f;
+                D3 O{ 0.0, 0.0, 0.0 };
+                int lastCell = -1;
+                if (tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
+                for (int s = s0; s < sp.nSub; ++s) {
+                    if (tet < 0) { w = 0.0; break; } // S1: left the domain -> frozen (particles.cu:334-338)
+                    const int cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
+                    D3 vel;
+                    const D3 disp = displacement<RNG>(m, sp, rng, s, cell, P, vel);
+                    const int r = walk_fast32(m, f, O, tet, P, disp, hops);
+                    if (r < 0) { deferAt = s; break; }
+                    tet = r;
+                    P = xadd(P, disp);
+                    lastCell = cell;
+                    nsteps++;
                 }
-                ty.exact++;
-                tail_convex_exact(m, P, disp, vel, tet, w, sp.reflect, ty);
-            } else {
-                ty.exact++;
-                tail_bary_exact(m, P, disp, vel, tet, sp.reflect, ty);
+                st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
+                st_stream_i(pv.tet + i, tet);
+                if (sp.writeVel && lastCell >= 0 && deferAt < 0) {
+                    const double *uc = m.ucell + 3ll * lastCell;
+                    st_stream4(pv.vel + i, make_double4(__ldg(uc), __ldg(uc + 1), __ldg(uc + 2), -1.0));
+                }
             }
         }
-        if (live) {
+        // deferral queue: one atomic per warp
+        const unsigned mask = __ballot_sync(0xffffffffu, deferAt >= 0);
+        if (mask) {
+            const int lane = threadIdx.x & 31;
+            int qb = 0;
+            if (lane == 0) qb = (int)atomicAdd(sp.countOut, (unsigned)__popc(mask));
+            qb = __shfl_sync(0xffffffffu, qb, 0);
+            if (deferAt >= 0) sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
+        }
+        if (!QMODE) break;
+    }
+    flush_counters(sp, 0u, 0u, hops, nsteps);
+}
+
+// k_fast_inline<RNG>: same fast walk with the exact tail inline (no queues).  Used for the stateful
+// XORWOW stream, whose generator state cannot be rewound for a deferred sub-step.
+template <int RNG>
+__global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_fast_inline(const MeshView m, const ParticleView pv, const StepParams sp)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    Tally ty{ 0u, 0u, 0u, 0u };
+    unsigned nsteps = 0;
+    if (i < pv.n) {
+        const double4 p4 = ld_stream4(pv.pos + i);
+        int tet = ld_stream_i(pv.tet + i);
+        D3 P{ p4.x, p4.y, p4.z };
+        double w = p4.w;
+        if (w != 0.0) {
+            Rng<RNG> rng;
+            rng.open(pv, i, sp);
+            Fast32 f;
+            D3 O{ 0.0, 0.0, 0.0 }, vel{ 0.0, 0.0, 0.0 };
+            bool velValid = false;
+            if (tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
+            for (int s = 0; s < sp.nSub; ++s) {
+                if (w == 0.0) break;
+                if (tet < 0) { w = 0.0; break; }
+                const int cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
+                const D3 disp = displacement<RNG>(m, sp, rng, s, cell, P, vel);
+                velValid = true;
+                nsteps++;
+                const int r = walk_fast32(m, f, O, tet, P, disp, ty.hops);
+                if (r >= 0) {
+                    tet = r;
+                    P = xadd(P, disp);
+                } else {
+                    ty.exact++;
+                    tail_convex_exact(m, P, disp, vel, tet, w, sp.reflect, ty);
+                    if (tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
+                }
+            }
             rng.close(pv, i);
             st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
             st_stream_i(pv.tet + i, tet);
             if (sp.writeVel && velValid) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
         }
     }
-    if (!QUEUED) break;
-    }
-    // statistics: warp reduce, one atomic per warp and counter
-    unsigned vals[5] = { ty.esc, ty.refl, ty.exact, ty.hops, nsteps };
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        unsigned x = __reduce_add_sync(0xffffffffu, vals[c]);
-        if ((threadIdx.x & 31) == 0 && x) atomicAdd(sp.counters + c, (unsigned long long)x);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_fast: the lean main kernel of the filtered policy.  Same sub-step loop, but it contains no
-// exact-arithmetic code at all: the first sub-step whose walk is refused is NOT executed -- the
-// particle is written back as it was at the start of that sub-step and (particle, sub-step) is
-// appended to the deferral queue with one warp-aggregated atomic.  k_substeps<.., QUEUED> then
-// finishes the queued particles (exact path inline).  Keeping the rare exact path out of this
-// kernel is what lets it run at a higher occupancy (registers) and without its divergence.
-// ------------------------------------------------------------------------------------------------
-template <int RNG>
-__global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned hops = 0, nsteps = 0;
-    int deferAt = -1;
-    if (i < pv.n) {
-        const double4 p4 = ld_stream4(pv.pos + i);
-        int tet = ld_stream_i(pv.tet + i);
-        D3 P{ p4.x, p4.y, p4.z };
-        double w = p4.w;
-        int lastCell = -1;
-        if (w != 0.0) {
-            Rng<RNG> rng;
-            rng.open(pv, i, sp);
-            WalkState ws;
-            if (tet >= 0) ws_load(m, tet, ws);
-            for (int s = 0; s < sp.nSub; ++s) {
-                if (tet < 0) { w = 0.0; break; } // S1: left the domain -> frozen (particles.cu:334-338)
-                const int cell = m.tetcell ? __ldg(m.tetcell + tet) : ws.cell;
-                const double *uc = m.ucell + 3ll * cell;
-                const D3 vel{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
-                D3 disp{ __dsub_rn(__fma_rn(sp.dt, vel.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, vel.y, P.y), P.y),
-                         __dsub_rn(__fma_rn(sp.dt, vel.z, P.z), P.z) };
-                double x0, x1, x2;
-                if (rng.draw(s, x0, x1, x2)) {
-                    disp.x = __fma_rn(x0, sp.randDisp, disp.x);
-                    disp.y = __fma_rn(x1, sp.randDisp, disp.y);
-                    disp.z = __fma_rn(x2, sp.randDisp, disp.z);
-                }
-                const int r = walk_filtered(m, ws, tet, P, disp, hops);
-                if (r < 0) { deferAt = s; break; }
-                tet = r;
-                P = xadd(P, disp);
-                lastCell = cell;
-                nsteps++;
-            }
-            st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
-            st_stream_i(pv.tet + i, tet);
-            if (sp.writeVel && lastCell >= 0 && deferAt < 0) {
-                const double *uc = m.ucell + 3ll * lastCell;
-                st_stream4(pv.vel + i, make_double4(__ldg(uc), __ldg(uc + 1), __ldg(uc + 2), -1.0));
-            }
-        }
-    }
-    // deferral queue: one atomic per warp
-    const unsigned mask = __ballot_sync(0xffffffffu, deferAt >= 0);
-    if (mask) {
-        const int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == 0) base = (int)atomicAdd(sp.queueCount, (unsigned)__popc(mask));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (deferAt >= 0) sp.queue[base + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
-    }
-    unsigned x = __reduce_add_sync(0xffffffffu, hops);
-    if ((threadIdx.x & 31) == 0 && x) atomicAdd(sp.counters + CNT_HOPS, (unsigned long long)x);
-    x = __reduce_add_sync(0xffffffffu, nsteps);
-    if ((threadIdx.x & 31) == 0 && x) atomicAdd(sp.counters + CNT_SUBSTEPS, (unsigned long long)x);
+    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps);
 }
 
 // src/initCuda.H:184-199: the one cudaAdvect right after seeding; its only lasting effect is to
@@ -421,15 +453,12 @@ template <int RNG> __global__ void k_debug_normals(const ParticleView pv, const 
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-template <int LOC, bool FILT> static void launch_rng(cpf_context *ctx, const MeshView &m, const ParticleView &pv,
-                                                     const StepParams &sp, int rng, dim3 grid)
-{
-    switch (rng) {
-    case CPF_RNG_XORWOW: k_substeps<LOC, FILT, CPF_RNG_XORWOW, false><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
-    case CPF_RNG_PHILOX: k_substeps<LOC, FILT, CPF_RNG_PHILOX, false><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
-    default: k_substeps<LOC, FILT, CPF_RNG_NONE, false><<<grid, 128, 0, ctx->stream>>>(m, pv, sp); break;
+#define CPF_RNG_SWITCH(rng, CALL)                                              \
+    switch (rng) {                                                             \
+    case CPF_RNG_XORWOW: { constexpr int R = CPF_RNG_XORWOW; CALL; } break;     \
+    case CPF_RNG_PHILOX: { constexpr int R = CPF_RNG_PHILOX; CALL; } break;     \
+    default: { constexpr int R = CPF_RNG_NONE; CALL; } break;                   \
     }
-}
 
 int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
 {
@@ -445,11 +474,14 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
     sp.seed = ctx->cfg.seed;
     sp.step0 = ctx->step_index;
     sp.counters = ctx->d_counters;
-    int rng = ctx->cfg.rng;
+    sp.queueIn = sp.queueOut = nullptr;
+    sp.countIn = sp.countOut = nullptr;
+    const int rng = ctx->cfg.rng;
     if (rng == CPF_RNG_XORWOW && !ctx->rng_ready) {
         int rc = launch_init_rng(ctx);
         if (rc) return rc;
     }
+    cudaStream_t st = ctx->stream;
     const dim3 grid((unsigned)((ctx->n + 127) / 128));
     if (ctx->profiling) {
         if (ctx->profUsed + 2 > ctx->profEvents.size()) {
@@ -459,31 +491,51 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
             ctx->profEvents.push_back(a);
             ctx->profEvents.push_back(b);
         }
-        CPF_CUDA(ctx, cudaEventRecord(ctx->profEvents[ctx->profUsed], ctx->stream));
+        CPF_CUDA(ctx, cudaEventRecord(ctx->profEvents[ctx->profUsed], st));
     }
-    sp.queue = ctx->d_queue;
-    sp.queueCount = ctx->d_queue_count;
-    if (ctx->cfg.locator == CPF_LOCATOR_BARY) launch_rng<CPF_LOCATOR_BARY, false>(ctx, m, pv, sp, rng, grid);
-    else if (ctx->cfg.path == CPF_PATH_EXACT) launch_rng<CPF_LOCATOR_CONVEX, false>(ctx, m, pv, sp, rng, grid);
-    else if (rng == CPF_RNG_XORWOW) launch_rng<CPF_LOCATOR_CONVEX, true>(ctx, m, pv, sp, rng, grid); // stateful stream: no deferral
-    else {
-        // two-kernel filtered policy: lean fast kernel + queued finisher
-        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned), ctx->stream));
-        const dim3 qgrid(std::min<unsigned>(grid.x, 148u * 8u)); // the finisher strides over the queue
-        if (rng == CPF_RNG_PHILOX) {
-            k_fast<CPF_RNG_PHILOX><<<grid, 128, 0, ctx->stream>>>(m, pv, sp);
-            k_substeps<CPF_LOCATOR_CONVEX, true, CPF_RNG_PHILOX, true><<<qgrid, 128, 0, ctx->stream>>>(m, pv, sp);
-        } else {
-            k_fast<CPF_RNG_NONE><<<grid, 128, 0, ctx->stream>>>(m, pv, sp);
-            k_substeps<CPF_LOCATOR_CONVEX, true, CPF_RNG_NONE, true><<<qgrid, 128, 0, ctx->stream>>>(m, pv, sp);
+    if (ctx->cfg.locator == CPF_LOCATOR_BARY) {
+        CPF_RNG_SWITCH(rng, (k_exact<CPF_LOCATOR_BARY, R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
+        ctx->launches++;
+    } else if (ctx->cfg.path == CPF_PATH_EXACT) {
+        CPF_RNG_SWITCH(rng, (k_exact<CPF_LOCATOR_CONVEX, R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
+        ctx->launches++;
+    } else if (rng == CPF_RNG_XORWOW) {
+        k_fast_inline<CPF_RNG_XORWOW><<<grid, 128, 0, st>>>(m, pv, sp);
+        ctx->launches++;
+    } else {
+        // filtered policy: lean fast kernel -> [one exact sub-step -> resume fast]* -> exact finisher
+        const int rounds = std::min(CPF_MAX_ROUNDS, nSub - 1);
+        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * (CPF_MAX_ROUNDS + 2), st));
+        const dim3 qgrid(std::min<unsigned>(grid.x, 148u * 8u));
+        StepParams a = sp;
+        a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
+        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0><<<grid, 128, 0, st>>>(m, pv, a);
+        else k_fast<CPF_RNG_NONE, 0><<<grid, 128, 0, st>>>(m, pv, a);
+        ctx->launches++;
+        for (int r = 0; r < rounds; ++r) {
+            StepParams e = sp, b = sp;
+            e.queueIn = ctx->d_queue[r & 1]; e.countIn = ctx->d_queue_count + r;
+            b.queueIn = e.queueIn; b.countIn = e.countIn;
+            b.queueOut = ctx->d_queue[(r + 1) & 1]; b.countOut = ctx->d_queue_count + r + 1;
+            if (rng == CPF_RNG_PHILOX) {
+                k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_PHILOX, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
+                k_fast<CPF_RNG_PHILOX, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
+            } else {
+                k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_NONE, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
+                k_fast<CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
+            }
+            ctx->launches += 2;
         }
+        StepParams z = sp;
+        z.queueIn = ctx->d_queue[rounds & 1]; z.countIn = ctx->d_queue_count + rounds;
+        if (rng == CPF_RNG_PHILOX) k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_PHILOX, 2><<<qgrid, 128, 0, st>>>(m, pv, z);
+        else k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, z);
         ctx->launches++;
     }
     if (ctx->profiling) {
-        CPF_CUDA(ctx, cudaEventRecord(ctx->profEvents[ctx->profUsed + 1], ctx->stream));
+        CPF_CUDA(ctx, cudaEventRecord(ctx->profEvents[ctx->profUsed + 1], st));
         ctx->profUsed += 2;
     }
-    ctx->launches++;
     ctx->step_index += (unsigned long long)nSub;
     CPF_CUDA(ctx, cudaGetLastError());
     return CPF_OK;

@@ -37,7 +37,8 @@ static void free_particles(cpf_context *ctx)
         cudaFree(ctx->d_pos[b]); cudaFree(ctx->d_tet[b]); cudaFree(ctx->d_pid[b]); cudaFree(ctx->d_vel[b]); cudaFree(ctx->d_rng[b]);
         ctx->d_pos[b] = nullptr; ctx->d_tet[b] = nullptr; ctx->d_pid[b] = nullptr; ctx->d_vel[b] = nullptr; ctx->d_rng[b] = nullptr;
     }
-    cudaFree(ctx->d_queue); cudaFree(ctx->d_queue_count); ctx->d_queue = nullptr; ctx->d_queue_count = nullptr;
+    cudaFree(ctx->d_queue[0]); cudaFree(ctx->d_queue[1]); cudaFree(ctx->d_queue_count);
+    ctx->d_queue[0] = ctx->d_queue[1] = nullptr; ctx->d_queue_count = nullptr;
     ctx->n = 0; ctx->pcur = 0; ctx->permuted = false; ctx->rng_ready = false; ctx->have_tets = false;
 }
 
@@ -59,8 +60,9 @@ static int alloc_particles(cpf_context *ctx, long long n)
         CPF_CUDA(ctx, cudaMalloc(&ctx->d_vel[b], sizeof(double4) * (size_t)n));
         CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_vel[b], 0, sizeof(double4) * (size_t)n, ctx->stream));
     }
-    CPF_CUDA(ctx, cudaMalloc(&ctx->d_queue, sizeof(int2) * (size_t)n));
-    CPF_CUDA(ctx, cudaMalloc(&ctx->d_queue_count, sizeof(unsigned)));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_queue[0], sizeof(int2) * (size_t)n));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_queue[1], sizeof(int2) * (size_t)n));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_queue_count, sizeof(unsigned) * 16));
     ctx->n = n;
     k_iota_fill<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->d_pid[0], ctx->d_tet[0]);
     ctx->launches++;

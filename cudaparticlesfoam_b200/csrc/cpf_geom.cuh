@@ -6,9 +6,10 @@
 //    round-to-nearest intrinsics so that no compiler decision can change a bit.  Follows
 //    third_party/RTXAdvect/cuda/DeviceTetMesh.cuh:82-156,193-199, query/ConvexQuery.cu:32-131,
 //    239-317, query/RTQuery.cu:35-107 and owl/common/math/vec.h:317-345 of the reference.
-//  * FILTERED: cheap un-normalised predicates with guard bands; whenever a decision of the
-//    reference could depend on rounding (or a wall is touched) it reports NEED_EXACT and the
-//    caller re-runs the sub-step with the EXACT policy, so results stay bit-identical.
+//  * FILTERED: cheap un-normalised fp32 predicates with a rigorous error bound and guard band;
+//    whenever a decision of the reference could depend on rounding (or a wall is touched) the walk
+//    reports NEED_EXACT and the sub-step is redone with the EXACT policy, so results stay
+//    bit-identical to the reference.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -94,6 +95,7 @@ struct MeshView {
     const double4 *__restrict__ vpos; // [nVerts]
     const int4 *__restrict__ tetv;    // [nTets] sorted vertex ids
     const int4 *__restrict__ tetrec;  // [nTets][2] {links, apex ids} (32 B, one 256-bit load)
+    const uint4 *__restrict__ tetfast; // [nTets][4] 64-byte fp32 record of the fast walk (see Fast32)
     const uint16_t *__restrict__ tetcode;
     const int *__restrict__ tetcell;  // [nTets] or nullptr (cell = max vertex id - nPoints)
     const double *__restrict__ ucell; // [nCells][3]
@@ -210,162 +212,119 @@ CPF_DEV void bary_exact(const Tet &T, D3 P, double w[4])
     w[3] = __dsub_rn(__dsub_rn(__dsub_rn(1.0, w[0]), w[1]), w[2]);
 }
 
-// ------------------------------------------------------------------------------------------------
-// FILTERED policy.
-//
-// The walk carries the current tet's geometry in registers (WalkState): four vertex ids + positions
-// and, per register slot, the link and the "apex" vertex id of the neighbour across the face
-// opposite that slot.  Crossing a face replaces exactly one vertex, so a hop costs ONE memory round
-// (the neighbour's 32-byte record and its single new vertex, issued together) instead of the
-// reference's four dependent gathers, and a particle that stays in its tet costs no mesh load at
-// all when sub-steps are fused.
-//
-// Decisions use un-normalised plane functions a_j + t*b_j (>= 0 inside) of the ORIGINAL segment
-// P0 -> P0+d, and the walk refuses (CPF_NEED_EXACT) whenever a decision of the reference could
-// depend on rounding:
-//   C1 start/entry point within the guard band of another face
-//   C2 end point within the guard band of any face plane of the visited tet
-//   C3 exit point within the guard band of another face (edge/vertex grazing, ties of dT)
-//   a wall is reached, no consistent exit exists, or the reference's 50-tet cap is approached.
-// ------------------------------------------------------------------------------------------------
 #define CPF_NEED_EXACT (-1)
-
-// Register roles: slot 0 holds the vertex that entered last (the "apex": the entry face is the one
-// opposite slot 0), slots 1..3 the three vertices shared with the previous tet.  ord[q] is the slot
-// of role q's vertex in the tet's stored record (ascending vertex ids), so links and apex ids are
-// picked from the raw record on demand instead of being permuted on every hop.
-struct WalkState {
-    D3 X[4];
-    int4 link, apex; // raw record of the current tet (ascending-id order)
-    int ord[4];
-    int cell;
-};
-
-CPF_DEV void ld_rec(const int4 *__restrict__ rec, int t, int4 &link, int4 &apex)
-{
-    asm("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=r"(link.x), "=r"(link.y), "=r"(link.z), "=r"(link.w), "=r"(apex.x), "=r"(apex.y), "=r"(apex.z), "=r"(apex.w)
-        : "l"(rec + 2ll * t));
-}
 
 CPF_DEV int sel4(int a, int b, int c, int d, int k)
 {
     const int lo = (k & 1) ? b : a, hi = (k & 1) ? d : c;
     return (k & 2) ? hi : lo;
 }
-CPF_DEV double dsel(bool c, double a, double b) { return c ? a : b; }
 
-// cold start: tet id -> full geometry (two dependent rounds: ids, then positions)
-CPF_DEV void ws_load(const MeshView &m, int tet, WalkState &ws)
-{
-    const int4 v = ld_int4(m.tetv, tet);
-    ld_rec(m.tetrec, tet, ws.link, ws.apex);
-    ws.X[0] = ld_vertex(m.vpos, v.x); ws.X[1] = ld_vertex(m.vpos, v.y);
-    ws.X[2] = ld_vertex(m.vpos, v.z); ws.X[3] = ld_vertex(m.vpos, v.w);
-    ws.ord[0] = 0; ws.ord[1] = 1; ws.ord[2] = 2; ws.ord[3] = 3;
-    ws.cell = m.tetcell ? 0 : v.w - m.nPoints;
-}
+// ------------------------------------------------------------------------------------------------
+// fp32 fast walk (k_fast).
+//
+// One self-contained 64-byte record per tet: links, the three lower-id vertices as fp32 offsets
+// from the tet's highest-id vertex (the "origin": for OpenFOAM decompositions the cell centre, so
+// all 12 tets of a cell share it), the origin's vertex id, 6*volume and the largest |offset|.
+// A hop is ONE 64-byte load; the fp64 origin position is fetched only when the walk enters
+// another cell.  All predicates run on the fp32 pipe.  Soundness: every comparison is made against
+// g = G*|V6| + ERR, where ERR = 2^-16 * E^2 * (E + 3(|r|+|d|)) bounds the rounding of the inputs
+// (offsets, r, d: one rounding each, relative 2^-24) and of the ~10 float operations behind each
+// plane function (|a_j| <= 6|r|E^2, see DESIGN.md "fp32 filter"); a wrongly chosen exit is caught
+// by C3.  Whatever fails the test is deferred to the exact kernel, so results stay bit-identical.
+// ------------------------------------------------------------------------------------------------
+struct Fast32 {
+    int4 link;
+    float X[3][3];
+    int origin;
+    float V6, E;
+};
 
-// cross the face opposite role s (es = its record slot, link >= 0): one memory round
-CPF_DEV int ws_hop(const MeshView &m, WalkState &ws, int s, int es, int link)
+CPF_DEV void f32_load(const MeshView &m, int tet, Fast32 &f)
 {
-    const int nid = sel4(ws.apex.x, ws.apex.y, ws.apex.z, ws.apex.w, es);
-    const int tet = link >> 2;
-    const int inj = link & 3; // record slot of the new apex inside the neighbour
-    ld_rec(m.tetrec, tet, ws.link, ws.apex);
-    const D3 Xn = ld_vertex(m.vpos, nid);
-    // kept vertices keep their relative id order: slot o of the old record -> (o minus the removed
-    // slot) -> (plus the inserted apex slot) in the neighbour's record
-    int no[4];
+    unsigned w[16];
+    const uint4 *p = m.tetfast + 4ll * tet;
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "l"(p + 2));
+    f.link = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int k = ws.ord[q] - (ws.ord[q] > es ? 1 : 0);
-        no[q] = k + (k >= inj ? 1 : 0);
-    }
-    // the previous apex (role 0) becomes one of the shared three: it takes the role that left
+    for (int k = 0; k < 3; ++k)
 #pragma unroll
-    for (int q = 1; q < 4; ++q) {
-        const bool mv = (q == s);
-        ws.X[q].x = dsel(mv, ws.X[0].x, ws.X[q].x);
-        ws.X[q].y = dsel(mv, ws.X[0].y, ws.X[q].y);
-        ws.X[q].z = dsel(mv, ws.X[0].z, ws.X[q].z);
-        ws.ord[q] = mv ? no[0] : no[q];
-    }
-    ws.X[0] = Xn;
-    ws.ord[0] = inj;
-    if (!m.tetcell && nid >= m.nPoints) ws.cell = nid - m.nPoints; // a cell-centre vertex entered
-    return tet;
+        for (int c = 0; c < 3; ++c) f.X[k][c] = __uint_as_float(w[4 + 3 * k + c]);
+    f.origin = (int)w[13];
+    f.V6 = __uint_as_float(w[14]);
+    f.E = __uint_as_float(w[15]);
 }
 
-// ~2^-20 seed + two Newton steps: a few ulp, no branches (the IEEE division's slow path and its
-// divergence are not needed for a filtered decision)
-CPF_DEV double fast_rcp(double x)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    return r;
-}
+CPF_DEV float fsel(bool c, float a, float b) { return c ? a : b; }
 
-// Walks from the tet held in ws (containing P0) along d.  Returns the final tet id (ws then holds
-// its geometry) or CPF_NEED_EXACT (ws is left somewhere along the way and must be reloaded).
-CPF_DEV int walk_filtered(const MeshView &m, WalkState &ws, int tet0, D3 P0, D3 d, unsigned &hops)
+// Returns the final tet (f then holds its record, O its origin) or CPF_NEED_EXACT.
+CPF_DEV int walk_fast32(const MeshView &m, Fast32 &f, D3 &O, int tet0, D3 P0, D3 disp, unsigned &hops)
 {
-    int cur = tet0;
-    bool first = true; // the first tet has no entry face; afterwards it is the face opposite role 0
-    double t_in = 0.0;
+    float rx = (float)(P0.x - O.x), ry = (float)(P0.y - O.y), rz = (float)(P0.z - O.z);
+    const float dx = (float)disp.x, dy = (float)disp.y, dz = (float)disp.z;
+    const float Dd = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+    float Rr = fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz));
+    const float G = (float)m.guard;
+    int cur = tet0, in_j = -1;
+    float t_in = 0.f;
     for (int it = 0; it < 48; ++it) {
         hops++;
-        const D3 e1{ ws.X[1].x - ws.X[0].x, ws.X[1].y - ws.X[0].y, ws.X[1].z - ws.X[0].z };
-        const D3 e2{ ws.X[2].x - ws.X[0].x, ws.X[2].y - ws.X[0].y, ws.X[2].z - ws.X[0].z };
-        const D3 e3{ ws.X[3].x - ws.X[0].x, ws.X[3].y - ws.X[0].y, ws.X[3].z - ws.X[0].z };
-        const D3 n1{ e2.y * e3.z - e2.z * e3.y, e2.z * e3.x - e2.x * e3.z, e2.x * e3.y - e2.y * e3.x };
-        const D3 n2{ e3.y * e1.z - e3.z * e1.y, e3.z * e1.x - e3.x * e1.z, e3.x * e1.y - e3.y * e1.x };
-        const D3 n3{ e1.y * e2.z - e1.z * e2.y, e1.z * e2.x - e1.x * e2.z, e1.x * e2.y - e1.y * e2.x };
-        const double V6s = e1.x * n1.x + e1.y * n1.y + e1.z * n1.z;
-        const double sg = V6s < 0.0 ? -1.0 : 1.0; // orientation: make "inside" positive
-        const D3 r{ P0.x - ws.X[0].x, P0.y - ws.X[0].y, P0.z - ws.X[0].z };
-        double a[4], b[4];
-        a[1] = sg * (r.x * n1.x + r.y * n1.y + r.z * n1.z);
-        a[2] = sg * (r.x * n2.x + r.y * n2.y + r.z * n2.z);
-        a[3] = sg * (r.x * n3.x + r.y * n3.y + r.z * n3.z);
-        b[1] = sg * (d.x * n1.x + d.y * n1.y + d.z * n1.z);
-        b[2] = sg * (d.x * n2.x + d.y * n2.y + d.z * n2.z);
-        b[3] = sg * (d.x * n3.x + d.y * n3.y + d.z * n3.z);
-        const double V6 = fabs(V6s);
-        a[0] = V6 - a[1] - a[2] - a[3];
-        b[0] = -(b[1] + b[2] + b[3]);
-        const double g = m.guard * V6;
-        bool bad = false, allin = true;
-        double as = 0.0, nbs = 1.0; // best exit so far: t = as/nbs
+        const float (&X)[3][3] = f.X;
+        // un-normalised normals of the faces opposite slots 0,1,2 (the origin is slot 3)
+        const float n0x = X[1][1] * X[2][2] - X[1][2] * X[2][1], n0y = X[1][2] * X[2][0] - X[1][0] * X[2][2], n0z = X[1][0] * X[2][1] - X[1][1] * X[2][0];
+        const float n1x = X[2][1] * X[0][2] - X[2][2] * X[0][1], n1y = X[2][2] * X[0][0] - X[2][0] * X[0][2], n1z = X[2][0] * X[0][1] - X[2][1] * X[0][0];
+        const float n2x = X[0][1] * X[1][2] - X[0][2] * X[1][1], n2y = X[0][2] * X[1][0] - X[0][0] * X[1][2], n2z = X[0][0] * X[1][1] - X[0][1] * X[1][0];
+        const float sg = f.V6 < 0.f ? -1.f : 1.f;
+        const float V = fabsf(f.V6);
+        float a[4], b[4];
+        a[0] = sg * (rx * n0x + ry * n0y + rz * n0z);
+        a[1] = sg * (rx * n1x + ry * n1y + rz * n1z);
+        a[2] = sg * (rx * n2x + ry * n2y + rz * n2z);
+        b[0] = sg * (dx * n0x + dy * n0y + dz * n0z);
+        b[1] = sg * (dx * n1x + dy * n1y + dz * n1z);
+        b[2] = sg * (dx * n2x + dy * n2y + dz * n2z);
+        a[3] = V - a[0] - a[1] - a[2];
+        b[3] = -(b[0] + b[1] + b[2]);
+        const float E = f.E;
+        const float g = G * V + 1.52587890625e-5f * (E * E) * (E + 3.f * (Rr + Dd));
+        bool bad = !(V > 1e-30f), allin = true;
+        float as = 0.f, nbs = 1.f;
         int js = -1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const double e = a[j] + b[j];
-            const bool notin = (j != 0) | first;
-            bad |= notin & (fma(t_in, b[j], a[j]) < g); // C1
-            bad |= fabs(e) < g;                         // C2
-            allin &= (e > 0.0);
-            const double nb = -b[j];
-            const bool cand = notin & (nb > 0.0) & (e < 0.0);
-            const bool better = cand & ((js < 0) | (a[j] * nbs < as * nb)); // t_j < t_best, no division
-            as = dsel(better, a[j], as);
-            nbs = dsel(better, nb, nbs);
+            const float e = a[j] + b[j];
+            const bool notin = (j != in_j);
+            bad |= notin & (fmaf(t_in, b[j], a[j]) < g); // C1
+            bad |= fabsf(e) < g;                         // C2
+            allin &= (e > 0.f);
+            const float nb = -b[j];
+            const bool cand = notin & (nb > 0.f) & (e < 0.f);
+            const bool better = cand & ((js < 0) | (a[j] * nbs < as * nb));
+            as = fsel(better, a[j], as);
+            nbs = fsel(better, nb, nbs);
             js = better ? j : js;
         }
         if (bad) return CPF_NEED_EXACT;
         if (allin) return cur;
         if (js < 0) return CPF_NEED_EXACT;
-        const double t = as * fast_rcp(nbs);
+        const float t = __fdividef(as, nbs);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bad |= (j != js) & (fma(t, b[j], a[j]) < g); // C3
-        const int es = sel4(ws.ord[0], ws.ord[1], ws.ord[2], ws.ord[3], js);
-        const int link = sel4(ws.link.x, ws.link.y, ws.link.z, ws.link.w, es);
-        if (bad | !(t - t_in >= 1e-9 * (1.0 - t_in)) | !(t <= 1.0) | (link < 0)) return CPF_NEED_EXACT; // incl. walls
-        cur = ws_hop(m, ws, js, es, link);
-        first = false;
+        for (int j = 0; j < 4; ++j) bad |= (j != js) & (fmaf(t, b[j], a[j]) < g); // C3
+        const int link = sel4(f.link.x, f.link.y, f.link.z, f.link.w, js);
+        if (bad | !(t > t_in) | !(t <= 1.f) | (link < 0)) return CPF_NEED_EXACT; // incl. walls
+        cur = link >> 2;
+        in_j = link & 3;
         t_in = t;
+        const int oldOrigin = f.origin;
+        f32_load(m, cur, f);
+        if (f.origin != oldOrigin) { // entered another cell: re-express the start point
+            O = ld_vertex(m.vpos, f.origin);
+            rx = (float)(P0.x - O.x); ry = (float)(P0.y - O.y); rz = (float)(P0.z - O.z);
+            Rr = fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz));
+        }
     }
     return CPF_NEED_EXACT;
 }

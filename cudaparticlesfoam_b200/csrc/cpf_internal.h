@@ -32,8 +32,8 @@ struct StepParams {
     unsigned long long seed;
     unsigned long long step0; // global sub-step index of the first fused sub-step (Philox counter)
     unsigned long long *counters;
-    int2 *queue;            // deferral queue: (particle slot, sub-step to resume at)
-    unsigned *queueCount;
+    int2 *queueIn, *queueOut;          // deferral queues: (particle slot, sub-step to resume at)
+    unsigned *countIn, *countOut;
 };
 
 // BVH over tets for initial / lost-particle location (cpf_locate.cu)
@@ -62,6 +62,7 @@ struct cpf_context {
     bool cellFromVertex = false;
     double4 *d_vpos = nullptr;
     int4 *d_tetv = nullptr;      // sorted ids
+    uint4 *d_tetfast = nullptr;  // [nTets][4]: 64-byte fp32 record of the fast walk
     int4 *d_tetrec = nullptr;    // [nTets][2]: {links, apex vertex id of the neighbour across each face}
     uint16_t *d_tetcode = nullptr;
     int *d_tetcell = nullptr;
@@ -99,8 +100,8 @@ struct cpf_context {
     size_t scratch_bytes = 0;
 
     unsigned long long *d_counters = nullptr;
-    int2 *d_queue = nullptr;          // [n] deferral queue of the two-kernel filtered policy
-    unsigned *d_queue_count = nullptr;
+    int2 *d_queue[2] = { nullptr, nullptr }; // [n] ping-pong deferral queues of the filtered policy
+    unsigned *d_queue_count = nullptr;       // one counter per round
 };
 
 namespace cpf {

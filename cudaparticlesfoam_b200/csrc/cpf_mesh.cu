@@ -141,6 +141,37 @@ __global__ void k_link_faces(long long nEntries, const unsigned long long *__res
     rec[8ll * t + 4 + j] = apex;
 }
 
+// fp32 fast record (cpf_geom.cuh Fast32): offsets of the three lower-id vertices from the highest-id
+// vertex, computed in fp64 and rounded once.
+__global__ void k_build_fast(long long nTets, const int4 *__restrict__ tetv, const double4 *__restrict__ vpos,
+                             const int4 *__restrict__ tetrec, uint4 *__restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTets) return;
+    const int4 v = tetv[t];
+    const int4 l = tetrec[2 * t];
+    const D3 O = ld_vertex(vpos, v.w);
+    const int ids[3] = { v.x, v.y, v.z };
+    double X[3][3];
+    float Xf[3][3];
+    float E = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const D3 p = ld_vertex(vpos, ids[k]);
+        X[k][0] = p.x - O.x; X[k][1] = p.y - O.y; X[k][2] = p.z - O.z;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { Xf[k][c] = (float)X[k][c]; E = fmaxf(E, fabsf(Xf[k][c])); }
+    }
+    const double v6 = X[0][0] * (X[1][1] * X[2][2] - X[1][2] * X[2][1]) + X[0][1] * (X[1][2] * X[2][0] - X[1][0] * X[2][2]) +
+                      X[0][2] * (X[1][0] * X[2][1] - X[1][1] * X[2][0]);
+    E = E * 1.0000002f; // never below the true maximum
+    uint4 *o = out + 4 * t;
+    o[0] = make_uint4((unsigned)l.x, (unsigned)l.y, (unsigned)l.z, (unsigned)l.w);
+    o[1] = make_uint4(__float_as_uint(Xf[0][0]), __float_as_uint(Xf[0][1]), __float_as_uint(Xf[0][2]), __float_as_uint(Xf[1][0]));
+    o[2] = make_uint4(__float_as_uint(Xf[1][1]), __float_as_uint(Xf[1][2]), __float_as_uint(Xf[2][0]), __float_as_uint(Xf[2][1]));
+    o[3] = make_uint4(__float_as_uint(Xf[2][2]), (unsigned)v.w, __float_as_uint((float)v6), __float_as_uint(E));
+}
+
 __global__ void k_pack_positions(long long n, const double *__restrict__ xyz, double4 *__restrict__ out)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,9 +191,9 @@ int fail(cpf_context *ctx, int code, const char *fmt, ...)
 
 static void free_mesh(cpf_context *ctx)
 {
-    cudaFree(ctx->d_vpos); cudaFree(ctx->d_tetv); cudaFree(ctx->d_tetrec); cudaFree(ctx->d_tetcode); cudaFree(ctx->d_tetcell);
+    cudaFree(ctx->d_vpos); cudaFree(ctx->d_tetv); cudaFree(ctx->d_tetrec); cudaFree(ctx->d_tetfast); cudaFree(ctx->d_tetcode); cudaFree(ctx->d_tetcell);
     cudaFree(ctx->d_ucell[0]); cudaFree(ctx->d_ucell[1]); cudaFree(ctx->d_uvert); cudaFree(ctx->d_patch_kind);
-    ctx->d_vpos = nullptr; ctx->d_tetv = nullptr; ctx->d_tetrec = nullptr; ctx->d_tetcode = nullptr; ctx->d_tetcell = nullptr;
+    ctx->d_vpos = nullptr; ctx->d_tetv = nullptr; ctx->d_tetrec = nullptr; ctx->d_tetfast = nullptr; ctx->d_tetcode = nullptr; ctx->d_tetcell = nullptr;
     ctx->d_ucell[0] = ctx->d_ucell[1] = nullptr; ctx->d_uvert = nullptr; ctx->d_patch_kind = nullptr;
     free_bvh(ctx);
     ctx->have_mesh = false;
@@ -248,6 +279,11 @@ int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, lon
     ctx->launches++;
     CPF_CUDA(ctx, cudaGetLastError());
 
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetfast, sizeof(uint4) * 4 * (size_t)nTets));
+    k_build_fast<<<(unsigned)((nTets + 127) / 128), 128, 0, st>>>(nTets, ctx->d_tetv, ctx->d_vpos, ctx->d_tetrec, ctx->d_tetfast);
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+
     unsigned flags = 0;
     unsigned long long hbits = 0, nb = 0;
     CPF_CUDA(ctx, cudaMemcpyAsync(&flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost, st));
@@ -281,7 +317,7 @@ int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, lon
 MeshView mesh_view(const cpf_context *ctx)
 {
     MeshView m;
-    m.vpos = ctx->d_vpos; m.tetv = ctx->d_tetv; m.tetrec = ctx->d_tetrec; m.tetcode = ctx->d_tetcode;
+    m.vpos = ctx->d_vpos; m.tetv = ctx->d_tetv; m.tetrec = ctx->d_tetrec; m.tetfast = ctx->d_tetfast; m.tetcode = ctx->d_tetcode;
     m.tetcell = ctx->cellFromVertex ? nullptr : ctx->d_tetcell;
     m.ucell = ctx->d_ucell[ctx->ucur];
     m.uvert = ctx->d_uvert;
