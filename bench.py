@@ -29,7 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_ALG = 72  # bytes per particle per launch: double4 position+flag and int32 tet id, read and written
+B_ALG = 72  # algorithmic bytes per particle-step (double4 position+flag and int32 tet id, read + written)
 
 WORKLOADS = {
     # BASELINE.json configs[2] / north-star target: 1M-cell channel, 1e7 tracers, field refreshed every step
@@ -237,7 +237,9 @@ def run_ours(args, w, rank, world, local_rank):
     peak, peak_src = _peaks()
     avg_launch_ms = prof_ms / max(nl, 1)
     sub_per_launch = (w["ncycles"] * args.steps) / max(nl, 1)
-    achieved = B_ALG * st1["n_active"] / (avg_launch_ms * 1e-3) / 1e9
+    # achieved GB/s = B_alg x particle-steps/s of the fused kernel(s); with k sub-steps fused per launch the
+    # particle state actually crosses HBM once per launch, so measured DRAM traffic (`traffic`) is BELOW the algorithmic bytes
+    achieved = B_ALG * psteps / (prof_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
@@ -257,9 +259,10 @@ def run_ours(args, w, rank, world, local_rank):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": ck,
-        "roofline": {"bound": "hbm", "kernel": "cpf::k_substeps", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "bytes_per_particle_per_launch": B_ALG,
-                     "avg_launch_ms": avg_launch_ms, "launches_timed": nl, "kernel_share_of_step": prof_ms / ms},
+        "roofline": {"bound": "hbm", "kernel": "cpf::k_fast (+ k_exact rounds)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_particle_step": B_ALG,
+                     "algorithmic_bytes_per_launch": B_ALG * psteps / max(nl, 1), "avg_launch_ms": avg_launch_ms, "launches_timed": nl,
+                     "substeps_per_launch": sub_per_launch, "kernel_share_of_step": prof_ms / ms},
         "stats": {"exact_fraction": (st1["n_exact"] - st0["n_exact"]) / max(psteps, 1), "hops_per_substep": (st1["n_hops"] - st0["n_hops"]) / max(psteps, 1),
                   "reflections": st1["n_reflections"] - st0["n_reflections"], "active": st1["n_active"], "mesh_build_s": t_mesh, "initial_locate_s": t_loc},
     }
@@ -364,7 +367,7 @@ def main():
     ap.add_argument("--ref-arm", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--workload", default="channel1M_1e7", choices=sorted(WORKLOADS))
     ap.add_argument("--sort-interval", type=int, default=20)
-    ap.add_argument("--fuse", type=int, default=1)
+    ap.add_argument("--fuse", type=int, default=10)
     ap.add_argument("--exact", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -21,7 +21,7 @@
 #define CPF_MAX_ROUNDS 3 /* exact<->fast ping-pong rounds before the exact finisher */
 #endif
 #ifndef CPF_FAST_MIN_BLOCKS
-#define CPF_FAST_MIN_BLOCKS 5
+#define CPF_FAST_MIN_BLOCKS 7
 #endif
 #ifdef CPF_TAIL_NOINLINE
 #define CPF_TAIL __device__ __noinline__
