@@ -99,8 +99,8 @@ class ClockSampler:
             self.proc.terminate()
 
 
-def build_inputs(w, rank):
-    from cudaparticlesfoam_b200 import synth
+def build_inputs(w, rank, world=1):
+    from cudaparticlesfoam_b200 import parallel, synth
 
     if w["mesh"] == "channel":
         nx, ny, nz = w["dims"]
@@ -108,7 +108,14 @@ def build_inputs(w, rank):
     else:
         pm = synth.box_mesh(*w["dims"], jitter=w["jitter"])
     span = pm.hi - pm.lo
-    p = synth.seed_box(w["n"], pm.lo + 0.02 * span, pm.hi - 0.02 * span, seed=1591593751 + 7919 * rank)
+    # weak scaling: ONE global cloud of world*n particles, partitioned by contiguous index range; every rank
+    # generates only its own slice (same stream as a single big seed_box call would give)
+    start, count = parallel.partition(w["n"] * world, world, rank)
+    lo, hi = pm.lo + 0.02 * span, pm.hi - 0.02 * span
+    p = np.empty((count, 4))
+    for ax in range(3):
+        p[:, ax] = lo[ax] + synth.uniform01(1591593751, start + count, stream=ax)[start:] * (hi[ax] - lo[ax])
+    p[:, 3] = 1.0
     if w["field"] == "channel":
         fields = [synth.field_channel(pm.cell_centres, t=0.05 * k, lo=pm.lo, hi=pm.hi) for k in range(4)]
     else:
@@ -136,7 +143,7 @@ def run_ours(args, w, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    pm, p, fields = build_inputs(w, rank)
+    pm, p, fields = build_inputs(w, rank, world)
     tr = api.ParticleTracker(device=local_rank, rng=api.RNG_PHILOX if w["D"] > 0 else api.RNG_NONE, diffusion_coeff=w["D"], dt=w["dt"],
                              sort_interval=args.sort_interval, fuse_substeps=args.fuse, path=api.PATH_EXACT if args.exact else api.PATH_FILTERED)
     # one explicit non-default stream shared by torch (copies, NCCL, timing events) and the library
@@ -163,9 +170,10 @@ def run_ours(args, w, rank, world, local_rank):
     h2d = ncell * 24
     d2h = 0
 
+    from cudaparticlesfoam_b200 import parallel
+
     def bcast(t):
-        if world > 1:
-            dist.broadcast(t, src=0)
+        parallel.broadcast_field(t, src=0)  # NCCL over NVLink when world > 1, no-op otherwise
 
     def step_resident(k):
         src = u_dev[k % len(u_dev)]
@@ -187,8 +195,7 @@ def run_ours(args, w, rank, world, local_rank):
         st = tr.stats()  # D2H of the counters (synchronises the stream)
         d2h = 8 * 11
         if world > 1:
-            stat_dev.copy_(torch.tensor([st["n_active"], st["n_reflections"], st["n_exact"], st["kinetic_energy"]], dtype=torch.float64))
-            dist.all_reduce(stat_dev)
+            st = parallel.reduce_stats(st, device=dev)  # particle statistics come back over NCCL
         return st
 
     def timed(fn, K):

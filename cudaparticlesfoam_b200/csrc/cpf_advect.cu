@@ -116,7 +116,7 @@ CPF_TAIL void tail_convex_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int 
 {
     const D3 E0 = xadd(P, disp);
     D3 E = E0, S = P;
-    int cur = tet, in_j = -1;
+    int cur = tet, in_j = -1, wallLink = -1;
     bool wall = false;
     Tet T;
     int4 v;
@@ -127,7 +127,7 @@ CPF_TAIL void tail_convex_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int 
         if (out < 0) break;
         const int link = link_at(T.link, out);
         in_j = out;
-        if (link < 0) { wall = true; break; }
+        if (link < 0) { wall = true; wallLink = link; break; }
         cur = link >> 2;
         in_j = link & 3;
     }
@@ -156,20 +156,28 @@ CPF_TAIL void tail_convex_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int 
                 if (out < 0) break;
                 const int link = link_at(T.link, out);
                 in_j = out;
-                if (link < 0) { hitwall = true; break; }
+                if (link < 0) { hitwall = true; wallLink = link; break; }
                 cur = link >> 2;
                 in_j = link & 3;
             }
             if (!hitwall) { next = cur; break; } // end point found (or 50-tet cap: next == cur)
         }
         Phit = S;
+        // per-patch boundary action (extension; the reference reflects everywhere, RTQuery.cu:165-166):
+        // an ESCAPE patch parks the particle at the exit point and deactivates it
+        if (m.patch_kind[-wallLink - 1] == CPF_PATCH_ESCAPE) {
+            P = Phit;
+            w = 0.0;
+            tet = -(cur + 1);
+            ty.esc++;
+            return;
+        }
         ty.refl++;
         reflect_exact(T, Phit, E, vel);
     }
     const D3 nd = xsub(E, Phit);
     tet = next;
     P = xadd(Phit, nd); // p = P_hit (S4) then p += disp (S5)
-    (void)w;
 }
 
 // RTX=true build: barycentric point walk + RTreflection
@@ -249,11 +257,11 @@ CPF_DEV D3 displacement(const MeshView &m, const StepParams &sp, Rng<RNG> &rng, 
     return disp;
 }
 
-CPF_DEV void flush_counters(const StepParams &sp, unsigned refl, unsigned exact, unsigned hops, unsigned nsteps)
+CPF_DEV void flush_counters(const StepParams &sp, unsigned refl, unsigned exact, unsigned hops, unsigned nsteps, unsigned esc = 0u)
 {
-    unsigned vals[5] = { 0u, refl, exact, hops, nsteps };
+    unsigned vals[5] = { esc, refl, exact, hops, nsteps };
 #pragma unroll
-    for (int c = 1; c < 5; ++c) {
+    for (int c = 0; c < 5; ++c) {
         unsigned x = __reduce_add_sync(0xffffffffu, vals[c]);
         if ((threadIdx.x & 31) == 0 && x) atomicAdd(sp.counters + c, (unsigned long long)x);
     }
@@ -301,7 +309,123 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact(const MeshView m,
         if (sp.writeVel && velValid && s1 == sp.nSub) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
         if (QMODE == 1) sp.queueIn[slot].y = s1;
     }
-    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps);
+    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_general<RNG>: integrators and interpolation the reference does not wire up (RK2 midpoint, RK4,
+// vertex / cellPoint-style interpolation), in the reference's arithmetic for every building block;
+// semantics as written down in DESIGN.md section 7 (the test oracle restates them).  Default ConvexPoly locator.
+// ------------------------------------------------------------------------------------------------
+CPF_DEV D3 vertex_velocity_exact(const MeshView &m, int tet, D3 P)
+{
+    int4 v;
+    const Tet T = load_tet(m, tet, v);
+    const int sid[4] = { v.x, v.y, v.z, v.w };
+    int k[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) k[q] = (T.code >> (2 * q)) & 3u;
+    const D3 A = T.P[k[0]], B = T.P[k[1]], C = T.P[k[2]], D = T.P[k[3]];
+    const double rden = __drcp_rn(xdet(A, B, C, D));
+    const double wA = __dmul_rn(xdet(P, B, C, D), rden);
+    const double wB = __dmul_rn(xdet(A, P, C, D), rden);
+    const double wC = __dmul_rn(xdet(A, B, P, D), rden);
+    const D3 cr = xcross(xsub(B, A), xsub(C, A)), rr = xsub(P, A);
+    const double wD = __dmul_rn(__fma_rn(cr.z, rr.z, __fma_rn(cr.y, rr.y, __dmul_rn(cr.x, rr.x))), rden);
+    const double *uA = m.uvert + 3ll * sid[k[0]], *uB = m.uvert + 3ll * sid[k[1]], *uC = m.uvert + 3ll * sid[k[2]],
+                 *uD = m.uvert + 3ll * sid[k[3]];
+    D3 r;
+    r.x = __fma_rn(wD, uD[0], __fma_rn(wC, uC[0], __fma_rn(wA, uA[0], __dmul_rn(wB, uB[0]))));
+    r.y = __fma_rn(wD, uD[1], __fma_rn(wC, uC[1], __fma_rn(wA, uA[1], __dmul_rn(wB, uB[1]))));
+    r.z = __fma_rn(wD, uD[2], __fma_rn(wC, uC[2], __fma_rn(wA, uA[2], __dmul_rn(wB, uB[2]))));
+    return r;
+}
+
+CPF_DEV D3 velocity_at(const MeshView &m, int interp, int tet, D3 P)
+{
+    if (interp == CPF_INTERP_VERTEX) return vertex_velocity_exact(m, tet, P);
+    const int cell = tet_cell(m, tet, ld_int4(m.tetv, tet));
+    const double *uc = m.ucell + 3ll * cell;
+    return D3{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+}
+
+// tet of a stage point: the reference's segment walk from (from, tet); beyond a wall -> last tet
+CPF_DEV int stage_tet(const MeshView &m, D3 from, D3 to, int tet, unsigned &hops)
+{
+    D3 S = from;
+    int cur = tet, in_j = -1;
+    int4 v;
+    for (int i = 0; i < 50; ++i) {
+        const Tet T = load_tet(m, cur, v);
+        hops++;
+        const int out = trace_exact(T, S, to, in_j);
+        if (out < 0) break;
+        const int link = link_at(T.link, out);
+        if (link < 0) break;
+        cur = link >> 2;
+        in_j = link & 3;
+    }
+    return cur;
+}
+
+CPF_DEV D3 axpy3(double h, D3 k, D3 P) { return D3{ __fma_rn(h, k.x, P.x), __fma_rn(h, k.y, P.y), __fma_rn(h, k.z, P.z) }; }
+
+template <int RNG>
+__global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const ParticleView pv, const StepParams sp)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    Tally ty{ 0u, 0u, 0u, 0u };
+    unsigned nsteps = 0;
+    if (i < pv.n) {
+        double4 p4 = ld_stream4(pv.pos + i);
+        int tet = ld_stream_i(pv.tet + i);
+        D3 P{ p4.x, p4.y, p4.z };
+        double w = p4.w;
+        D3 vel{ 0.0, 0.0, 0.0 };
+        bool velValid = false;
+        if (w != 0.0) {
+            Rng<RNG> rng;
+            rng.open(pv, i, sp);
+            for (int s = 0; s < sp.nSub; ++s) {
+                if (w == 0.0) break;
+                if (tet < 0) { w = 0.0; break; }
+                const D3 k1 = velocity_at(m, sp.interp, tet, P);
+                vel = k1;
+                if (sp.integrator == CPF_RK2) {
+                    const D3 Pm = axpy3(__dmul_rn(0.5, sp.dt), k1, P);
+                    vel = velocity_at(m, sp.interp, stage_tet(m, P, Pm, tet, ty.hops), Pm);
+                } else if (sp.integrator == CPF_RK4) {
+                    const double h = __dmul_rn(0.5, sp.dt);
+                    const D3 P2 = axpy3(h, k1, P);
+                    const D3 k2 = velocity_at(m, sp.interp, stage_tet(m, P, P2, tet, ty.hops), P2);
+                    const D3 P3 = axpy3(h, k2, P);
+                    const D3 k3 = velocity_at(m, sp.interp, stage_tet(m, P, P3, tet, ty.hops), P3);
+                    const D3 P4 = axpy3(sp.dt, k3, P);
+                    const D3 k4 = velocity_at(m, sp.interp, stage_tet(m, P, P4, tet, ty.hops), P4);
+                    vel.x = __ddiv_rn(__fma_rn(2.0, __dadd_rn(k2.x, k3.x), __dadd_rn(k1.x, k4.x)), 6.0);
+                    vel.y = __ddiv_rn(__fma_rn(2.0, __dadd_rn(k2.y, k3.y), __dadd_rn(k1.y, k4.y)), 6.0);
+                    vel.z = __ddiv_rn(__fma_rn(2.0, __dadd_rn(k2.z, k3.z), __dadd_rn(k1.z, k4.z)), 6.0);
+                }
+                velValid = true;
+                D3 disp{ __dsub_rn(__fma_rn(sp.dt, vel.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, vel.y, P.y), P.y),
+                         __dsub_rn(__fma_rn(sp.dt, vel.z, P.z), P.z) };
+                double x0, x1, x2;
+                if (rng.draw(s, x0, x1, x2)) {
+                    disp.x = __fma_rn(x0, sp.randDisp, disp.x);
+                    disp.y = __fma_rn(x1, sp.randDisp, disp.y);
+                    disp.z = __fma_rn(x2, sp.randDisp, disp.z);
+                }
+                nsteps++;
+                ty.exact++;
+                tail_convex_exact(m, P, disp, vel, tet, w, sp.reflect, ty);
+            }
+            rng.close(pv, i);
+            st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
+            st_stream_i(pv.tet + i, tet);
+            if (sp.writeVel && velValid) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
+        }
+    }
+    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc);
 }
 
 // k_fast<RNG,QMODE>: the main kernel of the filtered policy (default ConvexPoly build).
@@ -413,7 +537,46 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_fast_inline(const MeshV
             if (sp.writeVel && velValid) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
         }
     }
-    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps);
+    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc);
+}
+
+// Point values from the cell field (OpenFOAM volPointInterpolation, interior weights 1/|p - C|),
+// then uvert = [point values..., cell values...] for the vertex (cellPoint-style) interpolation.
+__global__ void k_point_interp(int nPoints, int nCells, const int *__restrict__ off, const int *__restrict__ cells,
+                               const double4 *__restrict__ vpos, const double *__restrict__ ucell, double *__restrict__ uvert)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nPoints) {
+        const D3 P = ld_vertex(vpos, i);
+        double sumw = 0.0, ax = 0.0, ay = 0.0, az = 0.0;
+        for (int q = off[i]; q < off[i + 1]; ++q) {
+            const int c = cells[q];
+            const D3 d = xsub(P, ld_vertex(vpos, nPoints + c));
+            const double wgt = __drcp_rn(__dsqrt_rn(__fma_rn(d.z, d.z, __fma_rn(d.y, d.y, __dmul_rn(d.x, d.x)))));
+            sumw = __dadd_rn(sumw, wgt);
+            ax = __fma_rn(wgt, ucell[3ll * c], ax);
+            ay = __fma_rn(wgt, ucell[3ll * c + 1], ay);
+            az = __fma_rn(wgt, ucell[3ll * c + 2], az);
+        }
+        uvert[3ll * i] = __ddiv_rn(ax, sumw);
+        uvert[3ll * i + 1] = __ddiv_rn(ay, sumw);
+        uvert[3ll * i + 2] = __ddiv_rn(az, sumw);
+    } else if (i < nPoints + nCells) {
+        const int c = i - nPoints;
+        uvert[3ll * i] = ucell[3ll * c]; uvert[3ll * i + 1] = ucell[3ll * c + 1]; uvert[3ll * i + 2] = ucell[3ll * c + 2];
+    }
+}
+
+int launch_point_interp(cpf_context *ctx)
+{
+    if (!ctx->d_pc_off) return fail(ctx, CPF_ERR_INVALID, "vertex interpolation needs cpf_mesh_upload_poly with cfg.interp = CPF_INTERP_VERTEX, or cpf_update_vertex_velocity");
+    if (!ctx->d_uvert) CPF_CUDA(ctx, cudaMalloc(&ctx->d_uvert, sizeof(double) * 3 * (size_t)ctx->nVerts));
+    const int n = (int)ctx->nVerts;
+    k_point_interp<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->nPoints, (int)ctx->nCells, ctx->d_pc_off, ctx->d_pc_cells, ctx->d_vpos,
+                                                           ctx->d_ucell[ctx->ucur], ctx->d_uvert);
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+    return CPF_OK;
 }
 
 // src/initCuda.H:184-199: the one cudaAdvect right after seeding; its only lasting effect is to
@@ -493,7 +656,12 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
         }
         CPF_CUDA(ctx, cudaEventRecord(ctx->profEvents[ctx->profUsed], st));
     }
-    if (ctx->cfg.locator == CPF_LOCATOR_BARY) {
+    sp.integrator = ctx->cfg.integrator;
+    sp.interp = ctx->cfg.interp;
+    if (ctx->cfg.integrator != CPF_EULER || ctx->cfg.interp != CPF_INTERP_TET) {
+        CPF_RNG_SWITCH(rng, (k_general<R><<<grid, 128, 0, st>>>(m, pv, sp)));
+        ctx->launches++;
+    } else if (ctx->cfg.locator == CPF_LOCATOR_BARY) {
         CPF_RNG_SWITCH(rng, (k_exact<CPF_LOCATOR_BARY, R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
         ctx->launches++;
     } else if (ctx->cfg.path == CPF_PATH_EXACT) {

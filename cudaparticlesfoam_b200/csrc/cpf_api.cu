@@ -289,6 +289,26 @@ int cpf_mesh_upload_poly(cpf_context *ctx, int nPoints, const double *points, in
     int rc = build_device_mesh(ctx, (long long)nPoints + nCells, pos.data(), nTets, tets.data(), nullptr, tetPatch.data(), nCells,
                                nPoints, true);
     if (rc) return rc;
+    cudaFree(ctx->d_pc_off); cudaFree(ctx->d_pc_cells); ctx->d_pc_off = ctx->d_pc_cells = nullptr;
+    if (ctx->cfg.interp == CPF_INTERP_VERTEX) {
+        // point -> cells CSR (cells ascending, unique) for the point-value interpolation
+        std::vector<long long> pairs;
+        pairs.reserve((size_t)faceOffsets[nFaces] * 2);
+        for (int f = 0; f < nFaces; ++f)
+            for (int q = faceOffsets[f]; q < faceOffsets[f + 1]; ++q) {
+                pairs.push_back(((long long)faceVerts[q] << 32) | (unsigned)owner[f]);
+                if (f < nInternal) pairs.push_back(((long long)faceVerts[q] << 32) | (unsigned)neighbour[f]);
+            }
+        std::sort(pairs.begin(), pairs.end());
+        pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+        std::vector<int> off((size_t)nPoints + 1, 0), cl(pairs.size());
+        for (size_t k = 0; k < pairs.size(); ++k) { off[(size_t)(pairs[k] >> 32) + 1]++; cl[k] = (int)(pairs[k] & 0xffffffffll); }
+        for (int q = 0; q < nPoints; ++q) off[(size_t)q + 1] += off[(size_t)q];
+        CPF_CUDA(ctx, cudaMalloc(&ctx->d_pc_off, sizeof(int) * off.size()));
+        CPF_CUDA(ctx, cudaMalloc(&ctx->d_pc_cells, sizeof(int) * std::max<size_t>(cl.size(), 1)));
+        CPF_CUDA(ctx, cudaMemcpy(ctx->d_pc_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+        CPF_CUDA(ctx, cudaMemcpy(ctx->d_pc_cells, cl.data(), sizeof(int) * cl.size(), cudaMemcpyHostToDevice));
+    }
     return upload_patch_kinds(ctx, nPatches, patchKind);
 }
 
@@ -367,6 +387,7 @@ int cpf_update_velocity(cpf_context *ctx, const double *U, int on_device)
     const int nb = 1 - ctx->ucur;
     CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ucell[nb], U, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     ctx->ucur = nb;
+    if (ctx->cfg.interp == CPF_INTERP_VERTEX && ctx->d_pc_off) return launch_point_interp(ctx);
     return CPF_OK;
 }
 
@@ -443,8 +464,12 @@ int cpf_substeps(cpf_context *ctx, int n, double dt)
     if (!ctx) return CPF_ERR_INVALID;
     if (ctx->n == 0 || n <= 0) return CPF_OK;
     if (!ctx->have_mesh || !ctx->have_tets) return fail(ctx, CPF_ERR_INVALID, "cpf_substeps: mesh and located particles are required");
-    if (ctx->cfg.integrator != CPF_EULER || ctx->cfg.interp != CPF_INTERP_TET)
-        return fail(ctx, CPF_ERR_INVALID, "integrator/interp combination not available in this build");
+    if ((ctx->cfg.integrator != CPF_EULER || ctx->cfg.interp != CPF_INTERP_TET) && ctx->cfg.locator != CPF_LOCATOR_CONVEX)
+        return fail(ctx, CPF_ERR_INVALID, "RK2/RK4 and vertex interpolation are available with the convex locator only");
+    if (ctx->cfg.integrator != CPF_EULER && ctx->cfg.integrator != CPF_RK2 && ctx->cfg.integrator != CPF_RK4)
+        return fail(ctx, CPF_ERR_INVALID, "unknown integrator %d", ctx->cfg.integrator);
+    if (ctx->cfg.interp == CPF_INTERP_VERTEX && !ctx->d_uvert)
+        return fail(ctx, CPF_ERR_INVALID, "vertex interpolation: no vertex field (cpf_update_velocity after an upload with interp = VERTEX, or cpf_update_vertex_velocity)");
     cudaSetDevice(ctx->device);
     CPF_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     const int fuse = ctx->cfg.fuse_substeps > 0 ? ctx->cfg.fuse_substeps : 1;

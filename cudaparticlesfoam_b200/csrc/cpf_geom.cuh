@@ -172,8 +172,8 @@ CPF_DEV int trace_exact(const Tet &T, D3 &S, D3 E, int in_j)
     return out_j;
 }
 
-// query/ConvexQuery.cu:239-317 reflectInTet (see oracle/cpf_oracle.c reflect_in_tet for the
-// uninitialised-read note: no matching face leaves E and u untouched).
+// query/ConvexQuery.cu:239-317 reflectInTet.  When no face matches, the source reads uninitialised
+// P_reflect/u_reflect; the compiled reference leaves E and u untouched, as here.
 CPF_DEV void reflect_exact(const Tet &T, D3 Pxf, D3 &E, D3 &u)
 {
     const D3 d = xsub(E, Pxf);

@@ -29,6 +29,7 @@ struct StepParams {
     double randDisp;     // sqrt(2*D*dt), cuda/particles.cu:564
     int reflect;
     int writeVel;
+    int integrator, interp;
     unsigned long long seed;
     unsigned long long step0; // global sub-step index of the first fused sub-step (Philox counter)
     unsigned long long *counters;
@@ -69,6 +70,7 @@ struct cpf_context {
     double *d_ucell[2] = { nullptr, nullptr }; // double-buffered cell field, solver layout [nCells][3]
     int ucur = 0;
     double *d_uvert = nullptr;
+    int *d_pc_off = nullptr, *d_pc_cells = nullptr; // point -> cells CSR (vertex interpolation from the cell field)
     uint8_t *d_patch_kind = nullptr;
     double guard = 1e-7, hmin = 0.0;
     double bbox_lo[3] = { 0, 0, 0 }, bbox_hi[3] = { 0, 0, 0 };
@@ -131,6 +133,7 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel);
 int launch_initial_advect(cpf_context *ctx, double dt);
 int launch_debug_normals(cpf_context *ctx, double *d_xi);
 int launch_init_rng(cpf_context *ctx);
+int launch_point_interp(cpf_context *ctx);
 // cpf_sort.cu
 int sort_particles_by_cell(cpf_context *ctx);
 int gather_original_order(cpf_context *ctx, double4 *d_pos_out, double4 *d_vel_out, int *d_tet_out);

@@ -192,9 +192,9 @@ int fail(cpf_context *ctx, int code, const char *fmt, ...)
 static void free_mesh(cpf_context *ctx)
 {
     cudaFree(ctx->d_vpos); cudaFree(ctx->d_tetv); cudaFree(ctx->d_tetrec); cudaFree(ctx->d_tetfast); cudaFree(ctx->d_tetcode); cudaFree(ctx->d_tetcell);
-    cudaFree(ctx->d_ucell[0]); cudaFree(ctx->d_ucell[1]); cudaFree(ctx->d_uvert); cudaFree(ctx->d_patch_kind);
+    cudaFree(ctx->d_ucell[0]); cudaFree(ctx->d_ucell[1]); cudaFree(ctx->d_uvert); cudaFree(ctx->d_patch_kind); cudaFree(ctx->d_pc_off); cudaFree(ctx->d_pc_cells);
     ctx->d_vpos = nullptr; ctx->d_tetv = nullptr; ctx->d_tetrec = nullptr; ctx->d_tetfast = nullptr; ctx->d_tetcode = nullptr; ctx->d_tetcell = nullptr;
-    ctx->d_ucell[0] = ctx->d_ucell[1] = nullptr; ctx->d_uvert = nullptr; ctx->d_patch_kind = nullptr;
+    ctx->d_ucell[0] = ctx->d_ucell[1] = nullptr; ctx->d_uvert = nullptr; ctx->d_patch_kind = nullptr; ctx->d_pc_off = ctx->d_pc_cells = nullptr;
     free_bvh(ctx);
     ctx->have_mesh = false;
 }

@@ -683,3 +683,5 @@ void orc_bary_of(long n, const double *p, const int *tet, const double *pos, con
 }
 
 int orc_abi_version(void) { return 1; }
+
+#include "cpf_oracle_ext.c"

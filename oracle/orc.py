@@ -196,6 +196,60 @@ def bary_query(mesh, cl):
     lib().orc_bary_query(C.c_long(cl.n), _d(cl.p), _i(cl.tet), *mesh.args())
 
 
+def tet_polyface(pm) -> np.ndarray:
+    L = lib()
+    L.orc_tet_polyface.restype = C.c_long
+    n = 0
+    sizes = np.diff(pm.face_offsets) - 2
+    n = int(sizes[: pm.n_internal].sum() * 2 + sizes[pm.n_internal:].sum())
+    tf = np.empty(n, dtype=np.int32)
+    got = L.orc_tet_polyface(C.c_int(pm.n_cells), C.c_int(pm.n_faces), C.c_int(pm.n_internal), _i(pm.face_offsets), _i(pm.owner),
+                             _i(pm.neighbour), _i(tf))
+    assert got == n
+    return tf
+
+
+def face_kinds(pm, mesh: TetMesh, patch_kind) -> np.ndarray:
+    """[nFaces] uint8 action per tet-mesh face (0 reflect, 1 escape) from per-patch kinds: the boundary
+    triangle of a tet is the face opposite its centre vertex (slot 0) on the polyMesh face it was fanned from."""
+    patch_kind = np.asarray(patch_kind)
+    poly_patch = np.full(pm.n_faces, -1, dtype=np.int64)
+    for p in range(len(pm.patch_starts) - 1):
+        poly_patch[pm.patch_starts[p]:pm.patch_starts[p + 1]] = p
+    tf = tet_polyface(pm)
+    kinds = np.zeros(mesh.n_faces, dtype=np.uint8)
+    bd = poly_patch[tf] >= 0
+    kinds[mesh.tetfacets[bd, 0]] = patch_kind[poly_patch[tf[bd]]]
+    return kinds
+
+
+def point_values(pm, Ucell) -> np.ndarray:
+    Uv = np.empty((pm.n_points + pm.n_cells, 3))
+    lib().orc_point_values(C.c_int(pm.n_points), C.c_int(pm.n_cells), C.c_int(pm.n_faces), C.c_int(pm.n_internal), _i(pm.face_offsets),
+                           _i(pm.face_verts), _i(pm.owner), _i(pm.neighbour), _d(pm.points), _d(pm.cell_centres),
+                           _d(np.ascontiguousarray(Ucell, dtype=np.float64)), _d(Uv))
+    return Uv
+
+
+def ext_substeps(mesh: TetMesh, cl: Cloud, U, n_steps, dt, *, vertex_velocity=False, integrator=0, face_kind=None, reflect=True,
+                 xi=None, D=0.0) -> int:
+    """Generalised loop of oracle/cpf_oracle_ext.c (RK2=1 / RK4=4, vertex interpolation, escape patches)."""
+    L = lib()
+    L.orc_ext_substeps.restype = C.c_long
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    xp = None
+    if xi is not None:
+        xi = np.ascontiguousarray(xi, dtype=np.float64)
+        xp = _d(xi)
+    fk = None
+    if face_kind is not None:
+        face_kind = np.ascontiguousarray(face_kind, dtype=np.uint8)
+        fk = face_kind.ctypes.data_as(C.POINTER(C.c_ubyte))
+    return int(L.orc_ext_substeps(C.c_long(cl.n), C.c_int(n_steps), _d(cl.p), _i(cl.tet), _d(cl.vel), _d(cl.disp), C.c_double(dt),
+                                  *mesh.args(), _d(U), C.c_int(int(vertex_velocity)), C.c_int(int(integrator)), fk,
+                                  C.c_int(int(reflect)), xp, C.c_double(D)))
+
+
 def move(cl):
     lib().orc_move(C.c_long(cl.n), _d(cl.p), _d(cl.disp))
 
