@@ -11,6 +11,7 @@
 // one 256-bit load + one 32-bit load per particle per launch, the same back.  disp never touches
 // memory; vel is written only when the host can observe it (last sub-step of a call).
 #include <algorithm>
+#include <cstdlib>
 
 #include "cpf_internal.h"
 
@@ -18,7 +19,7 @@
 #define CPF_MIN_BLOCKS 4
 #endif
 #ifndef CPF_MAX_ROUNDS
-#define CPF_MAX_ROUNDS 3 /* exact<->fast ping-pong rounds before the exact finisher */
+#define CPF_MAX_ROUNDS 2 /* exact<->fast ping-pong rounds before the exact finisher */
 #endif
 #ifndef CPF_FAST_MIN_BLOCKS
 #define CPF_FAST_MIN_BLOCKS 7
@@ -494,48 +495,52 @@ __global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshVie
     flush_counters(sp, 0u, 0u, hops, nsteps);
 }
 
-// k_fast_inline<RNG>: same fast walk with the exact tail inline (no queues).  Used for the stateful
-// XORWOW stream, whose generator state cannot be rewound for a deferred sub-step.
-template <int RNG>
+// k_fast_inline<RNG,QMODE>: same fast walk with the exact tail inline.  QMODE 0 (thread i = particle
+// i) serves the stateful XORWOW stream, whose generator state cannot be rewound for a deferred
+// sub-step; QMODE 2 finishes whatever is still queued after the last ping-pong round.
+template <int RNG, int QMODE>
 __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_fast_inline(const MeshView m, const ParticleView pv, const StepParams sp)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     Tally ty{ 0u, 0u, 0u, 0u };
     unsigned nsteps = 0;
-    if (i < pv.n) {
+    const long long total = QMODE ? (long long)*sp.countIn : pv.n;
+    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
+        long long i = slot;
+        int s0 = 0;
+        if (QMODE) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y; }
+        if (s0 >= sp.nSub) continue;
         const double4 p4 = ld_stream4(pv.pos + i);
         int tet = ld_stream_i(pv.tet + i);
         D3 P{ p4.x, p4.y, p4.z };
         double w = p4.w;
-        if (w != 0.0) {
-            Rng<RNG> rng;
-            rng.open(pv, i, sp);
-            Fast32 f;
-            D3 O{ 0.0, 0.0, 0.0 }, vel{ 0.0, 0.0, 0.0 };
-            bool velValid = false;
-            if (tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
-            for (int s = 0; s < sp.nSub; ++s) {
-                if (w == 0.0) break;
-                if (tet < 0) { w = 0.0; break; }
-                const int cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
-                const D3 disp = displacement<RNG>(m, sp, rng, s, cell, P, vel);
-                velValid = true;
-                nsteps++;
-                const int r = walk_fast32(m, f, O, tet, P, disp, ty.hops);
-                if (r >= 0) {
-                    tet = r;
-                    P = xadd(P, disp);
-                } else {
-                    ty.exact++;
-                    tail_convex_exact(m, P, disp, vel, tet, w, sp.reflect, ty);
-                    if (tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
-                }
+        if (w == 0.0) continue;
+        Rng<RNG> rng;
+        rng.open(pv, i, sp);
+        Fast32 f;
+        D3 O{ 0.0, 0.0, 0.0 }, vel{ 0.0, 0.0, 0.0 };
+        bool velValid = false;
+        if (tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
+        for (int s = s0; s < sp.nSub; ++s) {
+            if (w == 0.0) break;
+            if (tet < 0) { w = 0.0; break; }
+            const int cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
+            const D3 disp = displacement<RNG>(m, sp, rng, s, cell, P, vel);
+            velValid = true;
+            nsteps++;
+            const int r = walk_fast32(m, f, O, tet, P, disp, ty.hops);
+            if (r >= 0) {
+                tet = r;
+                P = xadd(P, disp);
+            } else {
+                ty.exact++;
+                tail_convex_exact(m, P, disp, vel, tet, w, sp.reflect, ty);
+                if (tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
             }
-            rng.close(pv, i);
-            st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
-            st_stream_i(pv.tet + i, tet);
-            if (sp.writeVel && velValid) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
         }
+        rng.close(pv, i);
+        st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
+        st_stream_i(pv.tet + i, tet);
+        if (sp.writeVel && velValid) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
     }
     flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc);
 }
@@ -668,12 +673,13 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
         CPF_RNG_SWITCH(rng, (k_exact<CPF_LOCATOR_CONVEX, R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
         ctx->launches++;
     } else if (rng == CPF_RNG_XORWOW) {
-        k_fast_inline<CPF_RNG_XORWOW><<<grid, 128, 0, st>>>(m, pv, sp);
+        k_fast_inline<CPF_RNG_XORWOW, 0><<<grid, 128, 0, st>>>(m, pv, sp);
         ctx->launches++;
     } else {
         // filtered policy: lean fast kernel -> [one exact sub-step -> resume fast]* -> exact finisher
-        const int rounds = std::min(CPF_MAX_ROUNDS, nSub - 1);
-        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * (CPF_MAX_ROUNDS + 2), st));
+        static const int envRounds = getenv("CPF_ROUNDS") ? atoi(getenv("CPF_ROUNDS")) : CPF_MAX_ROUNDS; // experiment knob
+        const int rounds = std::max(0, std::min(std::min(envRounds, 12), nSub - 1));
+        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * 16, st));
         const dim3 qgrid(std::min<unsigned>(grid.x, 148u * 8u));
         StepParams a = sp;
         a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;

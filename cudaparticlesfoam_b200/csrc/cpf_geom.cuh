@@ -87,6 +87,7 @@ CPF_DEV D3 xtriNorm(D3 A, D3 B, D3 C)
 // ------------------------------------------------------------------------------------------------
 struct Tet {
     D3 P[4];
+    D3 N[4]; // inward unit normals of the sorted faces, exactly as traceIntet would compute them
     int4 link;
     unsigned code;
 };
@@ -96,6 +97,7 @@ struct MeshView {
     const int4 *__restrict__ tetv;    // [nTets] sorted vertex ids
     const int4 *__restrict__ tetrec;  // [nTets][2] {links, apex ids} (32 B, one 256-bit load)
     const uint4 *__restrict__ tetfast; // [nTets][4] 64-byte fp32 record of the fast walk (see Fast32)
+    const double4 *__restrict__ tetnrm; // [nTets][3] = 12 doubles: the four reference face normals (exact path)
     const uint16_t *__restrict__ tetcode;
     const int *__restrict__ tetcell;  // [nTets] or nullptr (cell = max vertex id - nPoints)
     const double *__restrict__ ucell; // [nCells][3]
@@ -120,6 +122,15 @@ CPF_DEV Tet load_tet(const MeshView &m, int t, int4 &vout)
     T.P[1] = ld_vertex(m.vpos, v.y);
     T.P[2] = ld_vertex(m.vpos, v.z);
     T.P[3] = ld_vertex(m.vpos, v.w);
+    {   // 96 bytes, three 256-bit loads
+        double q[12];
+        const double4 *np = m.tetnrm + 3ll * t;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(q[4 * k]), "=d"(q[4 * k + 1]), "=d"(q[4 * k + 2]), "=d"(q[4 * k + 3]) : "l"(np + k));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) T.N[j] = D3{ q[3 * j], q[3 * j + 1], q[3 * j + 2] };
+    }
     vout = v;
     return T;
 }
@@ -134,14 +145,23 @@ CPF_DEV void face_abc(const Tet &T, int j, D3 &A, D3 &B, D3 &C)
     C = (j <= 2) ? T.P[3] : T.P[2];
 }
 
-// inward unit normal of sorted face j exactly as traceIntet builds it (ConvexQuery.cu:73-79)
-CPF_DEV D3 face_normal_exact(const Tet &T, int j, D3 &A)
+// inward unit normal of sorted face j exactly as traceIntet builds it (ConvexQuery.cu:73-79):
+// normalize(cross(B-A, C-A)) of the ascending triple, negated when the tet is the face's `back`.
+// It is a pure function of the three vertex positions, so it is evaluated once at mesh build
+// (face_normal_build, same expression tree) and read back here: bit-identical, and the exact path
+// loses its sqrt + 3 divisions per face.
+CPF_DEV D3 face_normal_build(const Tet &T, int j)
 {
-    D3 B, C;
+    D3 A, B, C;
     face_abc(T, j, A, B, C);
     D3 n = xtriNorm(A, B, C);
     if ((T.code >> (8 + j)) & 1u) n = xneg(n);
     return n;
+}
+CPF_DEV D3 face_normal_exact(const Tet &T, int j, D3 &A)
+{
+    A = (j == 0) ? T.P[1] : T.P[0];
+    return j == 0 ? T.N[0] : (j == 1 ? T.N[1] : (j == 2 ? T.N[2] : T.N[3]));
 }
 
 // query/ConvexQuery.cu:32-131 traceIntet.  Returns the sorted face slot the segment leaves through
@@ -258,63 +278,67 @@ CPF_DEV void f32_load(const MeshView &m, int tet, Fast32 &f)
     f.E = __uint_as_float(w[15]);
 }
 
-CPF_DEV float fsel(bool c, float a, float b) { return c ? a : b; }
-
 // Returns the final tet (f then holds its record, O its origin) or CPF_NEED_EXACT.
+// Records are stored positively oriented (V6 > 0: slots 1 and 2 are exchanged at build time where
+// needed, links carry the STORED slot of the entry face), so "inside" is a_j >= 0 without a sign.
 CPF_DEV int walk_fast32(const MeshView &m, Fast32 &f, D3 &O, int tet0, D3 P0, D3 disp, unsigned &hops)
 {
+    const float INF = __int_as_float(0x7f800000);
     float rx = (float)(P0.x - O.x), ry = (float)(P0.y - O.y), rz = (float)(P0.z - O.z);
     const float dx = (float)disp.x, dy = (float)disp.y, dz = (float)disp.z;
     const float Dd = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
-    float Rr = fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz));
+    float RD3 = 3.f * (fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) + Dd);
     const float G = (float)m.guard;
     int cur = tet0, in_j = -1;
     float t_in = 0.f;
     for (int it = 0; it < 48; ++it) {
         hops++;
         const float (&X)[3][3] = f.X;
-        // un-normalised normals of the faces opposite slots 0,1,2 (the origin is slot 3)
+        // un-normalised inward normals of the faces opposite slots 0,1,2 (the origin is slot 3)
         const float n0x = X[1][1] * X[2][2] - X[1][2] * X[2][1], n0y = X[1][2] * X[2][0] - X[1][0] * X[2][2], n0z = X[1][0] * X[2][1] - X[1][1] * X[2][0];
         const float n1x = X[2][1] * X[0][2] - X[2][2] * X[0][1], n1y = X[2][2] * X[0][0] - X[2][0] * X[0][2], n1z = X[2][0] * X[0][1] - X[2][1] * X[0][0];
         const float n2x = X[0][1] * X[1][2] - X[0][2] * X[1][1], n2y = X[0][2] * X[1][0] - X[0][0] * X[1][2], n2z = X[0][0] * X[1][1] - X[0][1] * X[1][0];
-        const float sg = f.V6 < 0.f ? -1.f : 1.f;
-        const float V = fabsf(f.V6);
-        float a[4], b[4];
-        a[0] = sg * (rx * n0x + ry * n0y + rz * n0z);
-        a[1] = sg * (rx * n1x + ry * n1y + rz * n1z);
-        a[2] = sg * (rx * n2x + ry * n2y + rz * n2z);
-        b[0] = sg * (dx * n0x + dy * n0y + dz * n0z);
-        b[1] = sg * (dx * n1x + dy * n1y + dz * n1z);
-        b[2] = sg * (dx * n2x + dy * n2y + dz * n2z);
+        const float V = f.V6;
+        float a[4], b[4], e[4];
+        a[0] = rx * n0x + ry * n0y + rz * n0z;
+        a[1] = rx * n1x + ry * n1y + rz * n1z;
+        a[2] = rx * n2x + ry * n2y + rz * n2z;
+        b[0] = dx * n0x + dy * n0y + dz * n0z;
+        b[1] = dx * n1x + dy * n1y + dz * n1z;
+        b[2] = dx * n2x + dy * n2y + dz * n2z;
         a[3] = V - a[0] - a[1] - a[2];
         b[3] = -(b[0] + b[1] + b[2]);
         const float E = f.E;
-        const float g = G * V + 1.52587890625e-5f * (E * E) * (E + 3.f * (Rr + Dd));
-        bool bad = !(V > 1e-30f), allin = true;
-        float as = 0.f, nbs = 1.f;
+        const float g = fmaf(G, V, 1.52587890625e-5f * (E * E) * (E + RD3));
+        // C1 (entry/start point vs the other faces), C2 (end point vs every face plane)
+        float c1m = INF, eam = INF, emin = INF;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            e[j] = a[j] + b[j];
+            const float c1 = (j == in_j) ? INF : fmaf(t_in, b[j], a[j]);
+            c1m = fminf(c1m, c1);
+            eam = fminf(eam, fabsf(e[j]));
+            emin = fminf(emin, e[j]);
+        }
+        if (!(fminf(c1m, eam) >= g) | !(V > 1e-30f)) return CPF_NEED_EXACT;
+        if (emin > 0.f) return cur;
+        // exit face: smallest crossing parameter among the faces the segment leaves through
+        float t = INF;
         int js = -1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float e = a[j] + b[j];
-            const bool notin = (j != in_j);
-            bad |= notin & (fmaf(t_in, b[j], a[j]) < g); // C1
-            bad |= fabsf(e) < g;                         // C2
-            allin &= (e > 0.f);
-            const float nb = -b[j];
-            const bool cand = notin & (nb > 0.f) & (e < 0.f);
-            const bool better = cand & ((js < 0) | (a[j] * nbs < as * nb));
-            as = fsel(better, a[j], as);
-            nbs = fsel(better, nb, nbs);
+            const bool cand = (b[j] < 0.f) & (e[j] < 0.f) & (j != in_j);
+            const float tj = cand ? __fdividef(a[j], -b[j]) : INF;
+            const bool better = tj < t;
+            t = better ? tj : t;
             js = better ? j : js;
         }
-        if (bad) return CPF_NEED_EXACT;
-        if (allin) return cur;
-        if (js < 0) return CPF_NEED_EXACT;
-        const float t = __fdividef(as, nbs);
+        // C3: the exit point must be clear of every other face (edges/vertices, ties of dT)
+        float c3m = INF;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bad |= (j != js) & (fmaf(t, b[j], a[j]) < g); // C3
+        for (int j = 0; j < 4; ++j) c3m = fminf(c3m, (j == js) ? INF : fmaf(t, b[j], a[j]));
         const int link = sel4(f.link.x, f.link.y, f.link.z, f.link.w, js);
-        if (bad | !(t > t_in) | !(t <= 1.f) | (link < 0)) return CPF_NEED_EXACT; // incl. walls
+        if ((js < 0) | !(c3m >= g) | !(t > t_in) | !(t <= 1.f) | (link < 0)) return CPF_NEED_EXACT; // incl. walls
         cur = link >> 2;
         in_j = link & 3;
         t_in = t;
@@ -323,7 +347,7 @@ CPF_DEV int walk_fast32(const MeshView &m, Fast32 &f, D3 &O, int tet0, D3 P0, D3
         if (f.origin != oldOrigin) { // entered another cell: re-express the start point
             O = ld_vertex(m.vpos, f.origin);
             rx = (float)(P0.x - O.x); ry = (float)(P0.y - O.y); rz = (float)(P0.z - O.z);
-            Rr = fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz));
+            RD3 = 3.f * (fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) + Dd);
         }
     }
     return CPF_NEED_EXACT;

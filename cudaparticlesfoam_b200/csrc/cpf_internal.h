@@ -63,6 +63,7 @@ struct cpf_context {
     bool cellFromVertex = false;
     double4 *d_vpos = nullptr;
     int4 *d_tetv = nullptr;      // sorted ids
+    double4 *d_tetnrm = nullptr; // [nTets][3]: the four reference face normals per tet (96 B)
     uint4 *d_tetfast = nullptr;  // [nTets][4]: 64-byte fp32 record of the fast walk
     int4 *d_tetrec = nullptr;    // [nTets][2]: {links, apex vertex id of the neighbour across each face}
     uint16_t *d_tetcode = nullptr;

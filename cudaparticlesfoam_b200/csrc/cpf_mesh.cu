@@ -142,7 +142,17 @@ __global__ void k_link_faces(long long nEntries, const unsigned long long *__res
 }
 
 // fp32 fast record (cpf_geom.cuh Fast32): offsets of the three lower-id vertices from the highest-id
-// vertex, computed in fp64 and rounded once.
+// vertex, computed in fp64 and rounded once.  Stored positively oriented: where 6*volume of
+// (s0-O, s1-O, s2-O) is negative, slots 1 and 2 are exchanged (coordinates and links); every link
+// carries the STORED slot of the shared face inside the neighbour.
+CPF_DEV double sorted_v6(const int4 v, const double4 *__restrict__ vpos)
+{
+    const D3 O = ld_vertex(vpos, v.w), A = ld_vertex(vpos, v.x), B = ld_vertex(vpos, v.y), C = ld_vertex(vpos, v.z);
+    const double X[3][3] = { { A.x - O.x, A.y - O.y, A.z - O.z }, { B.x - O.x, B.y - O.y, B.z - O.z }, { C.x - O.x, C.y - O.y, C.z - O.z } };
+    return X[0][0] * (X[1][1] * X[2][2] - X[1][2] * X[2][1]) + X[0][1] * (X[1][2] * X[2][0] - X[1][0] * X[2][2]) +
+           X[0][2] * (X[1][0] * X[2][1] - X[1][1] * X[2][0]);
+}
+
 __global__ void k_build_fast(long long nTets, const int4 *__restrict__ tetv, const double4 *__restrict__ vpos,
                              const int4 *__restrict__ tetrec, uint4 *__restrict__ out)
 {
@@ -150,26 +160,52 @@ __global__ void k_build_fast(long long nTets, const int4 *__restrict__ tetv, con
     if (t >= nTets) return;
     const int4 v = tetv[t];
     const int4 l = tetrec[2 * t];
+    const double v6 = sorted_v6(v, vpos);
+    const bool flip = v6 < 0.0;
     const D3 O = ld_vertex(vpos, v.w);
-    const int ids[3] = { v.x, v.y, v.z };
-    double X[3][3];
+    const int ids[3] = { v.x, flip ? v.z : v.y, flip ? v.y : v.z };
+    int lk[4] = { l.x, flip ? l.z : l.y, flip ? l.y : l.z, l.w };
+    // re-express the neighbour-side slot in the neighbour's stored order
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (lk[k] >= 0) {
+            const int nt = lk[k] >> 2;
+            int ns = lk[k] & 3;
+            if ((ns == 1 || ns == 2) && sorted_v6(tetv[nt], vpos) < 0.0) ns = 3 - ns;
+            lk[k] = (nt << 2) | ns;
+        }
     float Xf[3][3];
     float E = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const D3 p = ld_vertex(vpos, ids[k]);
-        X[k][0] = p.x - O.x; X[k][1] = p.y - O.y; X[k][2] = p.z - O.z;
+        const double X[3] = { p.x - O.x, p.y - O.y, p.z - O.z };
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { Xf[k][c] = (float)X[k][c]; E = fmaxf(E, fabsf(Xf[k][c])); }
+        for (int c = 0; c < 3; ++c) { Xf[k][c] = (float)X[c]; E = fmaxf(E, fabsf(Xf[k][c])); }
     }
-    const double v6 = X[0][0] * (X[1][1] * X[2][2] - X[1][2] * X[2][1]) + X[0][1] * (X[1][2] * X[2][0] - X[1][0] * X[2][2]) +
-                      X[0][2] * (X[1][0] * X[2][1] - X[1][1] * X[2][0]);
     E = E * 1.0000002f; // never below the true maximum
     uint4 *o = out + 4 * t;
-    o[0] = make_uint4((unsigned)l.x, (unsigned)l.y, (unsigned)l.z, (unsigned)l.w);
+    o[0] = make_uint4((unsigned)lk[0], (unsigned)lk[1], (unsigned)lk[2], (unsigned)lk[3]);
     o[1] = make_uint4(__float_as_uint(Xf[0][0]), __float_as_uint(Xf[0][1]), __float_as_uint(Xf[0][2]), __float_as_uint(Xf[1][0]));
     o[2] = make_uint4(__float_as_uint(Xf[1][1]), __float_as_uint(Xf[1][2]), __float_as_uint(Xf[2][0]), __float_as_uint(Xf[2][1]));
-    o[3] = make_uint4(__float_as_uint(Xf[2][2]), (unsigned)v.w, __float_as_uint((float)v6), __float_as_uint(E));
+    o[3] = make_uint4(__float_as_uint(Xf[2][2]), (unsigned)v.w, __float_as_uint((float)fabs(v6)), __float_as_uint(E));
+}
+
+// reference face normals, once per (tet, sorted face): see face_normal_exact
+__global__ void k_build_normals(long long nTets, const int4 *__restrict__ tetv, const double4 *__restrict__ vpos,
+                                const uint16_t *__restrict__ tetcode, double *__restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTets) return;
+    const int4 v = tetv[t];
+    Tet T;
+    T.P[0] = ld_vertex(vpos, v.x); T.P[1] = ld_vertex(vpos, v.y); T.P[2] = ld_vertex(vpos, v.z); T.P[3] = ld_vertex(vpos, v.w);
+    T.code = tetcode[t];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const D3 n = face_normal_build(T, j);
+        out[12 * t + 3 * j] = n.x; out[12 * t + 3 * j + 1] = n.y; out[12 * t + 3 * j + 2] = n.z;
+    }
 }
 
 __global__ void k_pack_positions(long long n, const double *__restrict__ xyz, double4 *__restrict__ out)
@@ -191,9 +227,9 @@ int fail(cpf_context *ctx, int code, const char *fmt, ...)
 
 static void free_mesh(cpf_context *ctx)
 {
-    cudaFree(ctx->d_vpos); cudaFree(ctx->d_tetv); cudaFree(ctx->d_tetrec); cudaFree(ctx->d_tetfast); cudaFree(ctx->d_tetcode); cudaFree(ctx->d_tetcell);
+    cudaFree(ctx->d_vpos); cudaFree(ctx->d_tetv); cudaFree(ctx->d_tetrec); cudaFree(ctx->d_tetfast); cudaFree(ctx->d_tetnrm); cudaFree(ctx->d_tetcode); cudaFree(ctx->d_tetcell);
     cudaFree(ctx->d_ucell[0]); cudaFree(ctx->d_ucell[1]); cudaFree(ctx->d_uvert); cudaFree(ctx->d_patch_kind); cudaFree(ctx->d_pc_off); cudaFree(ctx->d_pc_cells);
-    ctx->d_vpos = nullptr; ctx->d_tetv = nullptr; ctx->d_tetrec = nullptr; ctx->d_tetfast = nullptr; ctx->d_tetcode = nullptr; ctx->d_tetcell = nullptr;
+    ctx->d_vpos = nullptr; ctx->d_tetv = nullptr; ctx->d_tetrec = nullptr; ctx->d_tetfast = nullptr; ctx->d_tetnrm = nullptr; ctx->d_tetcode = nullptr; ctx->d_tetcell = nullptr;
     ctx->d_ucell[0] = ctx->d_ucell[1] = nullptr; ctx->d_uvert = nullptr; ctx->d_patch_kind = nullptr; ctx->d_pc_off = ctx->d_pc_cells = nullptr;
     free_bvh(ctx);
     ctx->have_mesh = false;
@@ -279,6 +315,9 @@ int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, lon
     ctx->launches++;
     CPF_CUDA(ctx, cudaGetLastError());
 
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetnrm, sizeof(double) * 12 * (size_t)nTets));
+    k_build_normals<<<(unsigned)((nTets + 127) / 128), 128, 0, st>>>(nTets, ctx->d_tetv, ctx->d_vpos, ctx->d_tetcode, (double *)ctx->d_tetnrm);
+    ctx->launches++;
     CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetfast, sizeof(uint4) * 4 * (size_t)nTets));
     k_build_fast<<<(unsigned)((nTets + 127) / 128), 128, 0, st>>>(nTets, ctx->d_tetv, ctx->d_vpos, ctx->d_tetrec, ctx->d_tetfast);
     ctx->launches++;
@@ -317,7 +356,7 @@ int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, lon
 MeshView mesh_view(const cpf_context *ctx)
 {
     MeshView m;
-    m.vpos = ctx->d_vpos; m.tetv = ctx->d_tetv; m.tetrec = ctx->d_tetrec; m.tetfast = ctx->d_tetfast; m.tetcode = ctx->d_tetcode;
+    m.vpos = ctx->d_vpos; m.tetv = ctx->d_tetv; m.tetrec = ctx->d_tetrec; m.tetfast = ctx->d_tetfast; m.tetnrm = ctx->d_tetnrm; m.tetcode = ctx->d_tetcode;
     m.tetcell = ctx->cellFromVertex ? nullptr : ctx->d_tetcell;
     m.ucell = ctx->d_ucell[ctx->ucur];
     m.uvert = ctx->d_uvert;
