@@ -6,6 +6,8 @@
 // original index so that every download is returned in the reference's order.
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "cpf_internal.h"
 
 namespace cpf {
@@ -90,24 +92,33 @@ int gather_original_order(cpf_context *ctx, double4 *d_pos_out, double4 *d_vel_o
 }
 
 // cudaReportParticles (cuda/particles.cu:763-775) + kinetic energy (cuda/utils.cpp:253-258)
-__global__ void k_stats(long long n, const double4 *__restrict__ pos, const int *__restrict__ tet, const double4 *__restrict__ vel,
-                        unsigned long long *__restrict__ out_counts, double *__restrict__ out_ke)
+__global__ void __launch_bounds__(256) k_stats(long long n, const double4 *__restrict__ pos, const int *__restrict__ tet,
+                                               const double4 *__restrict__ vel, unsigned long long *__restrict__ out_counts,
+                                               double *__restrict__ out_ke)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned active = 0, neg = 0;
+    // grid-stride over a fixed grid, block reduction, ONE atomic per block and quantity
+    unsigned long long active = 0, neg = 0;
     double ke = 0.0;
-    if (i < n) {
-        active = pos[i].w != 0.0;
-        neg = tet[i] < 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        active += pos[i].w != 0.0;
+        neg += tet[i] < 0;
         const double4 v = vel[i];
-        ke = 0.5 * (v.x * v.x + v.y * v.y + v.z * v.z);
+        ke += 0.5 * (v.x * v.x + v.y * v.y + v.z * v.z);
     }
-    active = __reduce_add_sync(0xffffffffu, active);
-    neg = __reduce_add_sync(0xffffffffu, neg);
-    for (int o = 16; o > 0; o >>= 1) ke += __shfl_down_sync(0xffffffffu, ke, o);
-    if ((threadIdx.x & 31) == 0) {
-        if (active) atomicAdd(out_counts, (unsigned long long)active);
-        if (neg) atomicAdd(out_counts + 1, (unsigned long long)neg);
+    __shared__ unsigned long long sa[8], sn[8];
+    __shared__ double sk[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        active += __shfl_down_sync(0xffffffffu, active, o);
+        neg += __shfl_down_sync(0xffffffffu, neg, o);
+        ke += __shfl_down_sync(0xffffffffu, ke, o);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sa[wid] = active; sn[wid] = neg; sk[wid] = ke; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) { active += sa[k]; neg += sn[k]; ke += sk[k]; }
+        atomicAdd(out_counts, active);
+        atomicAdd(out_counts + 1, neg);
         atomicAdd(out_ke, ke);
     }
 }
@@ -123,7 +134,7 @@ int reduce_stats(cpf_context *ctx, cpf_stats *out)
     CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 64, ctx->stream));
     if (ctx->n) {
         const int a = ctx->pcur;
-        k_stats<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n, ctx->d_pos[a], ctx->d_tet[a], ctx->d_vel[a], d_c, d_ke);
+        k_stats<<<(unsigned)std::min<long long>((ctx->n + 255) / 256, 148 * 8), 256, 0, ctx->stream>>>(ctx->n, ctx->d_pos[a], ctx->d_tet[a], ctx->d_vel[a], d_c, d_ke);
         ctx->launches++;
     }
     unsigned long long h[3] = { 0, 0, 0 }, cnt[CNT_COUNT] = { 0 };
