@@ -53,6 +53,7 @@ SYMBOLS = {
     "cpf_set_tets": (C.c_int, [_vp, _ip]),
     "cpf_locate_initial": (C.c_int, [_vp]),
     "cpf_init_rng": (C.c_int, [_vp]),
+    "cpf_relocate_lost": (C.c_int, [_vp]),
     "cpf_advect": (C.c_int, [_vp, C.c_double, _ip]),
     "cpf_substeps": (C.c_int, [_vp, C.c_int, C.c_double]),
     "cpf_initial_advect": (C.c_int, [_vp]),

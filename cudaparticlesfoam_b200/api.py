@@ -102,10 +102,12 @@ class ParticleTracker:
         """initCuda.H:76-139: decomposition + topology + upload + locator build."""
         pk = None if patch_kind is None else np.ascontiguousarray(patch_kind, dtype=np.int32)
         npatch = len(pm.patch_starts) - 1
+        tb = getattr(pm, "tet_base_pt", None)
+        tb = None if tb is None else np.ascontiguousarray(tb, dtype=np.int32)
         self._chk(self.lib.cpf_mesh_upload_poly(
             self.h, pm.n_points, _dp(pm.points), pm.n_faces, _ip(pm.face_offsets), _ip(pm.face_verts), _ip(pm.owner),
-            pm.n_internal, _ip(pm.neighbour), pm.n_cells, _dp(pm.cell_centres), None, npatch, _ip(pm.patch_starts),
-            _ip(pk) if pk is not None else None))
+            pm.n_internal, _ip(pm.neighbour), pm.n_cells, _dp(pm.cell_centres), _ip(tb) if tb is not None else None, npatch,
+            _ip(pm.patch_starts), _ip(pk) if pk is not None else None))
 
     def upload_tets(self, pos, tets, tet_cell=None, n_cells=0):
         pos = np.ascontiguousarray(pos, dtype=np.float64)
@@ -161,6 +163,9 @@ class ParticleTracker:
 
     def locate_initial(self):
         self._chk(self.lib.cpf_locate_initial(self.h))
+
+    def relocate_lost(self):
+        self._chk(self.lib.cpf_relocate_lost(self.h))
 
     def init_rng(self):
         self._chk(self.lib.cpf_init_rng(self.h))

@@ -449,6 +449,14 @@ int cpf_locate_initial(cpf_context *ctx)
     return locate_particles(ctx);
 }
 
+int cpf_relocate_lost(cpf_context *ctx)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    if (!ctx->have_mesh || !ctx->have_tets) return fail(ctx, CPF_ERR_INVALID, "cpf_relocate_lost: mesh and located particles are required");
+    cudaSetDevice(ctx->device);
+    return locate_particles(ctx, true);
+}
+
 int cpf_init_rng(cpf_context *ctx)
 {
     if (!ctx || ctx->n == 0) return fail(ctx, CPF_ERR_INVALID, "cpf_init_rng: no particles");

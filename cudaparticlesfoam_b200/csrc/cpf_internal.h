@@ -128,7 +128,7 @@ int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, lon
 // cpf_locate.cu
 int build_bvh(cpf_context *ctx);
 void free_bvh(cpf_context *ctx);
-int locate_particles(cpf_context *ctx);
+int locate_particles(cpf_context *ctx, bool lostOnly = false);
 // cpf_advect.cu
 int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel);
 int launch_initial_advect(cpf_context *ctx, double dt);

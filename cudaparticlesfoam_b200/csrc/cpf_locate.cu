@@ -102,7 +102,10 @@ CPF_DEV bool in_box(const float4 lo, const float4 hi, D3 P)
            P.z <= (double)hi.z;
 }
 
-__global__ void __launch_bounds__(128) k_locate(const MeshView m, const BvhView bv, const ParticleView pv)
+// lostOnly: relocate only particles that are still active but carry a negative tet id (lost after a
+// failed reflection sequence) -- the reference freezes those forever (cuda/particles.cu:334-338)
+__global__ void __launch_bounds__(128) k_locate(const MeshView m, const BvhView bv, const ParticleView pv, const int lostOnly,
+                                                unsigned long long *__restrict__ relocated)
 {
     extern __shared__ float4 smem[];
     float4 *sLo = smem, *sHi = smem + bv.topNodes;
@@ -111,7 +114,8 @@ __global__ void __launch_bounds__(128) k_locate(const MeshView m, const BvhView 
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pv.n) return;
     const double4 p4 = pv.pos[i];
-    if (p4.w == 0.0) { pv.tet[i] = -1; return; }
+    if (lostOnly) { if (p4.w == 0.0 || pv.tet[i] >= 0) return; }
+    else if (p4.w == 0.0) { pv.tet[i] = -1; return; }
     const D3 P{ p4.x, p4.y, p4.z };
     int best = 0x7fffffff;
     int stack[72];
@@ -152,6 +156,10 @@ __global__ void __launch_bounds__(128) k_locate(const MeshView m, const BvhView 
                 if (w[0] >= 0.0 && w[1] >= 0.0 && w[2] >= 0.0 && w[3] >= 0.0) best = t;
             }
         }
+    }
+    if (lostOnly) {
+        if (best != 0x7fffffff) { pv.tet[i] = best; atomicAdd(relocated, 1ull); }
+        return;
     }
     pv.tet[i] = (best == 0x7fffffff) ? -1 : best;
 }
@@ -230,7 +238,7 @@ int build_bvh(cpf_context *ctx)
     return CPF_OK;
 }
 
-int locate_particles(cpf_context *ctx)
+int locate_particles(cpf_context *ctx, bool lostOnly)
 {
     if (!ctx->have_mesh) return fail(ctx, CPF_ERR_INVALID, "no mesh uploaded");
     if (ctx->n == 0) return CPF_OK;
@@ -244,10 +252,11 @@ int locate_particles(cpf_context *ctx)
     bv.nTets = ctx->nTets;
     const size_t smem = sizeof(float4) * 2 * (size_t)bv.topNodes;
     CPF_CUDA(ctx, cudaFuncSetAttribute(k_locate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_locate<<<(unsigned)((ctx->n + 127) / 128), 128, smem, ctx->stream>>>(mesh_view(ctx), bv, particle_view(ctx));
+    k_locate<<<(unsigned)((ctx->n + 127) / 128), 128, smem, ctx->stream>>>(mesh_view(ctx), bv, particle_view(ctx), lostOnly ? 1 : 0,
+                                                                           ctx->d_counters + CNT_LOST);
     ctx->launches++;
     CPF_CUDA(ctx, cudaGetLastError());
-    ctx->have_tets = true;
+    if (!lostOnly) ctx->have_tets = true;
     return CPF_OK;
 }
 

@@ -46,6 +46,7 @@ class PolyMesh:
     cell_centres: np.ndarray  # [nCells,3]
     patch_starts: np.ndarray  # [nPatches+1] face index ranges of the boundary patches
     patch_names: tuple = PATCH_NAMES
+    tet_base_pt: np.ndarray | None = None  # [nFaces] mesh.tetBasePtIs(); None => 0 for every face
     dims: tuple = (0, 0, 0)
     lo: np.ndarray = field(default_factory=lambda: np.zeros(3))
     hi: np.ndarray = field(default_factory=lambda: np.ones(3))
@@ -171,6 +172,57 @@ def box_mesh(nx: int, ny: int, nz: int, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), 
         lo=lo,
         hi=hi,
     )
+
+
+def polyhex_mesh(nx: int, ny: int, nz: int, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), jitter: float = 0.1,
+                 seed: int = 1591593751) -> PolyMesh:
+    """Polyhedral stand-in (BASELINE config 4 code path): the hex block with an extra point in the middle
+    of every x-directed edge, so the faces normal to y and z are hexagons, cells have 12 points and 20 tets
+    (variable fan sizes, tet != 12*cell + j), and tetBasePtIs is non-trivial (hexagons fan from their
+    first mid-edge point, like OpenFOAM picks base points that avoid sliver tets)."""
+    base = box_mesh(nx, ny, nz, lo=lo, hi=hi, jitter=jitter, seed=seed)
+    npx, npy, npz = nx + 1, ny + 1, nz + 1
+    n0 = base.n_points
+
+    def pid(i, j, k):
+        return i + npx * (j + npy * k)
+
+    def mid(i, j, k):  # midpoint of the edge (i,j,k)-(i+1,j,k)
+        return n0 + i + nx * (j + npy * k)
+
+    I, J, K = np.meshgrid(np.arange(nx), np.arange(npy), np.arange(npz), indexing="ij")
+    I = I.transpose(2, 1, 0).reshape(-1); J = J.transpose(2, 1, 0).reshape(-1); K = K.transpose(2, 1, 0).reshape(-1)
+    mids = 0.5 * (base.points[pid(I, J, K)] + base.points[pid(I + 1, J, K)])
+    h = (np.asarray(hi, float) - np.asarray(lo, float)) / np.array([nx, ny, nz], float)
+    # push interior mid-edge points a little off the straight edge (keeps boundary planes planar)
+    ry = (uniform01(seed, mids.shape[0], stream=211) * 2 - 1) * 0.08 * h[1]
+    rz = (uniform01(seed, mids.shape[0], stream=212) * 2 - 1) * 0.08 * h[2]
+    mids[:, 1] += np.where((J > 0) & (J < ny), ry, 0.0)
+    mids[:, 2] += np.where((K > 0) & (K < nz), rz, 0.0)
+    assert np.array_equal(mid(I, J, K), n0 + np.arange(mids.shape[0]))
+    points = np.concatenate([base.points, mids], axis=0)
+    # rebuild faces: insert the mid-edge point between two consecutive face points that differ in i only
+    inv = {}
+    P = np.arange(n0)
+    pi_, pj_, pk_ = P % npx, (P // npx) % npy, P // (npx * npy)
+    off, verts, tet_base = [0], [], []
+    fv = base.face_verts.reshape(-1, 4)
+    for f in range(fv.shape[0]):
+        q = fv[f]
+        out = []
+        for a in range(4):
+            u, v = int(q[a]), int(q[(a + 1) % 4])
+            out.append(u)
+            if pj_[u] == pj_[v] and pk_[u] == pk_[v] and abs(int(pi_[u]) - int(pi_[v])) == 1:
+                out.append(int(mid(min(pi_[u], pi_[v]), pj_[u], pk_[u])))
+        verts.extend(out)
+        off.append(len(verts))
+        tet_base.append(1 if len(out) == 6 and out[1] >= n0 else (0 if len(out) == 4 else next(k for k, x in enumerate(out) if x >= n0)))
+    pm = PolyMesh(points=np.ascontiguousarray(points), face_offsets=np.asarray(off, dtype=np.int32),
+                  face_verts=np.asarray(verts, dtype=np.int32), owner=base.owner, neighbour=base.neighbour,
+                  cell_centres=base.cell_centres, patch_starts=base.patch_starts, dims=(nx, ny, nz), lo=base.lo, hi=base.hi)
+    pm.tet_base_pt = np.asarray(tet_base, dtype=np.int32)
+    return pm
 
 
 def channel_mesh(nx=400, ny=50, nz=50, jitter: float = 0.0) -> PolyMesh:

@@ -144,6 +144,10 @@ int cpf_set_tets(cpf_context *ctx, const int *tet);
 /* replaces RTQuery(OptixQuery&,...) = OptiX ray cast + baryQuery (query/RTQuery.cu:295-310):
  * BVH point location, lowest containing tet id, -1 outside */
 int cpf_locate_initial(cpf_context *ctx);
+/* Lost-particle fallback (extension): particles that are still active but carry a negative tet id
+ * (e.g. after five failed reflections) are re-located with the BVH instead of being frozen on the
+ * next sub-step as the reference does (cuda/particles.cu:334-338).  Call between cpf_substeps. */
+int cpf_relocate_lost(cpf_context *ctx);
 /* initRandomGenerator (cuda/particles.cu:541-548) */
 int cpf_init_rng(cpf_context *ctx);
 

@@ -91,8 +91,10 @@ class TetMesh:
 def decompose(pm) -> tuple[np.ndarray, np.ndarray]:
     """A1: polyMesh -> tets (oracle restatement of src/initCuda.H:86-110)."""
     L = lib()
+    tb = getattr(pm, "tet_base_pt", None)
+    tb = None if tb is None else np.ascontiguousarray(tb, dtype=np.int32)
     a = (C.c_int(pm.n_points), C.c_int(pm.n_cells), C.c_int(pm.n_faces), C.c_int(pm.n_internal),
-         _i(pm.face_offsets), _i(pm.face_verts), _i(pm.owner), _i(pm.neighbour), None)
+         _i(pm.face_offsets), _i(pm.face_verts), _i(pm.owner), _i(pm.neighbour), _i(tb) if tb is not None else None)
     n = L.orc_decompose_poly(*a, None, None)
     tets = np.empty((n, 4), dtype=np.int32)
     tet_cell = np.empty(n, dtype=np.int32)

@@ -96,3 +96,29 @@ def test_outlet_escape(synth, orc, rng):
     assert gone.sum() == n_esc and np.abs(pp[gone, 0] - 1.0).max() < 1e-12 and (tt[gone] < 0).all()
     assert st["n_active"] == (~gone).sum()
     tr.close()
+
+
+def test_lost_particle_relocation(synth, orc):
+    """Lost-particle fallback: active particles with a negative tet id are re-located by the BVH
+    (lowest containing tet, as brute force), instead of being frozen on the next sub-step."""
+    from cudaparticlesfoam_b200 import api
+
+    pm, mesh, U, p = make_case(synth, orc, dims=(8, 8, 8), jitter=0.2, n=5000)
+    tet_true = orc.locate_brute(mesh, p)
+    lost = np.arange(0, 5000, 7)
+    tet = tet_true.copy()
+    tet[lost] = -1                      # pretend these were lost
+    p2 = p.copy()
+    p2[:3, 0] += 4.0                    # really outside: must stay lost
+    tet[:3] = -1
+    tr = api.ParticleTracker(rng=api.RNG_NONE)
+    tr.upload_poly(pm)
+    tr.update_velocity(U)
+    tr.set_particles(p2)
+    tr.set_tets(tet)
+    tr.relocate_lost()
+    _, _, tt = tr.download(pos=False, vel=False)
+    want = tet_true.copy()
+    want[:3] = -1
+    assert np.array_equal(tt, want)
+    tr.close()
