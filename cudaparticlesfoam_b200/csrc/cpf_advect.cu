@@ -495,6 +495,105 @@ __global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshVie
     flush_counters(sp, 0u, 0u, hops, nsteps);
 }
 
+// k_fastm<RNG,QMODE>: k_fast with ONE merged loop over the tet visits of all fused sub-steps of a lane
+// (see visit_fast32).  The random-walk deviates of the whole chunk are drawn up front, with all lanes
+// converged, into shared memory ([sub-step][component][thread], conflict-free), so the per-sub-step
+// prologue inside the divergent loop is only the velocity fetch and three fp64 FMAs.
+template <int RNG, int QMODE>
+__global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fastm(const MeshView m, const ParticleView pv, const StepParams sp)
+{
+    extern __shared__ float s_xi[];
+    unsigned hops = 0, nsteps = 0;
+    const long long total = QMODE ? (long long)*sp.countIn : pv.n;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride) { // warp-uniform trip count
+        const long long slot = base + threadIdx.x;
+        int deferAt = -1;
+        long long i = slot;
+        int s = 0;
+        bool have = slot < total;
+        if (QMODE && have) { const int2 q = sp.queueIn[slot]; i = q.x; s = q.y; have = s < sp.nSub; }
+        double4 p4 = make_double4(0.0, 0.0, 0.0, 0.0);
+        int tet = -1;
+        if (have) { p4 = ld_stream4(pv.pos + i); tet = ld_stream_i(pv.tet + i); }
+        D3 P{ p4.x, p4.y, p4.z };
+        double w = p4.w;
+        const bool live = have && (w != 0.0);
+        bool active = live;
+        if (RNG != CPF_RNG_NONE) {
+            Rng<RNG> rng;
+            if (live) rng.open(pv, i, sp);
+            for (int q = 0; q < sp.nSub; ++q) {
+                double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+                if (live && q >= s) rng.draw(q, x0, x1, x2);
+                s_xi[(q * 3 + 0) * 128 + threadIdx.x] = (float)x0;
+                s_xi[(q * 3 + 1) * 128 + threadIdx.x] = (float)x1;
+                s_xi[(q * 3 + 2) * 128 + threadIdx.x] = (float)x2;
+            }
+        }
+        Fast32 f;
+        D3 O{ 0.0, 0.0, 0.0 }, disp{ 0.0, 0.0, 0.0 };
+        WalkF ws;
+        int cell = -1, lastCell = -1, visits = 0;
+        bool needPro = true;
+        if (active && tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
+        while (__any_sync(0xffffffffu, active)) {
+            if (active && needPro) {
+                if (tet < 0) { w = 0.0; active = false; } // S1: left the domain -> frozen (particles.cu:334-338)
+                else {
+                    cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
+                    const double *uc = m.ucell + 3ll * cell;
+                    const double ux = __ldg(uc), uy = __ldg(uc + 1), uz = __ldg(uc + 2);
+                    disp = D3{ __dsub_rn(__fma_rn(sp.dt, ux, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, uy, P.y), P.y),
+                               __dsub_rn(__fma_rn(sp.dt, uz, P.z), P.z) };
+                    if (RNG != CPF_RNG_NONE) {
+                        disp.x = __fma_rn((double)s_xi[(s * 3 + 0) * 128 + threadIdx.x], sp.randDisp, disp.x);
+                        disp.y = __fma_rn((double)s_xi[(s * 3 + 1) * 128 + threadIdx.x], sp.randDisp, disp.y);
+                        disp.z = __fma_rn((double)s_xi[(s * 3 + 2) * 128 + threadIdx.x], sp.randDisp, disp.z);
+                    }
+                    walkf_begin(ws, O, P, disp, tet);
+                    visits = 0;
+                    needPro = false;
+                }
+            }
+            if (active) {
+                hops++;
+                const int oc = visit_fast32(m, f, O, P, ws);
+                if (oc == CPF_V_DONE) {
+                    tet = ws.cur;
+                    P = xadd(P, disp);
+                    lastCell = cell;
+                    nsteps++;
+                    needPro = true;
+                    if (++s >= sp.nSub) active = false;
+                } else if (oc == CPF_V_REFUSE || ++visits >= 48) {
+                    deferAt = s;
+                    active = false;
+                }
+            }
+        }
+        if (live) {
+            st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
+            st_stream_i(pv.tet + i, tet);
+            if (sp.writeVel && lastCell >= 0 && deferAt < 0) {
+                const double *uc = m.ucell + 3ll * lastCell;
+                st_stream4(pv.vel + i, make_double4(__ldg(uc), __ldg(uc + 1), __ldg(uc + 2), -1.0));
+            }
+        }
+        // deferral queue: one atomic per warp
+        const unsigned mask = __ballot_sync(0xffffffffu, deferAt >= 0);
+        if (mask) {
+            const int lane = threadIdx.x & 31;
+            int qb = 0;
+            if (lane == 0) qb = (int)atomicAdd(sp.countOut, (unsigned)__popc(mask));
+            qb = __shfl_sync(0xffffffffu, qb, 0);
+            if (deferAt >= 0) sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
+        }
+        if (!QMODE) break;
+    }
+    flush_counters(sp, 0u, 0u, hops, nsteps);
+}
+
 // k_fast_inline<RNG,QMODE>: same fast walk with the exact tail inline.  QMODE 0 (thread i = particle
 // i) serves the stateful XORWOW stream, whose generator state cannot be rewound for a deferred
 // sub-step; QMODE 2 finishes whatever is still queued after the last ping-pong round.
@@ -683,7 +782,12 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
         const dim3 qgrid(std::min<unsigned>(grid.x, 148u * 8u));
         StepParams a = sp;
         a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
-        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0><<<grid, 128, 0, st>>>(m, pv, a);
+        static const int merged = getenv("CPF_MERGED") ? atoi(getenv("CPF_MERGED")) : 1; // experiment knob
+        const size_t xiBytes = rng == CPF_RNG_PHILOX ? sizeof(float) * 3 * 128 * (size_t)nSub : 0;
+        if (merged) {
+            if (rng == CPF_RNG_PHILOX) k_fastm<CPF_RNG_PHILOX, 0><<<grid, 128, xiBytes, st>>>(m, pv, a);
+            else k_fastm<CPF_RNG_NONE, 0><<<grid, 128, 0, st>>>(m, pv, a);
+        } else if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0><<<grid, 128, 0, st>>>(m, pv, a);
         else k_fast<CPF_RNG_NONE, 0><<<grid, 128, 0, st>>>(m, pv, a);
         ctx->launches++;
         for (int r = 0; r < rounds; ++r) {
@@ -693,10 +797,12 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
             b.queueOut = ctx->d_queue[(r + 1) & 1]; b.countOut = ctx->d_queue_count + r + 1;
             if (rng == CPF_RNG_PHILOX) {
                 k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_PHILOX, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
-                k_fast<CPF_RNG_PHILOX, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
+                if (merged) k_fastm<CPF_RNG_PHILOX, 2><<<qgrid, 128, xiBytes, st>>>(m, pv, b);
+                else k_fast<CPF_RNG_PHILOX, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
             } else {
                 k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_NONE, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
-                k_fast<CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
+                if (merged) k_fastm<CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
+                else k_fast<CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
             }
             ctx->launches += 2;
         }

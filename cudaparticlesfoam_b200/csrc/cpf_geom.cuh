@@ -353,4 +353,86 @@ CPF_DEV int walk_fast32(const MeshView &m, Fast32 &f, D3 &O, int tet0, D3 P0, D3
     return CPF_NEED_EXACT;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The same walk, one visit at a time (k_fastm).  Lanes of a warp need different numbers of tet
+// visits per sub-step; running the visits of ALL fused sub-steps of a lane through one loop keeps
+// the lanes busy until their whole chunk is done instead of idling at every sub-step boundary.
+// ------------------------------------------------------------------------------------------------
+struct WalkF {
+    float rx, ry, rz, dx, dy, dz, RD3, Dd, t_in;
+    int in_j, cur;
+};
+enum { CPF_V_DONE = 0, CPF_V_HOP = 1, CPF_V_REFUSE = 2 };
+
+CPF_DEV void walkf_begin(WalkF &ws, const D3 &O, const D3 &P0, const D3 &disp, int tet)
+{
+    ws.rx = (float)(P0.x - O.x); ws.ry = (float)(P0.y - O.y); ws.rz = (float)(P0.z - O.z);
+    ws.dx = (float)disp.x; ws.dy = (float)disp.y; ws.dz = (float)disp.z;
+    ws.Dd = fmaxf(fmaxf(fabsf(ws.dx), fabsf(ws.dy)), fabsf(ws.dz));
+    ws.RD3 = 3.f * (fmaxf(fmaxf(fabsf(ws.rx), fabsf(ws.ry)), fabsf(ws.rz)) + ws.Dd);
+    ws.t_in = 0.f;
+    ws.in_j = -1;
+    ws.cur = tet;
+}
+
+// one iteration of walk_fast32 (identical predicates)
+CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, WalkF &ws)
+{
+    const float INF = __int_as_float(0x7f800000);
+    const float (&X)[3][3] = f.X;
+    const float n0x = X[1][1] * X[2][2] - X[1][2] * X[2][1], n0y = X[1][2] * X[2][0] - X[1][0] * X[2][2], n0z = X[1][0] * X[2][1] - X[1][1] * X[2][0];
+    const float n1x = X[2][1] * X[0][2] - X[2][2] * X[0][1], n1y = X[2][2] * X[0][0] - X[2][0] * X[0][2], n1z = X[2][0] * X[0][1] - X[2][1] * X[0][0];
+    const float n2x = X[0][1] * X[1][2] - X[0][2] * X[1][1], n2y = X[0][2] * X[1][0] - X[0][0] * X[1][2], n2z = X[0][0] * X[1][1] - X[0][1] * X[1][0];
+    const float V = f.V6;
+    float a[4], b[4], e[4];
+    a[0] = ws.rx * n0x + ws.ry * n0y + ws.rz * n0z;
+    a[1] = ws.rx * n1x + ws.ry * n1y + ws.rz * n1z;
+    a[2] = ws.rx * n2x + ws.ry * n2y + ws.rz * n2z;
+    b[0] = ws.dx * n0x + ws.dy * n0y + ws.dz * n0z;
+    b[1] = ws.dx * n1x + ws.dy * n1y + ws.dz * n1z;
+    b[2] = ws.dx * n2x + ws.dy * n2y + ws.dz * n2z;
+    a[3] = V - a[0] - a[1] - a[2];
+    b[3] = -(b[0] + b[1] + b[2]);
+    const float E = f.E;
+    const float g = fmaf((float)m.guard, V, 1.52587890625e-5f * (E * E) * (E + ws.RD3));
+    float c1m = INF, eam = INF, emin = INF;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        e[j] = a[j] + b[j];
+        const float c1 = (j == ws.in_j) ? INF : fmaf(ws.t_in, b[j], a[j]);
+        c1m = fminf(c1m, c1);
+        eam = fminf(eam, fabsf(e[j]));
+        emin = fminf(emin, e[j]);
+    }
+    if (!(fminf(c1m, eam) >= g) | !(V > 1e-30f)) return CPF_V_REFUSE;
+    if (emin > 0.f) return CPF_V_DONE;
+    float t = INF;
+    int js = -1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool cand = (b[j] < 0.f) & (e[j] < 0.f) & (j != ws.in_j);
+        const float tj = cand ? __fdividef(a[j], -b[j]) : INF;
+        const bool better = tj < t;
+        t = better ? tj : t;
+        js = better ? j : js;
+    }
+    float c3m = INF;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c3m = fminf(c3m, (j == js) ? INF : fmaf(t, b[j], a[j]));
+    const int link = sel4(f.link.x, f.link.y, f.link.z, f.link.w, js);
+    if ((js < 0) | !(c3m >= g) | !(t > ws.t_in) | !(t <= 1.f) | (link < 0)) return CPF_V_REFUSE;
+    ws.cur = link >> 2;
+    ws.in_j = link & 3;
+    ws.t_in = t;
+    const int oldOrigin = f.origin;
+    f32_load(m, ws.cur, f);
+    if (f.origin != oldOrigin) {
+        O = ld_vertex(m.vpos, f.origin);
+        ws.rx = (float)(P0.x - O.x); ws.ry = (float)(P0.y - O.y); ws.rz = (float)(P0.z - O.z);
+        ws.RD3 = 3.f * (fmaxf(fmaxf(fabsf(ws.rx), fabsf(ws.ry)), fabsf(ws.rz)) + ws.Dd);
+    }
+    return CPF_V_HOP;
+}
+
 } // namespace cpf
