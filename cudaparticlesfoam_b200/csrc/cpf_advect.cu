@@ -11,7 +11,6 @@
 // one 256-bit load + one 32-bit load per particle per launch, the same back.  disp never touches
 // memory; vel is written only when the host can observe it (last sub-step of a call).
 #include <algorithm>
-#include <cstdlib>
 
 #include "cpf_internal.h"
 
@@ -24,11 +23,7 @@
 #ifndef CPF_FAST_MIN_BLOCKS
 #define CPF_FAST_MIN_BLOCKS 7
 #endif
-#ifdef CPF_TAIL_NOINLINE
-#define CPF_TAIL __device__ __noinline__
-#else
 #define CPF_TAIL __device__ __forceinline__
-#endif
 
 namespace cpf {
 
@@ -430,77 +425,19 @@ __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const Part
 }
 
 // k_fast<RNG,QMODE>: the main kernel of the filtered policy (default ConvexPoly build).
-// fp32 guarded walk only -- no exact-arithmetic code, hence few registers and a high occupancy.
-// The first sub-step whose walk is refused is NOT executed: the particle is written back as it was
-// at the start of that sub-step and (particle, sub-step) is appended to the output queue with one
-// warp-aggregated atomic.  k_exact<..,1> performs that one sub-step exactly and this kernel, in
-// queue mode, resumes the particle.
+// fp32 guarded walk only -- no exact-arithmetic code, hence 72 registers and 7 CTAs per SM.
+// ONE merged loop runs the tet visits of all fused sub-steps of a lane (visit_fast32): lanes need
+// different numbers of visits per sub-step, and a merged loop keeps them busy until their whole
+// chunk is done instead of idling at every sub-step boundary.  The random-walk deviates of the chunk
+// are drawn up front, with all lanes converged, into shared memory ([sub-step][component][thread],
+// conflict-free), so the per-sub-step prologue inside the divergent loop is only the velocity fetch
+// and three fp64 FMAs.  The first sub-step whose walk is refused is NOT executed: the particle is
+// written back as it was at the start of that sub-step and (particle, sub-step) is appended to the
+// output queue with one warp-aggregated atomic (ballot + popc); k_exact<..,1> performs that one
+// sub-step in the reference's arithmetic and this kernel, in queue mode, resumes the particle.
 //   QMODE 0: thread i = particle i from sub-step 0      QMODE 2: entries of the input queue
 template <int RNG, int QMODE>
 __global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
-{
-    unsigned hops = 0, nsteps = 0;
-    const long long total = QMODE ? (long long)*sp.countIn : pv.n;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride) { // warp-uniform trip count
-        const long long slot = base + threadIdx.x;
-        int deferAt = -1;
-        long long i = slot;
-        int s0 = 0;
-        bool have = slot < total;
-        if (QMODE && have) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y; have = s0 < sp.nSub; }
-        if (have) {
-            const double4 p4 = ld_stream4(pv.pos + i);
-            int tet = ld_stream_i(pv.tet + i);
-            D3 P{ p4.x, p4.y, p4.z };
-            double w = p4.w;
-            if (w != 0.0) {
-                Rng<RNG> rng;
-                rng.open(pv, i, sp);
-                Fast32 f;
-                D3 O{ 0.0, 0.0, 0.0 };
-                int lastCell = -1;
-                if (tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
-                for (int s = s0; s < sp.nSub; ++s) {
-                    if (tet < 0) { w = 0.0; break; } // S1: left the domain -> frozen (particles.cu:334-338)
-                    const int cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
-                    D3 vel;
-                    const D3 disp = displacement<RNG>(m, sp, rng, s, cell, P, vel);
-                    const int r = walk_fast32(m, f, O, tet, P, disp, hops);
-                    if (r < 0) { deferAt = s; break; }
-                    tet = r;
-                    P = xadd(P, disp);
-                    lastCell = cell;
-                    nsteps++;
-                }
-                st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
-                st_stream_i(pv.tet + i, tet);
-                if (sp.writeVel && lastCell >= 0 && deferAt < 0) {
-                    const double *uc = m.ucell + 3ll * lastCell;
-                    st_stream4(pv.vel + i, make_double4(__ldg(uc), __ldg(uc + 1), __ldg(uc + 2), -1.0));
-                }
-            }
-        }
-        // deferral queue: one atomic per warp
-        const unsigned mask = __ballot_sync(0xffffffffu, deferAt >= 0);
-        if (mask) {
-            const int lane = threadIdx.x & 31;
-            int qb = 0;
-            if (lane == 0) qb = (int)atomicAdd(sp.countOut, (unsigned)__popc(mask));
-            qb = __shfl_sync(0xffffffffu, qb, 0);
-            if (deferAt >= 0) sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
-        }
-        if (!QMODE) break;
-    }
-    flush_counters(sp, 0u, 0u, hops, nsteps);
-}
-
-// k_fastm<RNG,QMODE>: k_fast with ONE merged loop over the tet visits of all fused sub-steps of a lane
-// (see visit_fast32).  The random-walk deviates of the whole chunk are drawn up front, with all lanes
-// converged, into shared memory ([sub-step][component][thread], conflict-free), so the per-sub-step
-// prologue inside the divergent loop is only the velocity fetch and three fp64 FMAs.
-template <int RNG, int QMODE>
-__global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fastm(const MeshView m, const ParticleView pv, const StepParams sp)
 {
     extern __shared__ float s_xi[];
     unsigned hops = 0, nsteps = 0;
@@ -776,18 +713,13 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
         ctx->launches++;
     } else {
         // filtered policy: lean fast kernel -> [one exact sub-step -> resume fast]* -> exact finisher
-        static const int envRounds = getenv("CPF_ROUNDS") ? atoi(getenv("CPF_ROUNDS")) : CPF_MAX_ROUNDS; // experiment knob
-        const int rounds = std::max(0, std::min(std::min(envRounds, 12), nSub - 1));
+        const int rounds = std::max(0, std::min(CPF_MAX_ROUNDS, nSub - 1));
         CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * 16, st));
         const dim3 qgrid(std::min<unsigned>(grid.x, 148u * 8u));
         StepParams a = sp;
         a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
-        static const int merged = getenv("CPF_MERGED") ? atoi(getenv("CPF_MERGED")) : 1; // experiment knob
         const size_t xiBytes = rng == CPF_RNG_PHILOX ? sizeof(float) * 3 * 128 * (size_t)nSub : 0;
-        if (merged) {
-            if (rng == CPF_RNG_PHILOX) k_fastm<CPF_RNG_PHILOX, 0><<<grid, 128, xiBytes, st>>>(m, pv, a);
-            else k_fastm<CPF_RNG_NONE, 0><<<grid, 128, 0, st>>>(m, pv, a);
-        } else if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0><<<grid, 128, 0, st>>>(m, pv, a);
+        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0><<<grid, 128, xiBytes, st>>>(m, pv, a);
         else k_fast<CPF_RNG_NONE, 0><<<grid, 128, 0, st>>>(m, pv, a);
         ctx->launches++;
         for (int r = 0; r < rounds; ++r) {
@@ -797,12 +729,10 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
             b.queueOut = ctx->d_queue[(r + 1) & 1]; b.countOut = ctx->d_queue_count + r + 1;
             if (rng == CPF_RNG_PHILOX) {
                 k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_PHILOX, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
-                if (merged) k_fastm<CPF_RNG_PHILOX, 2><<<qgrid, 128, xiBytes, st>>>(m, pv, b);
-                else k_fast<CPF_RNG_PHILOX, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
+                k_fast<CPF_RNG_PHILOX, 2><<<qgrid, 128, xiBytes, st>>>(m, pv, b);
             } else {
                 k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_NONE, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
-                if (merged) k_fastm<CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
-                else k_fast<CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
+                k_fast<CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
             }
             ctx->launches += 2;
         }

@@ -480,7 +480,7 @@ int cpf_substeps(cpf_context *ctx, int n, double dt)
         return fail(ctx, CPF_ERR_INVALID, "vertex interpolation: no vertex field (cpf_update_velocity after an upload with interp = VERTEX, or cpf_update_vertex_velocity)");
     cudaSetDevice(ctx->device);
     CPF_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    const int fuse = std::min(ctx->cfg.fuse_substeps > 0 ? ctx->cfg.fuse_substeps : 1, 16); // k_fastm stages 3 floats per fused sub-step in smem
+    const int fuse = std::min(ctx->cfg.fuse_substeps > 0 ? ctx->cfg.fuse_substeps : 1, 16); // k_fast stages 3 floats per fused sub-step in smem
     int done = 0;
     while (done < n) {
         if (ctx->cfg.sort_interval > 0 && ctx->since_sort >= ctx->cfg.sort_interval) {
