@@ -260,6 +260,9 @@ int cpf_mesh_upload_poly(cpf_context *ctx, int nPoints, const double *points, in
     for (int f = 0; f < nFaces; ++f) {
         const int sz = faceOffsets[f + 1] - faceOffsets[f];
         if (sz < 3) return fail(ctx, CPF_ERR_INVALID, "face %d has fewer than 3 points", f);
+        if (tetBasePt && (tetBasePt[f] < 0 || tetBasePt[f] >= sz)) return fail(ctx, CPF_ERR_INVALID, "tetBasePt[%d] out of range", f);
+        for (int q = faceOffsets[f]; q < faceOffsets[f + 1]; ++q)
+            if (faceVerts[q] < 0 || faceVerts[q] >= nPoints) return fail(ctx, CPF_ERR_INVALID, "face %d references point %d out of range", f, faceVerts[q]);
         nTets += (long long)(sz - 2) * (f < nInternal ? 2 : 1);
     }
     std::vector<int> tets((size_t)nTets * 4), tetPatch((size_t)nTets, -1);
@@ -319,6 +322,11 @@ int cpf_mesh_upload_tets(cpf_context *ctx, int nVerts, const double *positions, 
     if (!positions || !tetVerts || nVerts <= 0 || nTets <= 0) return fail(ctx, CPF_ERR_INVALID, "cpf_mesh_upload_tets: bad arguments");
     cudaSetDevice(ctx->device);
     if (!tetCell) nCells = (int)nTets;
+    else {
+        if (nCells <= 0) return fail(ctx, CPF_ERR_INVALID, "cpf_mesh_upload_tets: nCells must be positive when tetCell is given");
+        for (long long t = 0; t < nTets; ++t)
+            if (tetCell[t] < 0 || tetCell[t] >= nCells) return fail(ctx, CPF_ERR_INVALID, "tetCell[%lld] = %d out of range", t, tetCell[t]);
+    }
     bbox_of(ctx, nVerts, positions, true);
     int rc = build_device_mesh(ctx, nVerts, positions, nTets, tetVerts, tetCell, nullptr, nCells, 0, false);
     if (rc) return rc;

@@ -179,11 +179,17 @@ int build_bvh(cpf_context *ctx)
     free_bvh(ctx);
     cudaStream_t st = ctx->stream;
     const long long nT = ctx->nTets;
-    unsigned long long *d_k = nullptr, *d_k2 = nullptr;
-    int *d_id = nullptr;
-    CPF_CUDA(ctx, cudaMalloc(&d_k, sizeof(unsigned long long) * (size_t)nT));
-    CPF_CUDA(ctx, cudaMalloc(&d_k2, sizeof(unsigned long long) * (size_t)nT));
-    CPF_CUDA(ctx, cudaMalloc(&d_id, sizeof(int) * (size_t)nT));
+    struct Tmp { // freed on every return path
+        unsigned long long *k = nullptr, *k2 = nullptr;
+        int *id = nullptr;
+        void *tmp = nullptr;
+        ~Tmp() { cudaFree(k); cudaFree(k2); cudaFree(id); cudaFree(tmp); }
+    } T;
+    CPF_CUDA(ctx, cudaMalloc(&T.k, sizeof(unsigned long long) * (size_t)nT));
+    CPF_CUDA(ctx, cudaMalloc(&T.k2, sizeof(unsigned long long) * (size_t)nT));
+    CPF_CUDA(ctx, cudaMalloc(&T.id, sizeof(int) * (size_t)nT));
+    unsigned long long *d_k = T.k, *d_k2 = T.k2;
+    int *d_id = T.id;
     CPF_CUDA(ctx, cudaMalloc(&ctx->d_bvh_tet, sizeof(int) * (size_t)nT));
     double3 lo = make_double3(ctx->bbox_lo[0], ctx->bbox_lo[1], ctx->bbox_lo[2]);
     double3 inv;
@@ -193,9 +199,8 @@ int build_bvh(cpf_context *ctx)
     k_morton<<<(unsigned)((nT + 255) / 256), 256, 0, st>>>(nT, ctx->d_tetv, ctx->d_vpos, lo, inv, d_k, d_id);
     size_t tmpBytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, d_k, d_k2, d_id, ctx->d_bvh_tet, nT, 0, 63, st);
-    void *d_tmp = nullptr;
-    CPF_CUDA(ctx, cudaMalloc(&d_tmp, tmpBytes));
-    CPF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k, d_k2, d_id, ctx->d_bvh_tet, nT, 0, 63, st));
+    CPF_CUDA(ctx, cudaMalloc(&T.tmp, tmpBytes));
+    CPF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(T.tmp, tmpBytes, d_k, d_k2, d_id, ctx->d_bvh_tet, nT, 0, 63, st));
     ctx->launches += 5;
 
     long long n = (nT + 7) / 8;
@@ -234,7 +239,6 @@ int build_bvh(cpf_context *ctx)
                                       cudaMemcpyDeviceToDevice, st));
     }
     CPF_CUDA(ctx, cudaStreamSynchronize(st));
-    cudaFree(d_k); cudaFree(d_k2); cudaFree(d_id); cudaFree(d_tmp);
     return CPF_OK;
 }
 

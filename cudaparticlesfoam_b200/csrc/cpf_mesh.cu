@@ -20,12 +20,20 @@
 
 namespace cpf {
 
-enum MeshFlag { MF_REPEATED_VERTEX = 1, MF_BAD_VOLUME = 2, MF_ZERO_DET = 4, MF_NONMANIFOLD = 8, MF_ORIENTATION = 16, MF_OPEN_FACE = 32 };
+enum MeshFlag { MF_REPEATED_VERTEX = 1, MF_BAD_VOLUME = 2, MF_ZERO_DET = 4, MF_NONMANIFOLD = 8, MF_ORIENTATION = 16, MF_OPEN_FACE = 32, MF_BAD_INDEX = 64 };
+
+// scoped device allocation for the builder's temporaries (freed on every return path)
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)); }
+    operator T *() const { return p; }
+};
 
 struct FaceEntry { int c; int tf; }; // third vertex id, (tet<<2 | sorted face slot)
 
 // One thread per tet: validate, sort the vertex ids, derive perm/flip code, emit 4 face keys.
-__global__ void k_prepare_tets(long long nTets, const int4 *__restrict__ tetref, const double4 *__restrict__ vpos,
+__global__ void k_prepare_tets(long long nTets, int nVerts, const int4 *__restrict__ tetref, const double4 *__restrict__ vpos,
                                int4 *__restrict__ tetv, uint16_t *__restrict__ tetcode, unsigned long long *__restrict__ keys,
                                int *__restrict__ entryIdx, FaceEntry *__restrict__ entries, unsigned *__restrict__ flags,
                                unsigned long long *__restrict__ hminBits, int bits)
@@ -35,6 +43,14 @@ __global__ void k_prepare_tets(long long nTets, const int4 *__restrict__ tetref,
     const int4 r = tetref[t];
     int id[4] = { r.x, r.y, r.z, r.w };
     unsigned f = 0;
+    if ((unsigned)id[0] >= (unsigned)nVerts || (unsigned)id[1] >= (unsigned)nVerts || (unsigned)id[2] >= (unsigned)nVerts ||
+        (unsigned)id[3] >= (unsigned)nVerts) {
+        atomicOr(flags, (unsigned)MF_BAD_INDEX); // never touch positions through a bad index
+        tetv[t] = make_int4(0, 0, 0, 0);
+        tetcode[t] = 0;
+        for (int k = 0; k < 4; ++k) { keys[4 * t + k] = ~0ull; entryIdx[4 * t + k] = (int)(4 * t + k); entries[4 * t + k] = FaceEntry{ -1, (int)((t << 2) | k) }; }
+        return;
+    }
     if (id[0] == id[1] || id[0] == id[2] || id[0] == id[3] || id[1] == id[2] || id[1] == id[3] || id[2] == id[3]) f |= MF_REPEATED_VERTEX;
     const D3 A = ld_vertex(vpos, id[0]), B = ld_vertex(vpos, id[1]), C = ld_vertex(vpos, id[2]), D = ld_vertex(vpos, id[3]);
     // HostTetMesh.h:334-343 volume sign test: double arithmetic without contraction, narrowed to float
@@ -235,29 +251,34 @@ static void free_mesh(cpf_context *ctx)
     ctx->have_mesh = false;
 }
 
-int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, long long nTets, const int *tetVerts,
-                      const int *tetCell, const int *tetPatch, long long nCells, int nPoints, bool cellFromVertex)
+static int mesh_error(cpf_context *ctx, unsigned flags)
 {
-    if (nVerts <= 0 || nTets <= 0 || nCells <= 0) return fail(ctx, CPF_ERR_INVALID, "empty mesh");
-    if (nTets >= (1ll << 29)) return fail(ctx, CPF_ERR_INVALID, "more than 2^29 tets per GPU are not supported");
-    free_mesh(ctx);
-    cudaStream_t st = ctx->stream;
-    ctx->nVerts = nVerts; ctx->nTets = nTets; ctx->nCells = nCells; ctx->nPoints = nPoints;
-    ctx->cellFromVertex = cellFromVertex;
+    return fail(ctx, CPF_ERR_MESH, "invalid tet mesh:%s%s%s%s%s%s%s", (flags & MF_BAD_INDEX) ? " vertex id out of range;" : "",
+                (flags & MF_REPEATED_VERTEX) ? " repeated vertex in a tet;" : "",
+                (flags & MF_BAD_VOLUME) ? " zero or negative tet volume (orient tets so that det(A,B,C,D) > 0);" : "",
+                (flags & MF_ZERO_DET) ? " degenerate tet (det == 0);" : "",
+                (flags & MF_NONMANIFOLD) ? " face shared by more than two tets;" : "",
+                (flags & MF_ORIENTATION) ? " inconsistent face orientation;" : "",
+                (flags & MF_OPEN_FACE) ? " interior tet face without a neighbour;" : "");
+}
 
-    // -- raw uploads (async from the caller's buffers; pageable memory falls back to staged copies)
-    double *d_xyz = nullptr;
-    int4 *d_tetref = nullptr;
-    int *d_tetPatch = nullptr;
-    CPF_CUDA(ctx, cudaMalloc(&d_xyz, sizeof(double) * 3 * (size_t)nVerts));
-    CPF_CUDA(ctx, cudaMalloc(&d_tetref, sizeof(int4) * (size_t)nTets));
+static int build_device_mesh_impl(cpf_context *ctx, long long nVerts, const double *pos, long long nTets, const int *tetVerts,
+                                  const int *tetCell, const int *tetPatch, long long nCells)
+{
+    cudaStream_t st = ctx->stream;
+    // -- raw uploads
+    DevBuf<double> d_xyz;
+    DevBuf<int4> d_tetref;
+    DevBuf<int> d_tetPatch;
+    CPF_CUDA(ctx, d_xyz.alloc(3 * (size_t)nVerts));
+    CPF_CUDA(ctx, d_tetref.alloc((size_t)nTets));
     CPF_CUDA(ctx, cudaMemcpyAsync(d_xyz, pos, sizeof(double) * 3 * (size_t)nVerts, cudaMemcpyHostToDevice, st));
     CPF_CUDA(ctx, cudaMemcpyAsync(d_tetref, tetVerts, sizeof(int4) * (size_t)nTets, cudaMemcpyHostToDevice, st));
     if (tetPatch) {
-        CPF_CUDA(ctx, cudaMalloc(&d_tetPatch, sizeof(int) * (size_t)nTets));
+        CPF_CUDA(ctx, d_tetPatch.alloc((size_t)nTets));
         CPF_CUDA(ctx, cudaMemcpyAsync(d_tetPatch, tetPatch, sizeof(int) * (size_t)nTets, cudaMemcpyHostToDevice, st));
     }
-    if (!cellFromVertex) {
+    if (!ctx->cellFromVertex) {
         CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetcell, sizeof(int) * (size_t)nTets));
         if (tetCell) CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tetcell, tetCell, sizeof(int) * (size_t)nTets, cudaMemcpyHostToDevice, st));
         else {
@@ -280,34 +301,38 @@ int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, lon
 
     // -- per-tet preparation + face keys
     const long long nE = 4 * nTets;
-    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr, *d_hmin = nullptr, *d_nb = nullptr;
-    int *d_idx = nullptr, *d_idx2 = nullptr;
-    FaceEntry *d_entries = nullptr;
-    unsigned *d_flags = nullptr;
-    CPF_CUDA(ctx, cudaMalloc(&d_keys, sizeof(unsigned long long) * (size_t)nE));
-    CPF_CUDA(ctx, cudaMalloc(&d_keys2, sizeof(unsigned long long) * (size_t)nE));
-    CPF_CUDA(ctx, cudaMalloc(&d_idx, sizeof(int) * (size_t)nE));
-    CPF_CUDA(ctx, cudaMalloc(&d_idx2, sizeof(int) * (size_t)nE));
-    CPF_CUDA(ctx, cudaMalloc(&d_entries, sizeof(FaceEntry) * (size_t)nE));
-    CPF_CUDA(ctx, cudaMalloc(&d_flags, sizeof(unsigned)));
-    CPF_CUDA(ctx, cudaMalloc(&d_hmin, sizeof(unsigned long long)));
-    CPF_CUDA(ctx, cudaMalloc(&d_nb, sizeof(unsigned long long)));
+    DevBuf<unsigned long long> d_keys, d_keys2, d_hmin, d_nb;
+    DevBuf<int> d_idx, d_idx2;
+    DevBuf<FaceEntry> d_entries;
+    DevBuf<unsigned> d_flags;
+    CPF_CUDA(ctx, d_keys.alloc((size_t)nE));
+    CPF_CUDA(ctx, d_keys2.alloc((size_t)nE));
+    CPF_CUDA(ctx, d_idx.alloc((size_t)nE));
+    CPF_CUDA(ctx, d_idx2.alloc((size_t)nE));
+    CPF_CUDA(ctx, d_entries.alloc((size_t)nE));
+    CPF_CUDA(ctx, d_flags.alloc(1));
+    CPF_CUDA(ctx, d_hmin.alloc(1));
+    CPF_CUDA(ctx, d_nb.alloc(1));
     CPF_CUDA(ctx, cudaMemsetAsync(d_flags, 0, sizeof(unsigned), st));
     CPF_CUDA(ctx, cudaMemsetAsync(d_nb, 0, sizeof(unsigned long long), st));
     CPF_CUDA(ctx, cudaMemsetAsync(d_hmin, 0x7f, sizeof(unsigned long long), st)); // huge positive double
     int bits = 1;
     while ((1ll << bits) < nVerts) ++bits;
-    k_prepare_tets<<<(unsigned)((nTets + 127) / 128), 128, 0, st>>>(nTets, d_tetref, ctx->d_vpos, ctx->d_tetv, ctx->d_tetcode,
+    k_prepare_tets<<<(unsigned)((nTets + 127) / 128), 128, 0, st>>>(nTets, (int)nVerts, d_tetref, ctx->d_vpos, ctx->d_tetv, ctx->d_tetcode,
                                                                    d_keys, d_idx, d_entries, d_flags, d_hmin, bits);
     ctx->launches++;
     CPF_CUDA(ctx, cudaGetLastError());
+    unsigned flags = 0;
+    CPF_CUDA(ctx, cudaMemcpyAsync(&flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost, st));
+    CPF_CUDA(ctx, cudaStreamSynchronize(st));
+    if (flags) return mesh_error(ctx, flags); // nothing downstream may run on a malformed tet list
 
     // -- one radix sort on (smallest, second smallest) vertex id, 2*bits significant key bits
     size_t tmpBytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, d_keys, d_keys2, d_idx, d_idx2, (long long)nE, 0, 2 * bits, st);
-    void *d_tmp = nullptr;
-    CPF_CUDA(ctx, cudaMalloc(&d_tmp, tmpBytes));
-    CPF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_keys, d_keys2, d_idx, d_idx2, (long long)nE, 0, 2 * bits, st));
+    cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, d_keys.p, d_keys2.p, d_idx.p, d_idx2.p, (long long)nE, 0, 2 * bits, st);
+    DevBuf<unsigned char> d_tmp;
+    CPF_CUDA(ctx, d_tmp.alloc(tmpBytes));
+    CPF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp.p, tmpBytes, d_keys.p, d_keys2.p, d_idx.p, d_idx2.p, (long long)nE, 0, 2 * bits, st));
     ctx->launches += 4;
 
     k_link_faces<<<(unsigned)((nE + 127) / 128), 128, 0, st>>>(nE, d_keys2, d_idx2, d_entries, ctx->d_tetcode, d_tetPatch,
@@ -323,34 +348,41 @@ int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, lon
     ctx->launches++;
     CPF_CUDA(ctx, cudaGetLastError());
 
-    unsigned flags = 0;
     unsigned long long hbits = 0, nb = 0;
     CPF_CUDA(ctx, cudaMemcpyAsync(&flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost, st));
     CPF_CUDA(ctx, cudaMemcpyAsync(&hbits, d_hmin, sizeof hbits, cudaMemcpyDeviceToHost, st));
     CPF_CUDA(ctx, cudaMemcpyAsync(&nb, d_nb, sizeof nb, cudaMemcpyDeviceToHost, st));
     CPF_CUDA(ctx, cudaStreamSynchronize(st));
-    cudaFree(d_xyz); cudaFree(d_tetref); cudaFree(d_tetPatch); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_idx);
-    cudaFree(d_idx2); cudaFree(d_entries); cudaFree(d_flags); cudaFree(d_hmin); cudaFree(d_nb); cudaFree(d_tmp);
-    if (flags) {
-        free_mesh(ctx);
-        return fail(ctx, CPF_ERR_MESH,
-                    "invalid tet mesh:%s%s%s%s%s%s", (flags & MF_REPEATED_VERTEX) ? " repeated vertex in a tet;" : "",
-                    (flags & MF_BAD_VOLUME) ? " zero or negative tet volume (orient tets so that det(A,B,C,D) > 0);" : "",
-                    (flags & MF_ZERO_DET) ? " degenerate tet (det == 0);" : "",
-                    (flags & MF_NONMANIFOLD) ? " face shared by more than two tets;" : "",
-                    (flags & MF_ORIENTATION) ? " inconsistent face orientation;" : "",
-                    (flags & MF_OPEN_FACE) ? " interior tet face without a neighbour;" : "");
-    }
+    if (flags) return mesh_error(ctx, flags);
     double hmin;
     memcpy(&hmin, &hbits, sizeof hmin);
     ctx->hmin = hmin;
     ctx->nBoundaryFaces = (long long)nb;
     // guard band of the filtered path in barycentric units: at least 100x the reference's absolute
     // 1e-13 tolerance measured against the smallest tet height, never below 1e-7
-    double g = 1e-11 / hmin;
+    const double g = 1e-11 / hmin;
     ctx->guard = g > 1e-7 ? g : 1e-7;
     ctx->have_mesh = true;
     return build_bvh(ctx);
+}
+
+int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, long long nTets, const int *tetVerts,
+                      const int *tetCell, const int *tetPatch, long long nCells, int nPoints, bool cellFromVertex)
+{
+    if (nVerts <= 0 || nTets <= 0 || nCells <= 0) return fail(ctx, CPF_ERR_INVALID, "empty mesh");
+    if (nTets >= (1ll << 29)) return fail(ctx, CPF_ERR_INVALID, "more than 2^29 tets per GPU are not supported");
+    if (nVerts >= (1ll << 31)) return fail(ctx, CPF_ERR_INVALID, "more than 2^31 vertices are not supported");
+    free_mesh(ctx);
+    ctx->nVerts = nVerts; ctx->nTets = nTets; ctx->nCells = nCells; ctx->nPoints = nPoints;
+    ctx->cellFromVertex = cellFromVertex;
+    const int rc = build_device_mesh_impl(ctx, nVerts, pos, nTets, tetVerts, tetCell, tetPatch, nCells);
+    if (rc != CPF_OK) { // leave the context without a mesh, never with a half-built one
+        const std::string keep = ctx->err;
+        cudaStreamSynchronize(ctx->stream);
+        free_mesh(ctx);
+        ctx->err = keep;
+    }
+    return rc;
 }
 
 MeshView mesh_view(const cpf_context *ctx)

@@ -57,7 +57,19 @@ def test_invalid_meshes_are_rejected(synth, orc):
     bad[5, [1, 2]] = bad[5, [2, 1]]  # inverted tet
     with pytest.raises(api.CpfError) as e:
         tr.upload_tets(mesh.pos, bad, mesh.tet_cell, pm.n_cells)
-    assert e.value.code == 3
+    assert e.value.code == 3 and "volume" in str(e.value)
+    bad = mesh.idx.copy()
+    bad[7, 2] = mesh.pos.shape[0] + 5  # vertex id out of range: must be refused, not dereferenced
+    with pytest.raises(api.CpfError) as e:
+        tr.upload_tets(mesh.pos, bad, mesh.tet_cell, pm.n_cells)
+    assert e.value.code == 3 and "out of range" in str(e.value)
+    bad_cell = mesh.tet_cell.copy()
+    bad_cell[3] = pm.n_cells
+    with pytest.raises(api.CpfError) as e:
+        tr.upload_tets(mesh.pos, mesh.idx, bad_cell, pm.n_cells)
+    assert e.value.code == 1
+    with pytest.raises(api.CpfError):
+        tr.mesh_info()  # no half-built mesh is left behind by a failed upload
     tr.upload_tets(mesh.pos, mesh.idx, mesh.tet_cell, pm.n_cells)  # the handle is still usable
     tr.close()
 
