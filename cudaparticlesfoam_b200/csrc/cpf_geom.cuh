@@ -107,6 +107,7 @@ struct MeshView {
     long long nTets;
     int nCells;
     double guard; // barycentric guard band of the filtered path
+    float guardf; // the same, rounded up to fp32
 };
 
 CPF_DEV int link_at(int4 l, int j) { return j == 0 ? l.x : (j == 1 ? l.y : (j == 2 ? l.z : l.w)); }
@@ -243,19 +244,21 @@ CPF_DEV int sel4(int a, int b, int c, int d, int k)
 // ------------------------------------------------------------------------------------------------
 // fp32 fast walk (k_fast).
 //
-// One self-contained 64-byte record per tet: links, the three lower-id vertices as fp32 offsets
-// from the tet's highest-id vertex (the "origin": for OpenFOAM decompositions the cell centre, so
-// all 12 tets of a cell share it), the origin's vertex id, 6*volume and the largest |offset|.
-// A hop is ONE 64-byte load; the fp64 origin position is fetched only when the walk enters
-// another cell.  All predicates run on the fp32 pipe.  Soundness: every comparison is made against
-// g = G*|V6| + ERR, where ERR = 2^-16 * E^2 * (E + 3(|r|+|d|)) bounds the rounding of the inputs
-// (offsets, r, d: one rounding each, relative 2^-24) and of the ~10 float operations behind each
-// plane function (|a_j| <= 6|r|E^2, see DESIGN.md "fp32 filter"); a wrongly chosen exit is caught
-// by C3.  Whatever fails the test is deferred to the exact kernel, so results stay bit-identical.
+// One self-contained 64-byte record per tet: links, the un-normalised inward normals of the three
+// faces through the tet's highest-id vertex (the "origin": for OpenFOAM decompositions the cell
+// centre, so all 12 tets of a cell share it) -- computed in fp64 at build time, rounded once --,
+// the origin's vertex id, 6*volume and the largest |vertex offset| E.  A hop is ONE 64-byte load;
+// the fp64 origin position is fetched only when the walk enters another cell.  All predicates run
+// on the fp32 pipe.  Soundness: every comparison is made against g = G*|V6| + ERR, where
+// ERR = 2^-16 * E^2 * (E + 3(|r|+|d|)) bounds the rounding of the inputs (normals, r, d: one
+// rounding each, relative 2^-24, |N_c| <= 2E^2) and of the float operations behind each plane
+// function (<= 2^-24 (24 E^3 + 144 |r| E^2), see DESIGN.md "fp32 filter"); a wrongly chosen exit is
+// caught by C3.  Whatever fails the test is deferred to the exact kernel, so results stay
+// bit-identical.
 // ------------------------------------------------------------------------------------------------
 struct Fast32 {
     int4 link;
-    float X[3][3];
+    float N[3][3];
     int origin;
     float V6, E;
 };
@@ -272,92 +275,25 @@ CPF_DEV void f32_load(const MeshView &m, int tet, Fast32 &f)
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) f.X[k][c] = __uint_as_float(w[4 + 3 * k + c]);
+        for (int c = 0; c < 3; ++c) f.N[k][c] = __uint_as_float(w[4 + 3 * k + c]);
     f.origin = (int)w[13];
     f.V6 = __uint_as_float(w[14]);
     f.E = __uint_as_float(w[15]);
 }
 
-// Returns the final tet (f then holds its record, O its origin) or CPF_NEED_EXACT.
-// Records are stored positively oriented (V6 > 0: slots 1 and 2 are exchanged at build time where
-// needed, links carry the STORED slot of the entry face), so "inside" is a_j >= 0 without a sign.
-CPF_DEV int walk_fast32(const MeshView &m, Fast32 &f, D3 &O, int tet0, D3 P0, D3 disp, unsigned &hops)
+CPF_DEV float rcp_ftz(float x)
 {
-    const float INF = __int_as_float(0x7f800000);
-    float rx = (float)(P0.x - O.x), ry = (float)(P0.y - O.y), rz = (float)(P0.z - O.z);
-    const float dx = (float)disp.x, dy = (float)disp.y, dz = (float)disp.z;
-    const float Dd = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
-    float RD3 = 3.f * (fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) + Dd);
-    const float G = (float)m.guard;
-    int cur = tet0, in_j = -1;
-    float t_in = 0.f;
-    for (int it = 0; it < 48; ++it) {
-        hops++;
-        const float (&X)[3][3] = f.X;
-        // un-normalised inward normals of the faces opposite slots 0,1,2 (the origin is slot 3)
-        const float n0x = X[1][1] * X[2][2] - X[1][2] * X[2][1], n0y = X[1][2] * X[2][0] - X[1][0] * X[2][2], n0z = X[1][0] * X[2][1] - X[1][1] * X[2][0];
-        const float n1x = X[2][1] * X[0][2] - X[2][2] * X[0][1], n1y = X[2][2] * X[0][0] - X[2][0] * X[0][2], n1z = X[2][0] * X[0][1] - X[2][1] * X[0][0];
-        const float n2x = X[0][1] * X[1][2] - X[0][2] * X[1][1], n2y = X[0][2] * X[1][0] - X[0][0] * X[1][2], n2z = X[0][0] * X[1][1] - X[0][1] * X[1][0];
-        const float V = f.V6;
-        float a[4], b[4], e[4];
-        a[0] = rx * n0x + ry * n0y + rz * n0z;
-        a[1] = rx * n1x + ry * n1y + rz * n1z;
-        a[2] = rx * n2x + ry * n2y + rz * n2z;
-        b[0] = dx * n0x + dy * n0y + dz * n0z;
-        b[1] = dx * n1x + dy * n1y + dz * n1z;
-        b[2] = dx * n2x + dy * n2y + dz * n2z;
-        a[3] = V - a[0] - a[1] - a[2];
-        b[3] = -(b[0] + b[1] + b[2]);
-        const float E = f.E;
-        const float g = fmaf(G, V, 1.52587890625e-5f * (E * E) * (E + RD3));
-        // C1 (entry/start point vs the other faces), C2 (end point vs every face plane)
-        float c1m = INF, eam = INF, emin = INF;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            e[j] = a[j] + b[j];
-            const float c1 = (j == in_j) ? INF : fmaf(t_in, b[j], a[j]);
-            c1m = fminf(c1m, c1);
-            eam = fminf(eam, fabsf(e[j]));
-            emin = fminf(emin, e[j]);
-        }
-        if (!(fminf(c1m, eam) >= g) | !(V > 1e-30f)) return CPF_NEED_EXACT;
-        if (emin > 0.f) return cur;
-        // exit face: smallest crossing parameter among the faces the segment leaves through
-        float t = INF;
-        int js = -1;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool cand = (b[j] < 0.f) & (e[j] < 0.f) & (j != in_j);
-            const float tj = cand ? __fdividef(a[j], -b[j]) : INF;
-            const bool better = tj < t;
-            t = better ? tj : t;
-            js = better ? j : js;
-        }
-        // C3: the exit point must be clear of every other face (edges/vertices, ties of dT)
-        float c3m = INF;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) c3m = fminf(c3m, (j == js) ? INF : fmaf(t, b[j], a[j]));
-        const int link = sel4(f.link.x, f.link.y, f.link.z, f.link.w, js);
-        if ((js < 0) | !(c3m >= g) | !(t > t_in) | !(t <= 1.f) | (link < 0)) return CPF_NEED_EXACT; // incl. walls
-        cur = link >> 2;
-        in_j = link & 3;
-        t_in = t;
-        const int oldOrigin = f.origin;
-        f32_load(m, cur, f);
-        if (f.origin != oldOrigin) { // entered another cell: re-express the start point
-            O = ld_vertex(m.vpos, f.origin);
-            rx = (float)(P0.x - O.x); ry = (float)(P0.y - O.y); rz = (float)(P0.z - O.z);
-            RD3 = 3.f * (fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) + Dd);
-        }
-    }
-    return CPF_NEED_EXACT;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
-
 // ------------------------------------------------------------------------------------------------
-// The same walk, one visit at a time (k_fastm).  Lanes of a warp need different numbers of tet
-// visits per sub-step; running the visits of ALL fused sub-steps of a lane through one loop keeps
+// The walk, one tet visit at a time.  Lanes of a warp need different numbers of tet visits per
+// sub-step; k_fast runs the visits of ALL fused sub-steps of a lane through one loop, which keeps
 // the lanes busy until their whole chunk is done instead of idling at every sub-step boundary.
+// Records are stored positively oriented (V6 > 0: slots 1 and 2 are exchanged at build time where
+// needed, links carry the STORED slot of the entry face), so "inside" is a_j >= 0 without a sign.
 // ------------------------------------------------------------------------------------------------
 struct WalkF {
     float rx, ry, rz, dx, dy, dz, RD3, Dd, t_in;
@@ -376,26 +312,22 @@ CPF_DEV void walkf_begin(WalkF &ws, const D3 &O, const D3 &P0, const D3 &disp, i
     ws.cur = tet;
 }
 
-// one iteration of walk_fast32 (identical predicates)
 CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, WalkF &ws)
 {
     const float INF = __int_as_float(0x7f800000);
-    const float (&X)[3][3] = f.X;
-    const float n0x = X[1][1] * X[2][2] - X[1][2] * X[2][1], n0y = X[1][2] * X[2][0] - X[1][0] * X[2][2], n0z = X[1][0] * X[2][1] - X[1][1] * X[2][0];
-    const float n1x = X[2][1] * X[0][2] - X[2][2] * X[0][1], n1y = X[2][2] * X[0][0] - X[2][0] * X[0][2], n1z = X[2][0] * X[0][1] - X[2][1] * X[0][0];
-    const float n2x = X[0][1] * X[1][2] - X[0][2] * X[1][1], n2y = X[0][2] * X[1][0] - X[0][0] * X[1][2], n2z = X[0][0] * X[1][1] - X[0][1] * X[1][0];
+    const float (&N)[3][3] = f.N;
     const float V = f.V6;
     float a[4], b[4], e[4];
-    a[0] = ws.rx * n0x + ws.ry * n0y + ws.rz * n0z;
-    a[1] = ws.rx * n1x + ws.ry * n1y + ws.rz * n1z;
-    a[2] = ws.rx * n2x + ws.ry * n2y + ws.rz * n2z;
-    b[0] = ws.dx * n0x + ws.dy * n0y + ws.dz * n0z;
-    b[1] = ws.dx * n1x + ws.dy * n1y + ws.dz * n1z;
-    b[2] = ws.dx * n2x + ws.dy * n2y + ws.dz * n2z;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        a[j] = ws.rx * N[j][0] + ws.ry * N[j][1] + ws.rz * N[j][2];
+        b[j] = ws.dx * N[j][0] + ws.dy * N[j][1] + ws.dz * N[j][2];
+    }
     a[3] = V - a[0] - a[1] - a[2];
     b[3] = -(b[0] + b[1] + b[2]);
     const float E = f.E;
-    const float g = fmaf((float)m.guard, V, 1.52587890625e-5f * (E * E) * (E + ws.RD3));
+    const float g = fmaf(m.guardf, V, 1.52587890625e-5f * (E * E) * (E + ws.RD3));
+    // C1 (entry/start point vs the other faces), C2 (end point vs every face plane)
     float c1m = INF, eam = INF, emin = INF;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -407,32 +339,51 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
     }
     if (!(fminf(c1m, eam) >= g) | !(V > 1e-30f)) return CPF_V_REFUSE;
     if (emin > 0.f) return CPF_V_DONE;
-    float t = INF;
-    int js = -1;
+    // Exit face: smallest crossing parameter among the faces whose plane the end point is behind.
+    // (C1 passed and t_in <= 1, so e_j < 0 implies b_j < 0 and a_j >= g > 0: every t_j is positive, and
+    // positive floats order like their bit patterns -- the face index rides in the two lowest mantissa
+    // bits through one integer min.  A flushed denormal b_j gives t_j = +inf, which fails t <= 1 below.)
+    unsigned key = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const bool cand = (b[j] < 0.f) & (e[j] < 0.f) & (j != ws.in_j);
-        const float tj = cand ? __fdividef(a[j], -b[j]) : INF;
-        const bool better = tj < t;
-        t = better ? tj : t;
-        js = better ? j : js;
+        const bool cand = (e[j] < 0.f) & (j != ws.in_j);
+        const float tj = cand ? a[j] * rcp_ftz(-b[j]) : INF;
+        key = min(key, (__float_as_uint(tj) & ~3u) | (unsigned)j);
     }
+    const int js = (int)(key & 3u);
+    const float t = __uint_as_float(key & ~3u);
+    // C3: the exit point must be clear of every other face (edges/vertices, ties of dT)
     float c3m = INF;
 #pragma unroll
     for (int j = 0; j < 4; ++j) c3m = fminf(c3m, (j == js) ? INF : fmaf(t, b[j], a[j]));
     const int link = sel4(f.link.x, f.link.y, f.link.z, f.link.w, js);
-    if ((js < 0) | !(c3m >= g) | !(t > ws.t_in) | !(t <= 1.f) | (link < 0)) return CPF_V_REFUSE;
+    if (!((c3m >= g) && (t > ws.t_in) && (t <= 1.f) && (link >= 0))) return CPF_V_REFUSE; // incl. walls, no candidate
     ws.cur = link >> 2;
     ws.in_j = link & 3;
     ws.t_in = t;
     const int oldOrigin = f.origin;
     f32_load(m, ws.cur, f);
-    if (f.origin != oldOrigin) {
+    if (f.origin != oldOrigin) { // entered another cell: re-express the start point
         O = ld_vertex(m.vpos, f.origin);
         ws.rx = (float)(P0.x - O.x); ws.ry = (float)(P0.y - O.y); ws.rz = (float)(P0.z - O.z);
         ws.RD3 = 3.f * (fmaxf(fmaxf(fabsf(ws.rx), fabsf(ws.ry)), fabsf(ws.rz)) + ws.Dd);
     }
     return CPF_V_HOP;
+}
+
+// Whole walk of one sub-step (k_fast_inline).  Returns the final tet (f then holds its record, O its
+// origin) or CPF_NEED_EXACT.
+CPF_DEV int walk_fast32(const MeshView &m, Fast32 &f, D3 &O, int tet0, D3 P0, D3 disp, unsigned &hops)
+{
+    WalkF ws;
+    walkf_begin(ws, O, P0, disp, tet0);
+    for (int it = 0; it < 48; ++it) {
+        hops++;
+        const int oc = visit_fast32(m, f, O, P0, ws);
+        if (oc == CPF_V_DONE) return ws.cur;
+        if (oc == CPF_V_REFUSE) break;
+    }
+    return CPF_NEED_EXACT;
 }
 
 } // namespace cpf

@@ -190,21 +190,30 @@ __global__ void k_build_fast(long long nTets, const int4 *__restrict__ tetv, con
             if ((ns == 1 || ns == 2) && sorted_v6(tetv[nt], vpos) < 0.0) ns = 3 - ns;
             lk[k] = (nt << 2) | ns;
         }
-    float Xf[3][3];
+    double X[3][3];
     float E = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const D3 p = ld_vertex(vpos, ids[k]);
-        const double X[3] = { p.x - O.x, p.y - O.y, p.z - O.z };
+        X[k][0] = p.x - O.x; X[k][1] = p.y - O.y; X[k][2] = p.z - O.z;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { Xf[k][c] = (float)X[c]; E = fmaxf(E, fabsf(Xf[k][c])); }
+        for (int c = 0; c < 3; ++c) E = fmaxf(E, fabsf((float)X[k][c]));
     }
     E = E * 1.0000002f; // never below the true maximum
+    // inward normals of the faces opposite slots 0,1,2 (the origin is slot 3): N_j = X_{j+1} x X_{j+2}
+    float Nf[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const double *u = X[(j + 1) % 3], *w = X[(j + 2) % 3];
+        Nf[j][0] = (float)(u[1] * w[2] - u[2] * w[1]);
+        Nf[j][1] = (float)(u[2] * w[0] - u[0] * w[2]);
+        Nf[j][2] = (float)(u[0] * w[1] - u[1] * w[0]);
+    }
     uint4 *o = out + 4 * t;
     o[0] = make_uint4((unsigned)lk[0], (unsigned)lk[1], (unsigned)lk[2], (unsigned)lk[3]);
-    o[1] = make_uint4(__float_as_uint(Xf[0][0]), __float_as_uint(Xf[0][1]), __float_as_uint(Xf[0][2]), __float_as_uint(Xf[1][0]));
-    o[2] = make_uint4(__float_as_uint(Xf[1][1]), __float_as_uint(Xf[1][2]), __float_as_uint(Xf[2][0]), __float_as_uint(Xf[2][1]));
-    o[3] = make_uint4(__float_as_uint(Xf[2][2]), (unsigned)v.w, __float_as_uint((float)fabs(v6)), __float_as_uint(E));
+    o[1] = make_uint4(__float_as_uint(Nf[0][0]), __float_as_uint(Nf[0][1]), __float_as_uint(Nf[0][2]), __float_as_uint(Nf[1][0]));
+    o[2] = make_uint4(__float_as_uint(Nf[1][1]), __float_as_uint(Nf[1][2]), __float_as_uint(Nf[2][0]), __float_as_uint(Nf[2][1]));
+    o[3] = make_uint4(__float_as_uint(Nf[2][2]), (unsigned)v.w, __float_as_uint((float)fabs(v6)), __float_as_uint(E));
 }
 
 // reference face normals, once per (tet, sorted face): see face_normal_exact
@@ -395,6 +404,7 @@ MeshView mesh_view(const cpf_context *ctx)
     m.patch_kind = ctx->d_patch_kind;
     m.nPoints = ctx->nPoints; m.nTets = ctx->nTets; m.nCells = (int)ctx->nCells;
     m.guard = ctx->guard;
+    m.guardf = (float)ctx->guard * 1.0000002f;
     return m;
 }
 
