@@ -447,9 +447,10 @@ __global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshVie
         const long long slot = base + threadIdx.x;
         int deferAt = -1;
         long long i = slot;
-        int s = 0;
+        int s = 0, sBegin = 0;
         bool have = slot < total;
         if (QMODE && have) { const int2 q = sp.queueIn[slot]; i = q.x; s = q.y; have = s < sp.nSub; }
+        sBegin = s;
         double4 p4 = make_double4(0.0, 0.0, 0.0, 0.0);
         int tet = -1;
         if (have) { p4 = ld_stream4(pv.pos + i); tet = ld_stream_i(pv.tet + i); }
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshVie
         Fast32 f;
         D3 O{ 0.0, 0.0, 0.0 }, disp{ 0.0, 0.0, 0.0 };
         WalkF ws;
-        int cell = -1, lastCell = -1, visits = 0;
+        int cell = -1, visits = 0; // cell: the cell whose velocity moved the particle in its latest sub-step
         bool needPro = true;
         if (active && tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
         while (__any_sync(0xffffffffu, active)) {
@@ -494,26 +495,27 @@ __global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshVie
                 }
             }
             if (active) {
-                hops++;
+                ++visits;
                 const int oc = visit_fast32(m, f, O, P, ws);
                 if (oc == CPF_V_DONE) {
                     tet = ws.cur;
                     P = xadd(P, disp);
-                    lastCell = cell;
-                    nsteps++;
+                    hops += visits;
                     needPro = true;
                     if (++s >= sp.nSub) active = false;
-                } else if (oc == CPF_V_REFUSE || ++visits >= 48) {
+                } else if (oc == CPF_V_REFUSE || visits >= 48) {
+                    hops += visits;
                     deferAt = s;
                     active = false;
                 }
             }
         }
         if (live) {
+            nsteps += (unsigned)(s - sBegin);
             st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
             st_stream_i(pv.tet + i, tet);
-            if (sp.writeVel && lastCell >= 0 && deferAt < 0) {
-                const double *uc = m.ucell + 3ll * lastCell;
+            if (sp.writeVel && cell >= 0 && deferAt < 0) {
+                const double *uc = m.ucell + 3ll * cell;
                 st_stream4(pv.vel + i, make_double4(__ldg(uc), __ldg(uc + 1), __ldg(uc + 2), -1.0));
             }
         }

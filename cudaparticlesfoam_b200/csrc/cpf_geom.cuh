@@ -250,11 +250,14 @@ CPF_DEV int sel4(int a, int b, int c, int d, int k)
 // the origin's vertex id, 6*volume and the largest |vertex offset| E.  A hop is ONE 64-byte load;
 // the fp64 origin position is fetched only when the walk enters another cell.  All predicates run
 // on the fp32 pipe.  Soundness: every comparison is made against g = G*|V6| + ERR, where
-// ERR = 2^-16 * E^2 * (E + 3(|r|+|d|)) bounds the rounding of the inputs (normals, r, d: one
-// rounding each, relative 2^-24, |N_c| <= 2E^2) and of the float operations behind each plane
-// function (<= 2^-24 (24 E^3 + 144 |r| E^2), see DESIGN.md "fp32 filter"); a wrongly chosen exit is
-// caught by C3.  Whatever fails the test is deferred to the exact kernel, so results stay
-// bit-identical.
+// ERR = 2^-18 * E^2 * (E + 3(R+D)), R = |r|inf, D = |d|inf, bounds the distance between a computed plane
+// function and its real value.  With u = 2^-24, |N_c| <= 2E^2, V6 <= 6E^3, one rounding on each of N, r, d, V6:
+//   a_j, j<3  (FMUL + 2 FFMA):   inputs 3*4u*R*E^2, operations u*(2+4+6)*R*E^2          -> 24u R E^2
+//   a_3 = V6 - a_0 - a_1 - a_2:  inputs 6u E^3 + 72u R E^2, operations u*(18 E^3 + 36 R E^2) -> u(24 E^3 + 108 R E^2)
+//   b_j likewise with D (b_3 <= 102u D E^2);  e_j = a_j + b_j, fma(t, b_j, a_j) with 0 <= t <= 1: one more rounding
+//   worst case (j = 3): u * E^2 * (30 E + 126 (R + D))  <=  0.66 * 2^-18 * E^2 * (E + 3(R+D)).
+// A wrongly chosen exit is caught by C3.  Whatever fails a test is deferred to the exact kernel, so results
+// stay bit-identical.
 // ------------------------------------------------------------------------------------------------
 struct Fast32 {
     int4 link;
@@ -326,7 +329,7 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
     a[3] = V - a[0] - a[1] - a[2];
     b[3] = -(b[0] + b[1] + b[2]);
     const float E = f.E;
-    const float g = fmaf(m.guardf, V, 1.52587890625e-5f * (E * E) * (E + ws.RD3));
+    const float g = fmaf(m.guardf, V, 3.814697265625e-6f * (E * E) * (E + ws.RD3));
     // C1 (entry/start point vs the other faces), C2 (end point vs every face plane)
     float c1m = INF, eam = INF, emin = INF;
 #pragma unroll
