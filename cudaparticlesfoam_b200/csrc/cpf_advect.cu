@@ -68,15 +68,22 @@ CPF_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+// MUFU approximations (abs. error ~1e-6, ample for a random walk), spelled as the .ftz PTX forms so that no
+// denormal/IEEE fix-up code is emitted: u1 >= 2^-25 and -2 ln u1 >= 2^-24 are normal numbers.  Every kernel
+// draws through this one function, so the deviates of a (particle, sub-step) are the same bits everywhere.
+CPF_DEV float mufu_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+CPF_DEV float mufu_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+CPF_DEV float mufu_sin(float x) { float r; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+CPF_DEV float mufu_cos(float x) { float r; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 CPF_DEV void box_muller_f32(uint32_t x, uint32_t y, double &n0, double &n1)
 {
-    const float u1 = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float u2 = ((float)(y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    // MUFU-based: lg2/sin/cos/sqrt approximations (abs. error ~1e-6) are ample for a random walk
-    const float r = __fsqrt_rn(-2.0f * __logf(u1));
-    const float ang = 6.283185307179586f * u2;
-    n0 = (double)(r * __sinf(ang));
-    n1 = (double)(r * __cosf(ang));
+    const float u1 = __fmaf_rn((float)(x >> 8), 1.0f / 16777216.0f, 0.5f / 16777216.0f);
+    const float u2 = __fmaf_rn((float)(y >> 8), 1.0f / 16777216.0f, 0.5f / 16777216.0f);
+    const float q = __fmul_rn(mufu_lg2(u1), -1.3862943611198906f); // -2 ln u1
+    const float r = __fmul_rn(q, mufu_rsqrt(q));
+    const float ang = __fmul_rn(6.283185307179586f, u2);
+    n0 = (double)__fmul_rn(r, mufu_sin(ang));
+    n1 = (double)__fmul_rn(r, mufu_cos(ang));
 }
 template <> struct Rng<CPF_RNG_PHILOX> {
     uint32_t id, k0, k1;
@@ -304,6 +311,118 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact(const MeshView m,
         st_stream_i(pv.tet + i, tet);
         if (sp.writeVel && velValid && s1 == sp.nSub) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
         if (QMODE == 1) sp.queueIn[slot].y = s1;
+    }
+    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc);
+}
+
+// k_exact_convex<RNG,QMODE>: k_exact for the default ConvexPoly build as ONE merged loop over tet visits.
+// A sub-step in the reference's arithmetic is a chain of visits (load the tet, traceIntet) interleaved with
+// rare events (wall reflection, end of the sub-step); lanes need very different numbers of visits, so the
+// per-lane loop nest of tail_convex_exact leaves most lanes of a warp idle.  Here every iteration performs
+// one visit for every lane that still has work, and the events move a small per-lane state machine:
+//   leg      reflections so far in this sub-step (the reflector's j, ConvexQuery.cu:343-397)
+//   legHops  visits in the current leg (the 50-tet cap of each walk loop)
+// The arithmetic and its order are those of tail_convex_exact; QMODE as for k_exact.
+template <int RNG, int QMODE>
+__global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact_convex(const MeshView m, const ParticleView pv, const StepParams sp)
+{
+    Tally ty{ 0u, 0u, 0u, 0u };
+    unsigned nsteps = 0;
+    const long long total = QMODE ? (long long)*sp.countIn : pv.n;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride) { // warp-uniform trip count
+        const long long slot = base + threadIdx.x;
+        long long i = slot;
+        int s = 0;
+        bool have = slot < total;
+        if (QMODE && have) { const int2 q = sp.queueIn[slot]; i = q.x; s = q.y; have = s < sp.nSub; }
+        const int sStop = (QMODE == 1) ? min(s + 1, sp.nSub) : sp.nSub;
+        double4 p4 = make_double4(0.0, 0.0, 0.0, 0.0);
+        int tet = -1;
+        if (have) { p4 = ld_stream4(pv.pos + i); tet = ld_stream_i(pv.tet + i); }
+        D3 P{ p4.x, p4.y, p4.z };
+        double w = p4.w;
+        const bool live = have && (w != 0.0);
+        bool active = live;
+        D3 vel{ 0.0, 0.0, 0.0 };
+        bool velValid = false;
+        Rng<RNG> rng;
+        if (live) rng.open(pv, i, sp);
+        D3 S{ 0.0, 0.0, 0.0 }, E = S, Phit = S;
+        int cur = -1, in_j = -1, leg = 0, legHops = 0;
+        bool needPro = true;
+        while (__any_sync(0xffffffffu, active)) {
+            if (active && needPro) {
+                if (tet < 0) { w = 0.0; active = false; } // S1: left the domain -> frozen (particles.cu:334-338)
+                else {
+                    const int cell = tet_cell(m, tet, ld_int4(m.tetv, tet));
+                    const D3 disp = displacement<RNG>(m, sp, rng, s, cell, P, vel);
+                    velValid = true;
+                    nsteps++;
+                    ty.exact++;
+                    E = xadd(P, disp); // also the S5 result of a sub-step without wall contact
+                    S = P;
+                    cur = tet; in_j = -1; leg = 0; legHops = 0;
+                    needPro = false;
+                }
+            }
+            if (active) {
+                int4 v;
+                const Tet T = load_tet(m, cur, v);
+                ty.hops++;
+                legHops++;
+                const int out = trace_exact(T, S, E, in_j);
+                bool subDone = false;
+                bool legEnd = out < 0; // the end point lies in this tet
+                if (!legEnd) {
+                    const int link = link_at(T.link, out);
+                    in_j = out;
+                    if (link >= 0) {
+                        cur = link >> 2;
+                        in_j = link & 3;
+                        legEnd = legHops >= 50; // the walk loop's cap: it ends on the tet just entered
+                    } else if (!sp.reflect) { // reflectWall == false: id -(tet+1), particle is moved, frozen next step
+                        tet = -(tet + 1);
+                        P = E;
+                        subDone = true;
+                    } else if (m.patch_kind[-link - 1] == CPF_PATCH_ESCAPE) { // extension, see tail_convex_exact
+                        P = S;
+                        w = 0.0;
+                        tet = -(cur + 1);
+                        ty.esc++;
+                        subDone = true;
+                    } else { // S4: convexReflector, up to 5 wall hits
+                        Phit = S;
+                        ty.refl++;
+                        reflect_exact(T, Phit, E, vel);
+                        legHops = 0;
+                        if (++leg >= 5) { // fifth hit: no further walk, the particle is lost (next == -1)
+                            tet = -1;
+                            P = xadd(Phit, xsub(E, Phit));
+                            subDone = true;
+                        }
+                    }
+                }
+                if (legEnd) {
+                    tet = cur;
+                    P = leg == 0 ? E : xadd(Phit, xsub(E, Phit)); // p = P_hit (S4) then p += disp (S5)
+                    subDone = true;
+                }
+                if (subDone) {
+                    needPro = true;
+                    if (++s >= sStop || w == 0.0) active = false;
+                }
+            }
+        }
+        if (live) {
+            rng.close(pv, i);
+            st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
+            st_stream_i(pv.tet + i, tet);
+            if (sp.writeVel && velValid && (s >= sp.nSub || w == 0.0))
+                st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
+            if (QMODE == 1) sp.queueIn[slot].y = (w == 0.0) ? sp.nSub : s;
+        }
+        if (!QMODE) break;
     }
     flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc);
 }
@@ -708,7 +827,7 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
         CPF_RNG_SWITCH(rng, (k_exact<CPF_LOCATOR_BARY, R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
         ctx->launches++;
     } else if (ctx->cfg.path == CPF_PATH_EXACT) {
-        CPF_RNG_SWITCH(rng, (k_exact<CPF_LOCATOR_CONVEX, R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
+        CPF_RNG_SWITCH(rng, (k_exact_convex<R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
         ctx->launches++;
     } else if (rng == CPF_RNG_XORWOW) {
         k_fast_inline<CPF_RNG_XORWOW, 0><<<grid, 128, 0, st>>>(m, pv, sp);
@@ -730,18 +849,18 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
             b.queueIn = e.queueIn; b.countIn = e.countIn;
             b.queueOut = ctx->d_queue[(r + 1) & 1]; b.countOut = ctx->d_queue_count + r + 1;
             if (rng == CPF_RNG_PHILOX) {
-                k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_PHILOX, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
+                k_exact_convex<CPF_RNG_PHILOX, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
                 k_fast<CPF_RNG_PHILOX, 2><<<qgrid, 128, xiBytes, st>>>(m, pv, b);
             } else {
-                k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_NONE, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
+                k_exact_convex<CPF_RNG_NONE, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
                 k_fast<CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
             }
             ctx->launches += 2;
         }
         StepParams z = sp;
         z.queueIn = ctx->d_queue[rounds & 1]; z.countIn = ctx->d_queue_count + rounds;
-        if (rng == CPF_RNG_PHILOX) k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_PHILOX, 2><<<qgrid, 128, 0, st>>>(m, pv, z);
-        else k_exact<CPF_LOCATOR_CONVEX, CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, z);
+        if (rng == CPF_RNG_PHILOX) k_exact_convex<CPF_RNG_PHILOX, 2><<<qgrid, 128, 0, st>>>(m, pv, z);
+        else k_exact_convex<CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, z);
         ctx->launches++;
     }
     if (ctx->profiling) {
