@@ -179,10 +179,15 @@ CPF_DEV int trace_exact(const Tet &T, D3 &S, D3 E, int in_j)
         if (j == in_j) continue; // inlet face: computed but never accepted by the reference
         D3 A;
         D3 n = face_normal_exact(T, j, A);
-        double fd = xdot(xsub(A, P0), n);
-        double dT = __ddiv_rn(fd, xdot(d, n));
-        if (isinf(dT)) dT = -1.0;
-        if (fd < CPF_TOL && dT > CPF_TOL && dT <= 1.0 && dT < best) {
+        const double fd = xdot(xsub(A, P0), n);
+        const double den = xdot(d, n);
+        // dT = fd/den is accepted only if fd < tol and tol < dT <= 1.  RN(fd/den) is positive only when fd and
+        // den have the same sign, and <= 1 exactly when |fd| <= |den| (distinct doubles differ by >= 2^-53
+        // relative, beyond the rounding midpoint), so the fp64 division is needed for those faces only;
+        // zero/infinite/NaN quotients (-1 in the reference) are rejected by the same tests.
+        if (!(fd < CPF_TOL) || !(fabs(fd) <= fabs(den)) || !((fd < 0.0) == (den < 0.0)) || fd == 0.0) continue;
+        const double dT = __ddiv_rn(fd, den);
+        if (dT > CPF_TOL && dT < best) {
             best = dT;
             out_j = j;
             S.x = __fma_rn(d.x, dT, P0.x);
