@@ -123,6 +123,8 @@ int cpf_create(const cpf_config *cfg, cpf_context **out)
         (e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->evRead[0], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->evRead[1], cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * CNT_COUNT)) != cudaSuccess ||
         (e = cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * CNT_COUNT)) != cudaSuccess) {
         g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
@@ -179,7 +181,7 @@ int cpf_destroy(cpf_context *ctx)
     release_mesh(ctx);
     cudaFree(ctx->d_counters); cudaFree(ctx->d_sort_hist); cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evCopy);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evCopy); cudaEventDestroy(ctx->evRead[0]); cudaEventDestroy(ctx->evRead[1]);
     for (cudaEvent_t ev : ctx->profEvents) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->ownStream); cudaStreamDestroy(ctx->copyStream);
     delete ctx;
@@ -393,7 +395,18 @@ int cpf_update_velocity(cpf_context *ctx, const double *U, int on_device)
     const size_t bytes = sizeof(double) * 3 * (size_t)ctx->nCells;
     // double-buffered: sub-steps already enqueued keep reading the previous field
     const int nb = 1 - ctx->ucur;
-    CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ucell[nb], U, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    if (on_device) {
+        CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ucell[nb], U, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        // Host field: the upload runs on the copy stream, concurrently with the sub-steps already enqueued on the
+        // compute stream (they read the other buffer).  The buffer being overwritten was last read by the kernels
+        // enqueued before the PREVIOUS refresh (evRead[nb]); kernels enqueued from now on wait for the copy.
+        CPF_CUDA(ctx, cudaEventRecord(ctx->evRead[ctx->ucur], ctx->stream));
+        CPF_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evRead[nb], 0));
+        CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ucell[nb], U, bytes, cudaMemcpyHostToDevice, ctx->copyStream));
+        CPF_CUDA(ctx, cudaEventRecord(ctx->evCopy, ctx->copyStream));
+        CPF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopy, 0));
+    }
     ctx->ucur = nb;
     if (ctx->cfg.interp == CPF_INTERP_VERTEX && ctx->d_pc_off) return launch_point_interp(ctx);
     return CPF_OK;

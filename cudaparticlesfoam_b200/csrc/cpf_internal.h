@@ -52,6 +52,7 @@ struct cpf_context {
     std::vector<cudaEvent_t> profEvents; // pairs
     size_t profUsed = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evCopy = nullptr;
+    cudaEvent_t evRead[2] = { nullptr, nullptr }; // per velocity buffer: end of the kernels that read it
     std::string err;
     float last_ms = 0.f;
     long long launches = 0;

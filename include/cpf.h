@@ -127,7 +127,10 @@ int cpf_mesh_download_neighbours(cpf_context *ctx, int *nbr /*[nTets][4]*/);
 /* Replaces the host 12x expansion + cudaUpdateVelocity of src/advect.H:44-57 and
  * cuda/particles.cu:733-749.  U is the solver's cell field [nCells][3] (fp64).  on_device != 0:
  * U is a device pointer (e.g. the NCCL broadcast buffer) and is consumed in place on the
- * library's stream. */
+ * library's stream.  on_device == 0: U is host memory; the upload goes to the idle half of a
+ * double buffer on a copy stream, so it overlaps sub-steps that are still running, and the
+ * sub-steps enqueued afterwards wait for it.  Page-locked host memory is read asynchronously:
+ * keep it unchanged until the next synchronising call (cpf_sync, cpf_stats_get, cpf_download). */
 int cpf_update_velocity(cpf_context *ctx, const double *U, int on_device);
 /* CPF_INTERP_VERTEX: explicit per-vertex field [nVerts][3] (points then centres); if never
  * called the library interpolates point values from the cell field (inverse-distance weights). */

@@ -249,6 +249,31 @@ def test_velocity_refresh_and_advect_cycle_count(synth, orc):
     tr.close()
 
 
+def test_field_upload_one_step_ahead_of_running_substeps(synth, orc):
+    """cpf_update_velocity with a HOST field uploads on the copy stream into the idle half of the double buffer:
+    issuing the refresh for step k+1 while the sub-steps of step k are still running (no synchronisation in
+    between, page-locked source) must neither disturb step k nor leak the old field into step k+1."""
+    import torch
+
+    pm, mesh, U, p = make_case(synth, orc, dims=(10, 10, 10), jitter=0.1, n=200000)
+    fields = [synth.field_uniform_vortex(pm.cell_centres, R=0.3, omega=2 * np.pi * (1 + 0.5 * k)) for k in range(5)]
+    pinned = [torch.from_numpy(np.ascontiguousarray(f)).pin_memory() for f in fields]
+    tet0 = orc.locate_brute(mesh, p)
+    cl = orc.Cloud.make(p, tet0)
+    tr = _tracker(sort_interval=0)
+    tr.upload_poly(pm)
+    tr.set_particles(p)
+    tr.locate_initial()
+    tr.update_velocity_ptr(pinned[0].data_ptr(), False)
+    for k in range(4):
+        tr.substeps(12, 2e-3)                                     # asynchronous: still running ...
+        tr.update_velocity_ptr(pinned[k + 1].data_ptr(), False)   # ... while the next field is uploaded
+        orc.substeps(mesh, cl, orc.expand_velocity(mesh, fields[k]), 12, 2e-3)
+    pp, vv, tt = tr.download()
+    _assert_same_state(pp, vv, tt, cl, "overlapped refresh")
+    tr.close()
+
+
 def test_empty_and_inactive_inputs(synth, orc):
     pm, mesh, U, p = make_case(synth, orc, dims=(4, 4, 4), jitter=0.0, n=64)
     tr = _tracker()
