@@ -18,10 +18,22 @@
 #define CPF_MIN_BLOCKS 4
 #endif
 #ifndef CPF_MAX_ROUNDS
-#define CPF_MAX_ROUNDS 2 /* exact<->fast ping-pong rounds before the exact finisher */
+#define CPF_MAX_ROUNDS 0 /* further [one exact sub-step -> resume fast] rounds before the exact finisher (measured: 0 is fastest) */
 #endif
 #ifndef CPF_FAST_MIN_BLOCKS
 #define CPF_FAST_MIN_BLOCKS 7
+#endif
+#ifndef CPF_WALL_MIN_BLOCKS
+#define CPF_WALL_MIN_BLOCKS 4 /* k_fast with in-place wall reflection (queue passes) */
+#endif
+#ifndef CPF_WALL_BATCH
+#define CPF_WALL_BATCH 32 /* lanes of a warp that must be waiting at a wall before they reflect together (32: all that are left; measured 4 < 8 < 16 < 32) */
+#endif
+#ifndef CPF_QUEUE_SORT
+#define CPF_QUEUE_SORT 0 /* order the first deferral queue by sub-step index before the wall-capable pass */
+#endif
+#ifndef CPF_WALL_PASS
+#define CPF_WALL_PASS 1 /* wall-capable fast pass over the refusals of the all-particles pass, before any exact work */
 #endif
 #define CPF_TAIL __device__ __forceinline__
 
@@ -555,11 +567,16 @@ __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const Part
 // output queue with one warp-aggregated atomic (ballot + popc); k_exact<..,1> performs that one
 // sub-step in the reference's arithmetic and this kernel, in queue mode, resumes the particle.
 //   QMODE 0: thread i = particle i from sub-step 0      QMODE 2: entries of the input queue
-template <int RNG, int QMODE>
-__global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
+// WALL = 1 (queue passes): a wall contact in the first tet of a sub-step -- the case of particles that live
+// next to a wall: diffusion at a wall, through-flow held against the reflecting outlet -- is reflected in place
+// with wall_reflect_first_tet (fp64, one face) and the walk goes on from the hit point; one such contact per
+// sub-step, anything else about a wall is still deferred.  Costs registers (6 CTAs/SM), hence not in the
+// all-particles pass, whose refusals land in the first queue pass anyway.
+template <int RNG, int QMODE, int WALL>
+__global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN_BLOCKS) k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 {
     extern __shared__ float s_xi[];
-    unsigned hops = 0, nsteps = 0;
+    unsigned hops = 0, nsteps = 0, refl = 0;
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride) { // warp-uniform trip count
@@ -589,13 +606,43 @@ __global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshVie
             }
         }
         Fast32 f;
-        D3 O{ 0.0, 0.0, 0.0 }, disp{ 0.0, 0.0, 0.0 };
+        D3 O{ 0.0, 0.0, 0.0 }, disp{ 0.0, 0.0, 0.0 }; // disp: after an in-place reflection (leg = 1) the reflected END POINT
+        D3 Phit{ 0.0, 0.0, 0.0 };
+        int leg = 0;
+        bool velDone = false;
         WalkF ws;
         int cell = -1, visits = 0; // cell: the cell whose velocity moved the particle in its latest sub-step
         bool needPro = true;
         if (active && tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
+        bool wallWait = false; // WALL: certified wall contact, waiting for the warp's next batched reflection
         while (__any_sync(0xffffffffu, active)) {
-            if (active && needPro) {
+            if (WALL) {
+                // The reflection is long and rare per lane: lanes that reach a wall wait until CPF_WALL_BATCH of them
+                // have gathered (or nobody else can move), then reflect together instead of one or two at a time.
+                const unsigned waiting = __ballot_sync(0xffffffffu, active && wallWait);
+                const unsigned running = __ballot_sync(0xffffffffu, active && !wallWait);
+                if (wallWait && (__popc(waiting) >= CPF_WALL_BATCH || running == 0u)) {
+                    wallWait = false;
+                    const double *uc = m.ucell + 3ll * cell;
+                    D3 Eref, u{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+                    if (wall_reflect_on_path(m, tet, ws.path, visits - 1, ws.cur, ws.wall_js, P, disp, Phit, Eref, u)) {
+                        disp = Eref;
+                        const int js = ws.wall_js, wallTet = ws.cur;
+                        walkf_begin(ws, O, Phit, xsub(Eref, Phit), wallTet); // leg 1: from the hit point, same tet
+                        ws.in_j = js;
+                        hops += visits;
+                        visits = 0;
+                        leg = 1;
+                        // the velocity a particle leaves the call with is the reflected one (reflectInTet's u)
+                        if (sp.writeVel && s == sp.nSub - 1) { st_stream4(pv.vel + i, make_double4(u.x, u.y, u.z, -1.0)); velDone = true; }
+                    } else {
+                        hops += visits;
+                        deferAt = s;
+                        active = false;
+                    }
+                }
+            }
+            if (active && !wallWait && needPro) {
                 if (tet < 0) { w = 0.0; active = false; } // S1: left the domain -> frozen (particles.cu:334-338)
                 else {
                     cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
@@ -610,22 +657,29 @@ __global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshVie
                     }
                     walkf_begin(ws, O, P, disp, tet);
                     visits = 0;
+                    leg = 0;
                     needPro = false;
                 }
             }
-            if (active) {
+            if (active && !wallWait) {
                 ++visits;
-                const int oc = visit_fast32(m, f, O, P, ws);
+                const int oc = visit_fast32(m, f, O, (WALL && leg) ? Phit : P, ws);
                 if (oc == CPF_V_DONE) {
                     tet = ws.cur;
-                    P = xadd(P, disp);
+                    if (WALL && leg) { P = xadd(Phit, xsub(disp, Phit)); refl++; } // p = P_hit (S4) then p += E - P_hit (S5)
+                    else P = xadd(P, disp);
                     hops += visits;
                     needPro = true;
                     if (++s >= sp.nSub) active = false;
-                } else if (oc == CPF_V_REFUSE || visits >= 48) {
-                    hops += visits;
-                    deferAt = s;
-                    active = false;
+                } else if (oc != CPF_V_HOP || visits >= 48) {
+                    if (WALL && oc == CPF_V_WALL && visits <= 15 && leg == 0 && sp.reflect && ws.Dd < 10.f &&
+                        m.patch_kind[-ws.wall_link - 1] != CPF_PATCH_ESCAPE) {
+                        wallWait = true;
+                    } else {
+                        hops += visits;
+                        deferAt = s;
+                        active = false;
+                    }
                 }
             }
         }
@@ -633,7 +687,7 @@ __global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshVie
             nsteps += (unsigned)(s - sBegin);
             st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
             st_stream_i(pv.tet + i, tet);
-            if (sp.writeVel && cell >= 0 && deferAt < 0) {
+            if (sp.writeVel && cell >= 0 && deferAt < 0 && !velDone) {
                 const double *uc = m.ucell + 3ll * cell;
                 st_stream4(pv.vel + i, make_double4(__ldg(uc), __ldg(uc + 1), __ldg(uc + 2), -1.0));
             }
@@ -645,11 +699,53 @@ __global__ void __launch_bounds__(128, CPF_FAST_MIN_BLOCKS) k_fast(const MeshVie
             int qb = 0;
             if (lane == 0) qb = (int)atomicAdd(sp.countOut, (unsigned)__popc(mask));
             qb = __shfl_sync(0xffffffffu, qb, 0);
-            if (deferAt >= 0) sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
+            if (deferAt >= 0) {
+                sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
+                if (sp.histOut) { // per-sub-step counts for k_queue_sort, one atomic per distinct sub-step in the warp
+                    const unsigned same = __match_any_sync(mask, deferAt);
+                    if (lane == __ffs(same) - 1) atomicAdd(sp.histOut + deferAt, (unsigned)__popc(same));
+                }
+            }
         }
         if (!QMODE) break;
     }
-    flush_counters(sp, 0u, 0u, hops, nsteps);
+    flush_counters(sp, refl, 0u, hops, nsteps);
+}
+
+// k_queue_sort: counting sort of a deferral queue by the sub-step index its entries resume at (hist = the counts
+// gathered while the queue was written).  The queue pass that follows runs each entry to the end of the chunk, so
+// entries with the same number of remaining sub-steps -- and, at the head of the list, the particles that sit
+// against a wall and bounce in every sub-step -- share warps instead of idling next to short-lived neighbours.
+__global__ void __launch_bounds__(256) k_queue_sort(const int2 *__restrict__ in, int2 *__restrict__ out, const unsigned *__restrict__ count,
+                                                    const unsigned *__restrict__ hist, unsigned *__restrict__ cursor, unsigned *__restrict__ countOut)
+{
+    __shared__ unsigned s_hist[16], s_base[16];
+    const unsigned total = *count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *countOut = total;
+    constexpr int PER = 8;
+    for (unsigned tile = blockIdx.x * (256u * PER); tile < total; tile += gridDim.x * (256u * PER)) { // block-uniform
+        if (threadIdx.x < 16) s_hist[threadIdx.x] = 0u;
+        __syncthreads();
+        int2 e[PER];
+        unsigned rank[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const unsigned idx = tile + k * 256u + threadIdx.x;
+            e[k] = idx < total ? in[idx] : make_int2(-1, 0);
+            rank[k] = e[k].x >= 0 ? atomicAdd(&s_hist[e[k].y & 15], 1u) : 0u;
+        }
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            unsigned start = 0;
+            for (unsigned b = 0; b < threadIdx.x; ++b) start += hist[b];
+            s_base[threadIdx.x] = start + (s_hist[threadIdx.x] ? atomicAdd(cursor + threadIdx.x, s_hist[threadIdx.x]) : 0u);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER; ++k)
+            if (e[k].x >= 0) out[s_base[e[k].y & 15] + rank[k]] = e[k];
+        __syncthreads();
+    }
 }
 
 // k_fast_inline<RNG,QMODE>: same fast walk with the exact tail inline.  QMODE 0 (thread i = particle
@@ -801,6 +897,7 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
     sp.counters = ctx->d_counters;
     sp.queueIn = sp.queueOut = nullptr;
     sp.countIn = sp.countOut = nullptr;
+    sp.histOut = nullptr;
     const int rng = ctx->cfg.rng;
     if (rng == CPF_RNG_XORWOW && !ctx->rng_ready) {
         int rc = launch_init_rng(ctx);
@@ -833,34 +930,50 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
         k_fast_inline<CPF_RNG_XORWOW, 0><<<grid, 128, 0, st>>>(m, pv, sp);
         ctx->launches++;
     } else {
-        // filtered policy: lean fast kernel -> [one exact sub-step -> resume fast]* -> exact finisher
+        // filtered policy: lean fast kernel -> wall-capable fast pass over its refusals
+        //                  -> [one exact sub-step -> resume fast (wall-capable)]* -> exact finisher
         const int rounds = std::max(0, std::min(CPF_MAX_ROUNDS, nSub - 1));
-        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * 16, st));
-        const dim3 qgrid(std::min<unsigned>(grid.x, 148u * 8u));
+        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * 64, st));
+        // queue kernels: one resident wave on the 148 SMs of a B200 (grid-stride loops inside)
+        const dim3 wgrid(std::min<unsigned>(grid.x, 148u * CPF_WALL_MIN_BLOCKS));
+        const dim3 egrid(std::min<unsigned>(grid.x, 148u * 8u));
+        const size_t xiBytes = rng == CPF_RNG_PHILOX ? sizeof(float) * 3 * 128 * (size_t)nSub : 0;
+        auto queue_params = [&](int q, bool withOut) { // queue q lives in d_queue[q & 1], its length in d_queue_count[q]
+            StepParams x = sp;
+            x.queueIn = ctx->d_queue[q & 1]; x.countIn = ctx->d_queue_count + q;
+            if (withOut) { x.queueOut = ctx->d_queue[(q + 1) & 1]; x.countOut = ctx->d_queue_count + q + 1; }
+            return x;
+        };
+        auto fast_queue_pass = [&](int q) {
+            const StepParams b = queue_params(q, true);
+            if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 2, 1><<<wgrid, 128, xiBytes, st>>>(m, pv, b);
+            else k_fast<CPF_RNG_NONE, 2, 1><<<wgrid, 128, 0, st>>>(m, pv, b);
+            ctx->launches++;
+        };
         StepParams a = sp;
         a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
-        const size_t xiBytes = rng == CPF_RNG_PHILOX ? sizeof(float) * 3 * 128 * (size_t)nSub : 0;
-        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0><<<grid, 128, xiBytes, st>>>(m, pv, a);
-        else k_fast<CPF_RNG_NONE, 0><<<grid, 128, 0, st>>>(m, pv, a);
+        if (CPF_WALL_PASS && CPF_QUEUE_SORT) a.histOut = ctx->d_queue_count + 16;
+        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0, 0><<<grid, 128, xiBytes, st>>>(m, pv, a);
+        else k_fast<CPF_RNG_NONE, 0, 0><<<grid, 128, 0, st>>>(m, pv, a);
         ctx->launches++;
-        for (int r = 0; r < rounds; ++r) {
-            StepParams e = sp, b = sp;
-            e.queueIn = ctx->d_queue[r & 1]; e.countIn = ctx->d_queue_count + r;
-            b.queueIn = e.queueIn; b.countIn = e.countIn;
-            b.queueOut = ctx->d_queue[(r + 1) & 1]; b.countOut = ctx->d_queue_count + r + 1;
-            if (rng == CPF_RNG_PHILOX) {
-                k_exact_convex<CPF_RNG_PHILOX, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
-                k_fast<CPF_RNG_PHILOX, 2><<<qgrid, 128, xiBytes, st>>>(m, pv, b);
-            } else {
-                k_exact_convex<CPF_RNG_NONE, 1><<<qgrid, 128, 0, st>>>(m, pv, e);
-                k_fast<CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, b);
-            }
-            ctx->launches += 2;
+        int q = 0;
+        if (CPF_WALL_PASS && CPF_QUEUE_SORT) { // queue 0 (d_queue[0]) -> sorted by sub-step -> queue 1 (d_queue[1])
+            k_queue_sort<<<148 * 2, 256, 0, st>>>(ctx->d_queue[0], ctx->d_queue[1], ctx->d_queue_count, ctx->d_queue_count + 16,
+                                               ctx->d_queue_count + 32, ctx->d_queue_count + 1);
+            ctx->launches++;
+            q = 1;
         }
-        StepParams z = sp;
-        z.queueIn = ctx->d_queue[rounds & 1]; z.countIn = ctx->d_queue_count + rounds;
-        if (rng == CPF_RNG_PHILOX) k_exact_convex<CPF_RNG_PHILOX, 2><<<qgrid, 128, 0, st>>>(m, pv, z);
-        else k_exact_convex<CPF_RNG_NONE, 2><<<qgrid, 128, 0, st>>>(m, pv, z);
+        if (CPF_WALL_PASS) fast_queue_pass(q++);
+        for (int r = 0; r < rounds; ++r) {
+            const StepParams e = queue_params(q, false);
+            if (rng == CPF_RNG_PHILOX) k_exact_convex<CPF_RNG_PHILOX, 1><<<egrid, 128, 0, st>>>(m, pv, e);
+            else k_exact_convex<CPF_RNG_NONE, 1><<<egrid, 128, 0, st>>>(m, pv, e);
+            ctx->launches++;
+            fast_queue_pass(q++);
+        }
+        const StepParams z = queue_params(q, false);
+        if (rng == CPF_RNG_PHILOX) k_exact_convex<CPF_RNG_PHILOX, 2><<<egrid, 128, 0, st>>>(m, pv, z);
+        else k_exact_convex<CPF_RNG_NONE, 2><<<egrid, 128, 0, st>>>(m, pv, z);
         ctx->launches++;
     }
     if (ctx->profiling) {

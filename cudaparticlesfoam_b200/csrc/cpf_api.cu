@@ -62,7 +62,7 @@ static int alloc_particles(cpf_context *ctx, long long n)
     }
     CPF_CUDA(ctx, cudaMalloc(&ctx->d_queue[0], sizeof(int2) * (size_t)n));
     CPF_CUDA(ctx, cudaMalloc(&ctx->d_queue[1], sizeof(int2) * (size_t)n));
-    CPF_CUDA(ctx, cudaMalloc(&ctx->d_queue_count, sizeof(unsigned) * 16));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_queue_count, sizeof(unsigned) * 64));
     ctx->n = n;
     k_iota_fill<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->d_pid[0], ctx->d_tet[0]);
     ctx->launches++;

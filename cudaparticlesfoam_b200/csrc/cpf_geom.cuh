@@ -252,7 +252,8 @@ CPF_DEV int sel4(int a, int b, int c, int d, int k)
 // One self-contained 64-byte record per tet: links, the un-normalised inward normals of the three
 // faces through the tet's highest-id vertex (the "origin": for OpenFOAM decompositions the cell
 // centre, so all 12 tets of a cell share it) -- computed in fp64 at build time, rounded once --,
-// the origin's vertex id, 6*volume and the largest |vertex offset| E.  A hop is ONE 64-byte load;
+// the origin's vertex id, 6*volume and the largest |vertex offset| E (its sign bit flags records whose
+// slots 1 and 2 were exchanged to make the orientation positive).  A hop is ONE 64-byte load;
 // the fp64 origin position is fetched only when the walk enters another cell.  All predicates run
 // on the fp32 pipe.  Soundness: every comparison is made against g = G*|V6| + ERR, where
 // ERR = 2^-18 * E^2 * (E + 3(R+D)), R = |r|inf, D = |d|inf, bounds the distance between a computed plane
@@ -306,8 +307,12 @@ CPF_DEV float rcp_ftz(float x)
 struct WalkF {
     float rx, ry, rz, dx, dy, dz, RD3, Dd, t_in;
     int in_j, cur;
+    int wall_js, wall_link; // set with CPF_V_WALL
+    unsigned path;          // stored exit slot of every hop of this leg, 2 bits each (wall handling)
 };
-enum { CPF_V_DONE = 0, CPF_V_HOP = 1, CPF_V_REFUSE = 2 };
+// CPF_V_WALL: every check passed and the certified exit face is a boundary face (callers without wall
+// handling treat it like a refusal: oc >= CPF_V_REFUSE)
+enum { CPF_V_DONE = 0, CPF_V_HOP = 1, CPF_V_REFUSE = 2, CPF_V_WALL = 3 };
 
 CPF_DEV void walkf_begin(WalkF &ws, const D3 &O, const D3 &P0, const D3 &disp, int tet)
 {
@@ -318,6 +323,7 @@ CPF_DEV void walkf_begin(WalkF &ws, const D3 &O, const D3 &P0, const D3 &disp, i
     ws.t_in = 0.f;
     ws.in_j = -1;
     ws.cur = tet;
+    ws.path = 0u;
 }
 
 CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, WalkF &ws)
@@ -333,7 +339,7 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
     }
     a[3] = V - a[0] - a[1] - a[2];
     b[3] = -(b[0] + b[1] + b[2]);
-    const float E = f.E;
+    const float E = fabsf(f.E);
     const float g = fmaf(m.guardf, V, 3.814697265625e-6f * (E * E) * (E + ws.RD3));
     // C1 (entry/start point vs the other faces), C2 (end point vs every face plane)
     float c1m = INF, eam = INF, emin = INF;
@@ -365,10 +371,12 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
 #pragma unroll
     for (int j = 0; j < 4; ++j) c3m = fminf(c3m, (j == js) ? INF : fmaf(t, b[j], a[j]));
     const int link = sel4(f.link.x, f.link.y, f.link.z, f.link.w, js);
-    if (!((c3m >= g) && (t > ws.t_in) && (t <= 1.f) && (link >= 0))) return CPF_V_REFUSE; // incl. walls, no candidate
+    if (!((c3m >= g) && (t > ws.t_in) && (t <= 1.f))) return CPF_V_REFUSE; // incl. "no candidate" (t = inf)
+    if (link < 0) { ws.wall_js = js; ws.wall_link = link; return CPF_V_WALL; }
     ws.cur = link >> 2;
     ws.in_j = link & 3;
     ws.t_in = t;
+    ws.path = (ws.path << 2) | (unsigned)js;
     const int oldOrigin = f.origin;
     f32_load(m, ws.cur, f);
     if (f.origin != oldOrigin) { // entered another cell: re-express the start point
@@ -377,6 +385,62 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
         ws.RD3 = 3.f * (fmaxf(fmaxf(fabsf(ws.rx), fabsf(ws.ry)), fabsf(ws.rz)) + ws.Dd);
     }
     return CPF_V_HOP;
+}
+
+// Wall contact on the first leg of a sub-step, in the reference's arithmetic but only for the faces the filter
+// has certified (C1-C3 passed at every visit; `path` holds the stored exit slot of each hop, 2 bits per hop; the
+// exit face js of the last tet is a boundary face):
+//   traceIntet (ConvexQuery.cu:32-131) accepts the exit face of every tet on the way with fd < tol, tol < dT <= 1
+//   and moves the segment start to S = fma(d, dT, S), d = E - S: replayed here face by face, so that the hit
+//   point P_hit carries exactly the reference's roundings;
+//   reflectInTet (ConvexQuery.cu:239-317) takes the first face in its order with |fd| or |dT| below tol.  C3 puts
+//   the hit point >= G*h >= 1e-11 away from every other face plane and |d| < 10 keeps their |dT| above 1e-12, so
+//   that face is the wall face, provided |fd| < tol there -- checked exactly.
+// Returns false when the reference's own tests on one of those faces do not hold (then the exact path decides).
+// On success: Phit = hit point, E = reflected end point, u = reflected velocity; the caller continues the walk
+// from Phit in the wall tet.
+CPF_DEV bool exact_crossing(const MeshView &m, int tet, int js, bool flipped, const D3 &E, D3 &S, D3 &A, D3 &n)
+{
+    const int j = (js == 1 || js == 2) ? (flipped ? 3 - js : js) : js; // stored slot -> sorted face
+    const int4 v = ld_int4(m.tetv, tet);
+    A = ld_vertex(m.vpos, j == 0 ? v.y : v.x);
+    const double *np = reinterpret_cast<const double *>(m.tetnrm) + 12ll * tet + 3 * j;
+    n = D3{ __ldg(np), __ldg(np + 1), __ldg(np + 2) };
+    const D3 d = xsub(E, S);
+    const double fd = xdot(xsub(A, S), n);
+    const double dT = __ddiv_rn(fd, xdot(d, n));
+    if (!(fd < CPF_TOL && dT > CPF_TOL && dT <= 1.0)) return false;
+    S = D3{ __fma_rn(d.x, dT, S.x), __fma_rn(d.y, dT, S.y), __fma_rn(d.z, dT, S.z) };
+    return true;
+}
+
+CPF_DEV bool wall_reflect_on_path(const MeshView &m, int startTet, unsigned path, int nHops, int wallTet, int js, const D3 &P,
+                                  const D3 &disp, D3 &Phit, D3 &E, D3 &u)
+{
+    E = xadd(P, disp);
+    D3 S = P, A, n;
+    int cur = startTet;
+    for (int h = 0; h < nHops; ++h) { // the interior crossings before the wall tet
+        const unsigned *rec = reinterpret_cast<const unsigned *>(m.tetfast + 4ll * cur);
+        const int hj = (int)((path >> (2 * (nHops - 1 - h))) & 3u); // the latest hop sits in the lowest bits
+        const bool flipped = (int)__ldg(rec + 15) < 0; // sign bit of E
+        const int link = (int)__ldg(rec + hj);
+        if (link < 0 || !exact_crossing(m, cur, hj, flipped, E, S, A, n)) return false;
+        cur = link >> 2;
+    }
+    if (cur != wallTet) return false;
+    const bool flipped = (int)__ldg(reinterpret_cast<const unsigned *>(m.tetfast + 4ll * cur) + 15) < 0;
+    if (!exact_crossing(m, cur, js, flipped, E, S, A, n)) return false;
+    Phit = S;
+    if (!(fabs(xdot(xsub(A, Phit), n)) < CPF_TOL)) return false;
+    const D3 r = xsub(E, A);
+    double sp = -__fma_rn(r.z, n.z, __fma_rn(r.y, n.y, __dmul_rn(r.x, n.x)));
+    sp = __dadd_rn(sp, sp);
+    double sv = -__fma_rn(u.z, n.z, __fma_rn(u.y, n.y, __dmul_rn(u.x, n.x)));
+    sv = __dadd_rn(sv, sv);
+    E = D3{ __fma_rn(sp, n.x, E.x), __fma_rn(sp, n.y, E.y), __fma_rn(sp, n.z, E.z) };
+    u = D3{ __fma_rn(sv, n.x, u.x), __fma_rn(sv, n.y, u.y), __fma_rn(sv, n.z, u.z) };
+    return true;
 }
 
 // Whole walk of one sub-step (k_fast_inline).  Returns the final tet (f then holds its record, O its
@@ -389,7 +453,7 @@ CPF_DEV int walk_fast32(const MeshView &m, Fast32 &f, D3 &O, int tet0, D3 P0, D3
         hops++;
         const int oc = visit_fast32(m, f, O, P0, ws);
         if (oc == CPF_V_DONE) return ws.cur;
-        if (oc == CPF_V_REFUSE) break;
+        if (oc >= CPF_V_REFUSE) break;
     }
     return CPF_NEED_EXACT;
 }

@@ -200,6 +200,7 @@ __global__ void k_build_fast(long long nTets, const int4 *__restrict__ tetv, con
         for (int c = 0; c < 3; ++c) E = fmaxf(E, fabsf((float)X[k][c]));
     }
     E = E * 1.0000002f; // never below the true maximum
+    if (flip) E = -E;   // sign bit: stored slots 1 and 2 are exchanged w.r.t. the sorted vertex order (wall handling)
     // inward normals of the faces opposite slots 0,1,2 (the origin is slot 3): N_j = X_{j+1} x X_{j+2}
     float Nf[3][3];
 #pragma unroll
