@@ -396,7 +396,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-arm", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--workload", default="channel1M_1e7", choices=sorted(WORKLOADS))
-    ap.add_argument("--sort-interval", type=int, default=20)
+    ap.add_argument("--sort-interval", type=int, default=50)
     ap.add_argument("--fuse", type=int, default=10)
     ap.add_argument("--exact", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
