@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN
                 }
             }
             if (active && !wallWait && needPro) {
-                if (tet < 0) { w = 0.0; active = false; } // S1: left the domain -> frozen (particles.cu:334-338)
+                if (tet < 0) active = false; // S1: left the domain -> frozen (particles.cu:334-338), w := 0 below
                 else {
                     cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
                     const double *uc = m.ucell + 3ll * cell;
@@ -684,6 +684,7 @@ __global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN
             }
         }
         if (live) {
+            if (tet < 0 && deferAt < 0) w = 0.0; // frozen in a prologue (tet only turns negative through the exact kernels)
             nsteps += (unsigned)(s - sBegin);
             st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
             st_stream_i(pv.tet + i, tet);
