@@ -63,6 +63,11 @@ SYMBOLS = {
     "cpf_download_cells": (C.c_int, [_vp, _ip]),
     "cpf_stats_get": (C.c_int, [_vp, C.POINTER(CpfStats)]),
     "cpf_write_vtu": (C.c_int, [_vp, C.c_char_p, C.c_uint]),
+    "cpf_write_vtu_async": (C.c_int, [_vp, C.c_char_p, C.c_uint, C.c_int]),
+    "cpf_output_wait": (C.c_int, [_vp]),
+    "cpf_checkpoint_save": (C.c_int, [_vp, C.c_char_p]),
+    "cpf_checkpoint_load": (C.c_int, [_vp, C.c_char_p]),
+    "cpf_step_index": (C.c_ulonglong, [_vp]),
     "cpf_num_particles": (_ll, [_vp]),
     "cpf_device_pointers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "cpf_debug_next_normals": (C.c_int, [_vp, _dp]),

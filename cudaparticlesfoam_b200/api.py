@@ -241,6 +241,21 @@ class ParticleTracker:
     def write_vtu(self, directory: str, step: int):
         self._chk(self.lib.cpf_write_vtu(self.h, directory.encode(), int(step)))
 
+    def write_vtu_async(self, directory: str, step: int, stride: int = 1):
+        """Binary (raw appended) particle_%04d.vtu written by the library's writer thread; returns once enqueued."""
+        self._chk(self.lib.cpf_write_vtu_async(self.h, directory.encode(), int(step), int(stride)))
+
+    def output_wait(self):
+        self._chk(self.lib.cpf_output_wait(self.h))
+
+    def checkpoint_save(self, path: str):
+        self._chk(self.lib.cpf_checkpoint_save(self.h, str(path).encode()))
+
+    def checkpoint_load(self, path: str):
+        """Needs the same mesh uploaded and the same random-walk configuration; continues bit-identically."""
+        self._chk(self.lib.cpf_checkpoint_load(self.h, str(path).encode()))
+        self.step = int(self.lib.cpf_step_index(self.h))
+
     def next_normals(self):
         xi = np.empty((self.n, 3))
         self._chk(self.lib.cpf_debug_next_normals(self.h, _dp(xi)))

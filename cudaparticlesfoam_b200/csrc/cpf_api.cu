@@ -176,6 +176,7 @@ int cpf_destroy(cpf_context *ctx)
 {
     if (!ctx) return CPF_OK;
     cudaSetDevice(ctx->device);
+    output_shutdown(ctx); // files handed to cpf_write_vtu_async are completed first
     cudaStreamSynchronize(ctx->stream);
     free_particles(ctx);
     release_mesh(ctx);
@@ -194,7 +195,7 @@ int cpf_sync(cpf_context *ctx)
 {
     if (!ctx) return CPF_ERR_INVALID;
     CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return CPF_OK;
+    return output_wait(ctx);
 }
 
 int cpf_set_config(cpf_context *ctx, const cpf_config *cfg)

@@ -43,6 +43,8 @@ struct BvhLevel { float4 *lo; float4 *hi; long long n; };
 
 } // namespace cpf
 
+namespace cpf { struct OutputState; }
+
 struct cpf_context {
     cpf_config cfg;
     int device = 0;
@@ -106,6 +108,7 @@ struct cpf_context {
 
     unsigned long long *d_counters = nullptr;
     int2 *d_queue[2] = { nullptr, nullptr }; // [n] ping-pong deferral queues of the filtered policy
+    cpf::OutputState *output = nullptr;      // asynchronous VTU writer (cpf_output.cu), created on first use
     unsigned *d_queue_count = nullptr;       // [64]: queue lengths [0..15], per-sub-step histogram [16..31], sort cursors [32..47]
 };
 
@@ -131,6 +134,9 @@ int build_device_mesh(cpf_context *ctx, long long nVerts, const double *pos, lon
 int build_bvh(cpf_context *ctx);
 void free_bvh(cpf_context *ctx);
 int locate_particles(cpf_context *ctx, bool lostOnly = false);
+// cpf_output.cu
+int output_wait(cpf_context *ctx);      // drain the asynchronous writer; reports its first I/O error
+void output_shutdown(cpf_context *ctx); // drain, join, free
 // cpf_advect.cu
 int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel);
 int launch_initial_advect(cpf_context *ctx, double dt);

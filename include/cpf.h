@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define CPF_ABI_VERSION 1
+#define CPF_ABI_VERSION 2
 
 typedef struct cpf_context cpf_context;
 
@@ -177,6 +177,26 @@ int cpf_download_cells(cpf_context *ctx, int *cell);
 int cpf_stats_get(cpf_context *ctx, cpf_stats *out);
 /* writeParticles2VTU (cuda/utils.cpp:144-283): particle_%04d.vtu in `dir` */
 int cpf_write_vtu(cpf_context *ctx, const char *dir, unsigned step);
+/* The same file name, arrays and array names, but written without stalling the advection
+ * (replaces the blocking copies + ASCII printing of cuda/utils.cpp:144-283 and
+ * the sync it forces in src/advect.H:163-175): every `stride`-th particle (original ids
+ * 0, stride, 2*stride, ...) is packed on the device, copied on the copy stream into one of two
+ * page-locked buffers and written by a writer thread as VTK XML with one raw appended-data
+ * section (little endian, UInt64 block headers).  Returns once the work is enqueued; blocks only
+ * while two earlier files are still being written. */
+int cpf_write_vtu_async(cpf_context *ctx, const char *dir, unsigned step, int stride);
+/* Blocks until every file handed to cpf_write_vtu_async is on disk and returns the writer's first
+ * I/O error, if any (cpf_sync and cpf_destroy drain the writer too). */
+int cpf_output_wait(cpf_context *ctx);
+/* Checkpoint / restart (the reference has none, src/initCuda.H:498): particle state
+ * in original order, the global sub-step index (the Philox counter), cumulative counters and, in
+ * XORWOW mode, the generator states.  cpf_checkpoint_load needs the same mesh uploaded and the
+ * same random-walk configuration; the run then continues bit-identically. */
+int cpf_checkpoint_save(cpf_context *ctx, const char *path);
+/* number of sub-steps executed since seeding (restored by cpf_checkpoint_load): the `step` counter of
+ * src/initCuda.H:498 and the Philox counter */
+unsigned long long cpf_step_index(cpf_context *ctx);
+int cpf_checkpoint_load(cpf_context *ctx, const char *path);
 long long cpf_num_particles(cpf_context *ctx);
 /* raw device pointers (for torch / NCCL plumbing); valid until the next set/seed/sort call */
 int cpf_device_pointers(cpf_context *ctx, void **pos4, void **tet, void **ucell);
