@@ -139,6 +139,34 @@ def test_filtered_path_rarely_needs_exact_arithmetic(synth, orc):
     tr.close()
 
 
+@pytest.mark.parametrize("fuse", [1, 6], ids=["unfused", "fused6"])
+def test_wall_contacts_after_several_hops_stay_in_the_fast_kernels(synth, orc, fuse):
+    """Uniform flow into a corner with steps of ~2.5 cells: particles cross many tets before they reach a wall,
+    bounce in nearly every sub-step and meet two or three walls at once near edges and the corner.  The wall-capable
+    queue pass replays the crossed faces in the reference's arithmetic (cpf_geom.cuh wall_reflect_on_path); the
+    second wall of a sub-step, and a reflection on the sub-step whose velocity is reported, go through the exact
+    kernel.  Everything must equal the oracle bit for bit -- positions, tets and the reflected velocities."""
+    pm, mesh, U, p = make_case(synth, orc, dims=(10, 9, 8), jitter=0.15, n=30000, field=(1.0, 0.8, 0.6))
+    Utet = orc.expand_velocity(mesh, U)
+    tet0 = orc.locate_brute(mesh, p)
+    cl = orc.Cloud.make(p, tet0)
+    tr = _tracker(path=0, fuse_substeps=fuse, sort_interval=7)
+    tr.upload_poly(pm)
+    tr.update_velocity(U)
+    tr.set_particles(p)
+    tr.locate_initial()
+    dt = 0.25
+    for chunk in (1, 6, 13):
+        orc.substeps(mesh, cl, Utet, chunk, dt)
+        tr.substeps(chunk, dt)
+        pp, vv, tt = tr.download()
+        _assert_same_state(pp, vv, tt, cl, f"corner flow after chunk {chunk}")
+    st = tr.stats()
+    assert st["n_reflections"] > 2 * p.shape[0], "the case must be dominated by wall contacts"
+    assert st["n_hops"] > 3 * st["n_substeps"], "and by long walks"
+    tr.close()
+
+
 def test_filtered_path_handles_degenerate_starts(synth, orc):
     """Particles sitting exactly on vertices, edges, faces and cell centres must take the exact
     path and still reproduce the oracle bit for bit."""
