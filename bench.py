@@ -160,7 +160,8 @@ def run_ours(args, w, rank, world, local_rank):
     tr.locate_initial()
     tr.sync()
     t_loc = time.time() - t0
-    tr.sort()
+    if not args.shuffled:
+        tr.sort()  # seeded positions are uniformly random, i.e. shuffled with respect to the cells
     ncell = pm.n_cells
     u_host = [torch.from_numpy(f).pin_memory() for f in fields]
     u_dev = [torch.from_numpy(f).to(dev) for f in fields]
@@ -279,7 +280,7 @@ def run_ours(args, w, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "description": w["desc"], "particles_per_gpu": w["n"], "cells": pm.n_cells,
-                   "substeps_per_step": w["ncycles"], "substeps_per_launch": sub_per_launch, "sort_interval": args.sort_interval,
+                   "substeps_per_step": w["ncycles"], "substeps_per_launch": sub_per_launch, "sort_interval": args.sort_interval, "initial_order": "shuffled" if args.shuffled else "sorted by cell",
                    "path": "exact" if args.exact else "filtered",
                    "e2e_path": ("host U -> cpf_update_velocity (copy stream, one step ahead of the sub-steps) -> cpf_advect -> cpf_stats_get" if world == 1
                                 else "rank 0 host U -> H2D -> ncclBroadcast -> cpf_update_velocity(device) -> cpf_advect -> cpf_stats_get + NCCL reduce"),
@@ -322,9 +323,30 @@ def cpu_baseline(w, pm, p, fields, tr=None, n_sample=1_000_000, n_sub=20):
     t0 = time.time()
     orc.substeps(mesh, cl, Utet, n_sub, w["dt"])
     dt = time.time() - t0
-    return {"value": n * n_sub / dt, "unit": "particle-steps/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"first {n} particles x {n_sub} sub-steps of the same mesh/field, no random walk; oracle/cpf_oracle.c with OpenMP; "
-                      f"topology build {t_build:.1f}s not timed"}
+    out = {"value": n * n_sub / dt, "unit": "particle-steps/s", "cores": os.cpu_count(), "kind": "port",
+           "sample": f"first {n} particles x {n_sub} sub-steps of the same mesh/field, no random walk; oracle/cpf_oracle.c with OpenMP; "
+                     f"topology build {t_build:.1f}s not timed"}
+    # second CPU column of SURVEY 8(d): OpenFOAM-style barycentric tracking, restated (OpenFOAM itself is not available)
+    try:
+        cf = orc.Cloud.make(ps.copy(), cl.tet.copy())
+        cf.p[:, :3] = cl.p[:, :3]
+        live = cf.tet >= 0
+        cf = orc.Cloud.make(np.ascontiguousarray(cf.p[live]), np.ascontiguousarray(cf.tet[live]))
+        orc.foamtrack_substeps(mesh, cf, Utet, 1, w["dt"])
+        t0 = time.time()
+        orc.foamtrack_substeps(mesh, cf, Utet, n_sub, w["dt"])
+        t_all = time.time() - t0
+        n1 = min(cf.n, 100_000)
+        c1 = orc.Cloud.make(np.ascontiguousarray(cf.p[:n1]), np.ascontiguousarray(cf.tet[:n1]))
+        t0 = time.time()
+        orc.foamtrack_substeps(mesh, c1, Utet, n_sub, w["dt"], threads=1)
+        t_one = time.time() - t0
+        out["foamtrack"] = {"label": "OpenFOAM-style CPU tracking (restated; OpenFOAM not available)", "unit": "particle-steps/s",
+                            "all_cores": cf.n * n_sub / t_all, "cores": os.cpu_count(), "one_core": n1 * n_sub / t_one,
+                            "sample": f"{cf.n} particles x {n_sub} sub-steps on all cores, {n1} x {n_sub} on one core; oracle/cpf_foamtrack.c"}
+    except Exception as e:  # the baseline column must never take the bench line down
+        out["foamtrack"] = {"unavailable": repr(e)}
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -397,6 +419,7 @@ def main():
     ap.add_argument("--ref-arm", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--workload", default="channel1M_1e7", choices=sorted(WORKLOADS))
     ap.add_argument("--sort-interval", type=int, default=50)
+    ap.add_argument("--shuffled", action="store_true", help="locality probe (SURVEY 8d): no initial sort by cell; combine with --sort-interval 0")
     ap.add_argument("--fuse", type=int, default=10)
     ap.add_argument("--exact", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

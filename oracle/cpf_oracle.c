@@ -685,3 +685,4 @@ void orc_bary_of(long n, const double *p, const int *tet, const double *pos, con
 int orc_abi_version(void) { return 1; }
 
 #include "cpf_oracle_ext.c"
+#include "cpf_foamtrack.c"

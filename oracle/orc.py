@@ -169,6 +169,16 @@ def substeps(mesh: TetMesh, cl: Cloud, U: np.ndarray, n_steps: int, dt: float, *
                        C.c_int(int(reflect)), xp, C.c_double(D))
 
 
+def foamtrack_substeps(mesh: TetMesh, cl: Cloud, Utet: np.ndarray, n_steps: int, dt: float, *, reflect=True, threads=0) -> int:
+    """OpenFOAM-style barycentric tracking restated (oracle/cpf_foamtrack.c): the second CPU baseline of SURVEY 8(d).
+    In place on cl.p / cl.tet; returns the number of face events."""
+    L = lib()
+    L.orc_foamtrack_substeps.restype = C.c_long
+    Utet = np.ascontiguousarray(Utet, dtype=np.float64)
+    return int(L.orc_foamtrack_substeps(C.c_long(cl.n), C.c_int(n_steps), _d(cl.p), _i(cl.tet), C.c_double(dt), *mesh.args(),
+                                        _d(Utet), C.c_int(int(reflect)), C.c_int(int(threads))))
+
+
 def advect(mesh, cl, U, dt, vertex_velocity=False):
     lib().orc_advect(C.c_long(cl.n), _d(cl.p), _i(cl.tet), _d(cl.vel), _d(cl.disp), C.c_double(dt), *mesh.args(),
                      _d(np.ascontiguousarray(U)), C.c_int(int(vertex_velocity)))
