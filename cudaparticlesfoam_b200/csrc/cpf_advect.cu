@@ -29,9 +29,6 @@
 #ifndef CPF_WALL_BATCH
 #define CPF_WALL_BATCH 32 /* lanes of a warp that must be waiting at a wall before they reflect together (32: all that are left; measured 4 < 8 < 16 < 32) */
 #endif
-#ifndef CPF_QUEUE_SORT
-#define CPF_QUEUE_SORT 0 /* order the first deferral queue by sub-step index before the wall-capable pass */
-#endif
 #ifndef CPF_WALL_PASS
 #define CPF_WALL_PASS 1 /* wall-capable fast pass over the refusals of the all-particles pass, before any exact work */
 #endif
@@ -700,53 +697,11 @@ __global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN
             int qb = 0;
             if (lane == 0) qb = (int)atomicAdd(sp.countOut, (unsigned)__popc(mask));
             qb = __shfl_sync(0xffffffffu, qb, 0);
-            if (deferAt >= 0) {
-                sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
-                if (sp.histOut) { // per-sub-step counts for k_queue_sort, one atomic per distinct sub-step in the warp
-                    const unsigned same = __match_any_sync(mask, deferAt);
-                    if (lane == __ffs(same) - 1) atomicAdd(sp.histOut + deferAt, (unsigned)__popc(same));
-                }
-            }
+            if (deferAt >= 0) sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
         }
         if (!QMODE) break;
     }
     flush_counters(sp, refl, 0u, hops, nsteps);
-}
-
-// k_queue_sort: counting sort of a deferral queue by the sub-step index its entries resume at (hist = the counts
-// gathered while the queue was written).  The queue pass that follows runs each entry to the end of the chunk, so
-// entries with the same number of remaining sub-steps -- and, at the head of the list, the particles that sit
-// against a wall and bounce in every sub-step -- share warps instead of idling next to short-lived neighbours.
-__global__ void __launch_bounds__(256) k_queue_sort(const int2 *__restrict__ in, int2 *__restrict__ out, const unsigned *__restrict__ count,
-                                                    const unsigned *__restrict__ hist, unsigned *__restrict__ cursor, unsigned *__restrict__ countOut)
-{
-    __shared__ unsigned s_hist[16], s_base[16];
-    const unsigned total = *count;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *countOut = total;
-    constexpr int PER = 8;
-    for (unsigned tile = blockIdx.x * (256u * PER); tile < total; tile += gridDim.x * (256u * PER)) { // block-uniform
-        if (threadIdx.x < 16) s_hist[threadIdx.x] = 0u;
-        __syncthreads();
-        int2 e[PER];
-        unsigned rank[PER];
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const unsigned idx = tile + k * 256u + threadIdx.x;
-            e[k] = idx < total ? in[idx] : make_int2(-1, 0);
-            rank[k] = e[k].x >= 0 ? atomicAdd(&s_hist[e[k].y & 15], 1u) : 0u;
-        }
-        __syncthreads();
-        if (threadIdx.x < 16) {
-            unsigned start = 0;
-            for (unsigned b = 0; b < threadIdx.x; ++b) start += hist[b];
-            s_base[threadIdx.x] = start + (s_hist[threadIdx.x] ? atomicAdd(cursor + threadIdx.x, s_hist[threadIdx.x]) : 0u);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < PER; ++k)
-            if (e[k].x >= 0) out[s_base[e[k].y & 15] + rank[k]] = e[k];
-        __syncthreads();
-    }
 }
 
 // k_fast_inline<RNG,QMODE>: same fast walk with the exact tail inline.  QMODE 0 (thread i = particle
@@ -898,7 +853,6 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
     sp.counters = ctx->d_counters;
     sp.queueIn = sp.queueOut = nullptr;
     sp.countIn = sp.countOut = nullptr;
-    sp.histOut = nullptr;
     const int rng = ctx->cfg.rng;
     if (rng == CPF_RNG_XORWOW && !ctx->rng_ready) {
         int rc = launch_init_rng(ctx);
@@ -953,17 +907,10 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
         };
         StepParams a = sp;
         a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
-        if (CPF_WALL_PASS && CPF_QUEUE_SORT) a.histOut = ctx->d_queue_count + 16;
         if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0, 0><<<grid, 128, xiBytes, st>>>(m, pv, a);
         else k_fast<CPF_RNG_NONE, 0, 0><<<grid, 128, 0, st>>>(m, pv, a);
         ctx->launches++;
         int q = 0;
-        if (CPF_WALL_PASS && CPF_QUEUE_SORT) { // queue 0 (d_queue[0]) -> sorted by sub-step -> queue 1 (d_queue[1])
-            k_queue_sort<<<148 * 2, 256, 0, st>>>(ctx->d_queue[0], ctx->d_queue[1], ctx->d_queue_count, ctx->d_queue_count + 16,
-                                               ctx->d_queue_count + 32, ctx->d_queue_count + 1);
-            ctx->launches++;
-            q = 1;
-        }
         if (CPF_WALL_PASS) fast_queue_pass(q++);
         for (int r = 0; r < rounds; ++r) {
             const StepParams e = queue_params(q, false);

@@ -35,7 +35,6 @@ struct StepParams {
     unsigned long long *counters;
     int2 *queueIn, *queueOut;          // deferral queues: (particle slot, sub-step to resume at)
     unsigned *countIn, *countOut;
-    unsigned *histOut;                 // optional [16]: entries appended to queueOut per sub-step index
 };
 
 // BVH over tets for initial / lost-particle location (cpf_locate.cu)
@@ -109,7 +108,7 @@ struct cpf_context {
     unsigned long long *d_counters = nullptr;
     int2 *d_queue[2] = { nullptr, nullptr }; // [n] ping-pong deferral queues of the filtered policy
     cpf::OutputState *output = nullptr;      // asynchronous VTU writer (cpf_output.cu), created on first use
-    unsigned *d_queue_count = nullptr;       // [64]: queue lengths [0..15], per-sub-step histogram [16..31], sort cursors [32..47]
+    unsigned *d_queue_count = nullptr;       // [64]: queue lengths, one per queue of a launch sequence
 };
 
 namespace cpf {
