@@ -23,6 +23,9 @@
 #ifndef CPF_FAST_MIN_BLOCKS
 #define CPF_FAST_MIN_BLOCKS 7
 #endif
+#ifndef CPF_RK_MIN_BLOCKS
+#define CPF_RK_MIN_BLOCKS 6 /* all-particles pass with RK2 stage walks; RK4 (two more velocity accumulators): one less */
+#endif
 #ifndef CPF_WALL_MIN_BLOCKS
 #define CPF_WALL_MIN_BLOCKS 4 /* k_fast with in-place wall reflection (queue passes) */
 #endif
@@ -494,13 +497,18 @@ CPF_DEV int stage_tet(const MeshView &m, D3 from, D3 to, int tet, unsigned &hops
 
 CPF_DEV D3 axpy3(double h, D3 k, D3 P) { return D3{ __fma_rn(h, k.x, P.x), __fma_rn(h, k.y, P.y), __fma_rn(h, k.z, P.z) }; }
 
-template <int RNG>
+//   QMODE 0: thread i = particle i, all nSub sub-steps      QMODE 2: entries of the deferral queue, their remaining sub-steps
+template <int RNG, int QMODE>
 __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const ParticleView pv, const StepParams sp)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     Tally ty{ 0u, 0u, 0u, 0u };
     unsigned nsteps = 0;
-    if (i < pv.n) {
+    const long long total = QMODE ? (long long)*sp.countIn : pv.n;
+    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
+        long long i = slot;
+        int s0 = 0;
+        if (QMODE) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y; }
+        if (s0 >= sp.nSub) continue;
         double4 p4 = ld_stream4(pv.pos + i);
         int tet = ld_stream_i(pv.tet + i);
         D3 P{ p4.x, p4.y, p4.z };
@@ -510,7 +518,7 @@ __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const Part
         if (w != 0.0) {
             Rng<RNG> rng;
             rng.open(pv, i, sp);
-            for (int s = 0; s < sp.nSub; ++s) {
+            for (int s = s0; s < sp.nSub; ++s) {
                 if (w == 0.0) break;
                 if (tet < 0) { w = 0.0; break; }
                 const D3 k1 = velocity_at(m, sp.interp, tet, P);
@@ -569,8 +577,13 @@ __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const Part
 // with wall_reflect_first_tet (fp64, one face) and the walk goes on from the hit point; one such contact per
 // sub-step, anything else about a wall is still deferred.  Costs registers (6 CTAs/SM), hence not in the
 // all-particles pass, whose refusals land in the first queue pass anyway.
-template <int RNG, int QMODE, int WALL>
-__global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN_BLOCKS) k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
+// INTEG = CPF_RK2 / CPF_RK4 (extensions): the stage points P + h*k are located with the same
+// guarded walk from (P, tet) -- a stage walk that ends at a certified wall face stays in that tet, like the exact
+// stage_tet -- and feed the cell velocities of the stages into v_eff; then the move walk runs as for Euler.  A
+// refused stage walk defers the whole sub-step to k_general.
+template <int RNG, int QMODE, int WALL, int INTEG>
+__global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : (INTEG == CPF_RK4 ? CPF_RK_MIN_BLOCKS - 1 : INTEG ? CPF_RK_MIN_BLOCKS : CPF_FAST_MIN_BLOCKS))
+k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 {
     extern __shared__ float s_xi[];
     unsigned hops = 0, nsteps = 0, refl = 0;
@@ -607,6 +620,9 @@ __global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN
         D3 Phit{ 0.0, 0.0, 0.0 };
         int leg = 0;
         bool velDone = false;
+        int stage = 0;                        // INTEG: 0 = move walk, 1..3 = walk to the stage point of k2..k4
+        D3 vel{ 0.0, 0.0, 0.0 }, k1s = vel, k23 = vel; // INTEG: v_eff (reported velocity), k1, k2 (+ k3)
+        bool velValid = false;
         WalkF ws;
         int cell = -1, visits = 0; // cell: the cell whose velocity moved the particle in its latest sub-step
         bool needPro = true;
@@ -622,6 +638,7 @@ __global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN
                     wallWait = false;
                     const double *uc = m.ucell + 3ll * cell;
                     D3 Eref, u{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+                    if (INTEG) u = vel;
                     if (wall_reflect_on_path(m, tet, ws.path, visits - 1, ws.cur, ws.wall_js, P, disp, Phit, Eref, u)) {
                         disp = Eref;
                         const int js = ws.wall_js, wallTet = ws.cur;
@@ -631,7 +648,8 @@ __global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN
                         visits = 0;
                         leg = 1;
                         // the velocity a particle leaves the call with is the reflected one (reflectInTet's u)
-                        if (sp.writeVel && s == sp.nSub - 1) { st_stream4(pv.vel + i, make_double4(u.x, u.y, u.z, -1.0)); velDone = true; }
+                        if (INTEG) vel = u;
+                        else if (sp.writeVel && s == sp.nSub - 1) { st_stream4(pv.vel + i, make_double4(u.x, u.y, u.z, -1.0)); velDone = true; }
                     } else {
                         hops += visits;
                         deferAt = s;
@@ -645,14 +663,21 @@ __global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN
                     cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
                     const double *uc = m.ucell + 3ll * cell;
                     const double ux = __ldg(uc), uy = __ldg(uc + 1), uz = __ldg(uc + 2);
-                    disp = D3{ __dsub_rn(__fma_rn(sp.dt, ux, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, uy, P.y), P.y),
-                               __dsub_rn(__fma_rn(sp.dt, uz, P.z), P.z) };
-                    if (RNG != CPF_RNG_NONE) {
-                        disp.x = __fma_rn((double)s_xi[(s * 3 + 0) * 128 + threadIdx.x], sp.randDisp, disp.x);
-                        disp.y = __fma_rn((double)s_xi[(s * 3 + 1) * 128 + threadIdx.x], sp.randDisp, disp.y);
-                        disp.z = __fma_rn((double)s_xi[(s * 3 + 2) * 128 + threadIdx.x], sp.randDisp, disp.z);
+                    if (INTEG) { // k1 = v(P, tet); first stage point P + dt/2 * k1 (RK2 midpoint and RK4 alike)
+                        k1s = D3{ ux, uy, uz };
+                        const D3 Pst = axpy3(__dmul_rn(0.5, sp.dt), k1s, P);
+                        walkf_begin(ws, O, P, xsub(Pst, P), tet);
+                        stage = 1;
+                    } else {
+                        disp = D3{ __dsub_rn(__fma_rn(sp.dt, ux, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, uy, P.y), P.y),
+                                   __dsub_rn(__fma_rn(sp.dt, uz, P.z), P.z) };
+                        if (RNG != CPF_RNG_NONE) {
+                            disp.x = __fma_rn((double)s_xi[(s * 3 + 0) * 128 + threadIdx.x], sp.randDisp, disp.x);
+                            disp.y = __fma_rn((double)s_xi[(s * 3 + 1) * 128 + threadIdx.x], sp.randDisp, disp.y);
+                            disp.z = __fma_rn((double)s_xi[(s * 3 + 2) * 128 + threadIdx.x], sp.randDisp, disp.z);
+                        }
+                        walkf_begin(ws, O, P, disp, tet);
                     }
-                    walkf_begin(ws, O, P, disp, tet);
                     visits = 0;
                     leg = 0;
                     needPro = false;
@@ -661,7 +686,44 @@ __global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN
             if (active && !wallWait) {
                 ++visits;
                 const int oc = visit_fast32(m, f, O, (WALL && leg) ? Phit : P, ws);
-                if (oc == CPF_V_DONE) {
+                if (INTEG && stage > 0 && (oc == CPF_V_DONE || oc == CPF_V_WALL)) {
+                    // the stage point lies in ws.cur (or beyond a certified wall face of it): take that cell's velocity
+                    hops += visits;
+                    visits = 0;
+                    const int scell = m.tetcell ? __ldg(m.tetcell + ws.cur) : f.origin - m.nPoints;
+                    const double *uc = m.ucell + 3ll * scell;
+                    const D3 kx{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+                    if (ws.cur != tet) { // every walk of a sub-step starts from (P, tet)
+                        const int stageOrigin = f.origin;
+                        f32_load(m, tet, f);
+                        if (f.origin != stageOrigin) O = ld_vertex(m.vpos, f.origin);
+                    }
+                    bool last = true;
+                    D3 Pst = P;
+                    if (INTEG == CPF_RK2) vel = kx;
+                    else if (stage == 1) { k23 = kx; Pst = axpy3(__dmul_rn(0.5, sp.dt), kx, P); last = false; }
+                    else if (stage == 2) { k23 = xadd(k23, kx); Pst = axpy3(sp.dt, kx, P); last = false; }
+                    else {
+                        vel.x = __ddiv_rn(__fma_rn(2.0, k23.x, __dadd_rn(k1s.x, kx.x)), 6.0);
+                        vel.y = __ddiv_rn(__fma_rn(2.0, k23.y, __dadd_rn(k1s.y, kx.y)), 6.0);
+                        vel.z = __ddiv_rn(__fma_rn(2.0, k23.z, __dadd_rn(k1s.z, kx.z)), 6.0);
+                    }
+                    if (last) {
+                        disp = D3{ __dsub_rn(__fma_rn(sp.dt, vel.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, vel.y, P.y), P.y),
+                                   __dsub_rn(__fma_rn(sp.dt, vel.z, P.z), P.z) };
+                        if (RNG != CPF_RNG_NONE) {
+                            disp.x = __fma_rn((double)s_xi[(s * 3 + 0) * 128 + threadIdx.x], sp.randDisp, disp.x);
+                            disp.y = __fma_rn((double)s_xi[(s * 3 + 1) * 128 + threadIdx.x], sp.randDisp, disp.y);
+                            disp.z = __fma_rn((double)s_xi[(s * 3 + 2) * 128 + threadIdx.x], sp.randDisp, disp.z);
+                        }
+                        walkf_begin(ws, O, P, disp, tet);
+                        stage = 0;
+                    } else {
+                        walkf_begin(ws, O, P, xsub(Pst, P), tet);
+                        ++stage;
+                    }
+                } else if (oc == CPF_V_DONE) {
+                    velValid = true;
                     tet = ws.cur;
                     if (WALL && leg) { P = xadd(Phit, xsub(disp, Phit)); refl++; } // p = P_hit (S4) then p += E - P_hit (S5)
                     else P = xadd(P, disp);
@@ -669,7 +731,7 @@ __global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN
                     needPro = true;
                     if (++s >= sp.nSub) active = false;
                 } else if (oc != CPF_V_HOP || visits >= 48) {
-                    if (WALL && oc == CPF_V_WALL && visits <= 15 && leg == 0 && sp.reflect && ws.Dd < 10.f &&
+                    if (WALL && oc == CPF_V_WALL && visits <= 15 && leg == 0 && (!INTEG || stage == 0) && sp.reflect && ws.Dd < 10.f &&
                         m.patch_kind[-ws.wall_link - 1] != CPF_PATCH_ESCAPE) {
                         wallWait = true;
                     } else {
@@ -685,7 +747,9 @@ __global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : CPF_FAST_MIN
             nsteps += (unsigned)(s - sBegin);
             st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
             st_stream_i(pv.tet + i, tet);
-            if (sp.writeVel && cell >= 0 && deferAt < 0 && !velDone) {
+            if (INTEG) {
+                if (sp.writeVel && velValid && deferAt < 0) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
+            } else if (sp.writeVel && cell >= 0 && deferAt < 0 && !velDone) {
                 const double *uc = m.ucell + 3ll * cell;
                 st_stream4(pv.vel + i, make_double4(__ldg(uc), __ldg(uc + 1), __ldg(uc + 2), -1.0));
             }
@@ -837,6 +901,57 @@ template <int RNG> __global__ void k_debug_normals(const ParticleView pv, const 
     default: { constexpr int R = CPF_RNG_NONE; CALL; } break;                   \
     }
 
+// Filtered policy (stateless RNG, ConvexPoly locator, cell-constant velocity), integrator I:
+//   lean fast kernel over all particles -> wall-capable fast pass over its refusals
+//   -> [one exact sub-step -> resume fast (wall-capable)]* (Euler only, CPF_MAX_ROUNDS) -> exact finisher.
+template <int I>
+static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleView &pv, const StepParams &sp, dim3 grid, int nSub, int rng)
+{
+    cudaStream_t st = ctx->stream;
+    const int rounds = I == CPF_EULER ? std::max(0, std::min(CPF_MAX_ROUNDS, nSub - 1)) : 0;
+    CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * 64, st));
+    // queue kernels: one resident wave on the 148 SMs of a B200 (grid-stride loops inside)
+    const dim3 wgrid(std::min<unsigned>(grid.x, 148u * CPF_WALL_MIN_BLOCKS));
+    const dim3 egrid(std::min<unsigned>(grid.x, 148u * 8u));
+    const size_t xiBytes = rng == CPF_RNG_PHILOX ? sizeof(float) * 3 * 128 * (size_t)nSub : 0;
+    auto queue_params = [&](int q, bool withOut) { // queue q lives in d_queue[q & 1], its length in d_queue_count[q]
+        StepParams x = sp;
+        x.queueIn = ctx->d_queue[q & 1]; x.countIn = ctx->d_queue_count + q;
+        if (withOut) { x.queueOut = ctx->d_queue[(q + 1) & 1]; x.countOut = ctx->d_queue_count + q + 1; }
+        return x;
+    };
+    auto fast_queue_pass = [&](int q) {
+        const StepParams b = queue_params(q, true);
+        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 2, 1, I><<<wgrid, 128, xiBytes, st>>>(m, pv, b);
+        else k_fast<CPF_RNG_NONE, 2, 1, I><<<wgrid, 128, 0, st>>>(m, pv, b);
+        ctx->launches++;
+    };
+    StepParams a = sp;
+    a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
+    if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0, 0, I><<<grid, 128, xiBytes, st>>>(m, pv, a);
+    else k_fast<CPF_RNG_NONE, 0, 0, I><<<grid, 128, 0, st>>>(m, pv, a);
+    ctx->launches++;
+    int q = 0;
+    if (CPF_WALL_PASS) fast_queue_pass(q++);
+    for (int r = 0; r < rounds; ++r) {
+        const StepParams e = queue_params(q, false);
+        if (rng == CPF_RNG_PHILOX) k_exact_convex<CPF_RNG_PHILOX, 1><<<egrid, 128, 0, st>>>(m, pv, e);
+        else k_exact_convex<CPF_RNG_NONE, 1><<<egrid, 128, 0, st>>>(m, pv, e);
+        ctx->launches++;
+        fast_queue_pass(q++);
+    }
+    const StepParams z = queue_params(q, false);
+    if (I == CPF_EULER) {
+        if (rng == CPF_RNG_PHILOX) k_exact_convex<CPF_RNG_PHILOX, 2><<<egrid, 128, 0, st>>>(m, pv, z);
+        else k_exact_convex<CPF_RNG_NONE, 2><<<egrid, 128, 0, st>>>(m, pv, z);
+    } else { // RK2 / RK4: the remaining sub-steps of what is still queued, stage walks in the reference's arithmetic
+        if (rng == CPF_RNG_PHILOX) k_general<CPF_RNG_PHILOX, 2><<<egrid, 128, 0, st>>>(m, pv, z);
+        else k_general<CPF_RNG_NONE, 2><<<egrid, 128, 0, st>>>(m, pv, z);
+    }
+    ctx->launches++;
+    return CPF_OK;
+}
+
 int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
 {
     if (ctx->n == 0 || nSub <= 0) return CPF_OK;
@@ -872,8 +987,10 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
     }
     sp.integrator = ctx->cfg.integrator;
     sp.interp = ctx->cfg.interp;
-    if (ctx->cfg.integrator != CPF_EULER || ctx->cfg.interp != CPF_INTERP_TET) {
-        CPF_RNG_SWITCH(rng, (k_general<R><<<grid, 128, 0, st>>>(m, pv, sp)));
+    const bool filteredOk = ctx->cfg.interp == CPF_INTERP_TET && ctx->cfg.locator == CPF_LOCATOR_CONVEX &&
+                            ctx->cfg.path == CPF_PATH_FILTERED && rng != CPF_RNG_XORWOW;
+    if (ctx->cfg.interp != CPF_INTERP_TET || (ctx->cfg.integrator != CPF_EULER && !filteredOk)) {
+        CPF_RNG_SWITCH(rng, (k_general<R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
         ctx->launches++;
     } else if (ctx->cfg.locator == CPF_LOCATOR_BARY) {
         CPF_RNG_SWITCH(rng, (k_exact<CPF_LOCATOR_BARY, R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
@@ -885,44 +1002,11 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
         k_fast_inline<CPF_RNG_XORWOW, 0><<<grid, 128, 0, st>>>(m, pv, sp);
         ctx->launches++;
     } else {
-        // filtered policy: lean fast kernel -> wall-capable fast pass over its refusals
-        //                  -> [one exact sub-step -> resume fast (wall-capable)]* -> exact finisher
-        const int rounds = std::max(0, std::min(CPF_MAX_ROUNDS, nSub - 1));
-        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * 64, st));
-        // queue kernels: one resident wave on the 148 SMs of a B200 (grid-stride loops inside)
-        const dim3 wgrid(std::min<unsigned>(grid.x, 148u * CPF_WALL_MIN_BLOCKS));
-        const dim3 egrid(std::min<unsigned>(grid.x, 148u * 8u));
-        const size_t xiBytes = rng == CPF_RNG_PHILOX ? sizeof(float) * 3 * 128 * (size_t)nSub : 0;
-        auto queue_params = [&](int q, bool withOut) { // queue q lives in d_queue[q & 1], its length in d_queue_count[q]
-            StepParams x = sp;
-            x.queueIn = ctx->d_queue[q & 1]; x.countIn = ctx->d_queue_count + q;
-            if (withOut) { x.queueOut = ctx->d_queue[(q + 1) & 1]; x.countOut = ctx->d_queue_count + q + 1; }
-            return x;
-        };
-        auto fast_queue_pass = [&](int q) {
-            const StepParams b = queue_params(q, true);
-            if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 2, 1><<<wgrid, 128, xiBytes, st>>>(m, pv, b);
-            else k_fast<CPF_RNG_NONE, 2, 1><<<wgrid, 128, 0, st>>>(m, pv, b);
-            ctx->launches++;
-        };
-        StepParams a = sp;
-        a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
-        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0, 0><<<grid, 128, xiBytes, st>>>(m, pv, a);
-        else k_fast<CPF_RNG_NONE, 0, 0><<<grid, 128, 0, st>>>(m, pv, a);
-        ctx->launches++;
-        int q = 0;
-        if (CPF_WALL_PASS) fast_queue_pass(q++);
-        for (int r = 0; r < rounds; ++r) {
-            const StepParams e = queue_params(q, false);
-            if (rng == CPF_RNG_PHILOX) k_exact_convex<CPF_RNG_PHILOX, 1><<<egrid, 128, 0, st>>>(m, pv, e);
-            else k_exact_convex<CPF_RNG_NONE, 1><<<egrid, 128, 0, st>>>(m, pv, e);
-            ctx->launches++;
-            fast_queue_pass(q++);
-        }
-        const StepParams z = queue_params(q, false);
-        if (rng == CPF_RNG_PHILOX) k_exact_convex<CPF_RNG_PHILOX, 2><<<egrid, 128, 0, st>>>(m, pv, z);
-        else k_exact_convex<CPF_RNG_NONE, 2><<<egrid, 128, 0, st>>>(m, pv, z);
-        ctx->launches++;
+        int rc;
+        if (ctx->cfg.integrator == CPF_RK2) rc = launch_filtered<CPF_RK2>(ctx, m, pv, sp, grid, nSub, rng);
+        else if (ctx->cfg.integrator == CPF_RK4) rc = launch_filtered<CPF_RK4>(ctx, m, pv, sp, grid, nSub, rng);
+        else rc = launch_filtered<CPF_EULER>(ctx, m, pv, sp, grid, nSub, rng);
+        if (rc) return rc;
     }
     if (ctx->profiling) {
         CPF_CUDA(ctx, cudaEventRecord(ctx->profEvents[ctx->profUsed + 1], st));
