@@ -560,23 +560,23 @@ __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const Part
     flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc);
 }
 
-// k_fast<RNG,QMODE>: the main kernel of the filtered policy (default ConvexPoly build).
-// fp32 guarded walk only -- no exact-arithmetic code, hence 72 registers and 7 CTAs per SM.
-// ONE merged loop runs the tet visits of all fused sub-steps of a lane (visit_fast32): lanes need
-// different numbers of visits per sub-step, and a merged loop keeps them busy until their whole
-// chunk is done instead of idling at every sub-step boundary.  The random-walk deviates of the chunk
-// are drawn up front, with all lanes converged, into shared memory ([sub-step][component][thread],
-// conflict-free), so the per-sub-step prologue inside the divergent loop is only the velocity fetch
-// and three fp64 FMAs.  The first sub-step whose walk is refused is NOT executed: the particle is
-// written back as it was at the start of that sub-step and (particle, sub-step) is appended to the
-// output queue with one warp-aggregated atomic (ballot + popc); k_exact<..,1> performs that one
-// sub-step in the reference's arithmetic and this kernel, in queue mode, resumes the particle.
+// k_fast<RNG,QMODE,WALL,INTEG>: the kernels of the filtered policy (default ConvexPoly build).
+// fp32 guarded walk -- in the all-particles pass (WALL = 0) no exact-arithmetic code at all, hence 72
+// registers and 7 CTAs per SM.  ONE merged loop runs the tet visits of all fused sub-steps of a lane
+// (visit_fast32): lanes need different numbers of visits per sub-step, and a merged loop keeps them busy
+// until their whole chunk is done instead of idling at every sub-step boundary.  The random-walk deviates
+// of the chunk are drawn up front, with all lanes converged, into shared memory ([sub-step][component]
+// [thread], conflict-free), so the per-sub-step prologue inside the divergent loop is only the velocity
+// fetch and three fp64 FMAs.  The first sub-step whose walk is refused is NOT executed: the particle is
+// written back as it was at the start of that sub-step and (particle, sub-step) is appended to the output
+// queue with one warp-aggregated atomic (ballot + popc); the next kernel of the launch sequence
+// (launch_filtered) takes it from there.
 //   QMODE 0: thread i = particle i from sub-step 0      QMODE 2: entries of the input queue
-// WALL = 1 (queue passes): a wall contact in the first tet of a sub-step -- the case of particles that live
-// next to a wall: diffusion at a wall, through-flow held against the reflecting outlet -- is reflected in place
-// with wall_reflect_first_tet (fp64, one face) and the walk goes on from the hit point; one such contact per
-// sub-step, anything else about a wall is still deferred.  Costs registers (6 CTAs/SM), hence not in the
-// all-particles pass, whose refusals land in the first queue pass anyway.
+// WALL = 1 (queue passes): a wall contact on the first leg of a sub-step -- the case of particles that live
+// next to a wall: diffusion at a wall, through-flow held against the reflecting outlet -- is reflected in
+// place with wall_reflect_on_path (fp64 replay of the certified crossings only) and the walk goes on from the
+// hit point; one such contact per sub-step, anything else about a wall is still deferred.  Costs registers
+// (4 CTAs/SM), hence not in the all-particles pass, whose refusals land in the first queue pass anyway.
 // INTEG = CPF_RK2 / CPF_RK4 (extensions): the stage points P + h*k are located with the same
 // guarded walk from (P, tet) -- a stage walk that ends at a certified wall face stays in that tet, like the exact
 // stage_tet -- and feed the cell velocities of the stages into v_eff; then the move walk runs as for Euler.  A
