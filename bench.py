@@ -147,7 +147,7 @@ def run_ours(args, w, rank, world, local_rank):
     integ = {"euler": api.EULER, "rk2": api.RK2, "rk4": api.RK4}[args.integrator]
     tr = api.ParticleTracker(device=local_rank, rng=api.RNG_PHILOX if w["D"] > 0 else api.RNG_NONE, diffusion_coeff=w["D"], dt=w["dt"],
                              sort_interval=args.sort_interval, fuse_substeps=args.fuse, path=api.PATH_EXACT if args.exact else api.PATH_FILTERED,
-                             integrator=integ)
+                             integrator=integ, interp=api.INTERP_VERTEX if args.interp == "vertex" else api.INTERP_TET)
     # one explicit non-default stream shared by torch (copies, NCCL, timing events) and the library
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -303,7 +303,7 @@ def run_ours(args, w, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "description": w["desc"], "particles_per_gpu": w["n"], "cells": pm.n_cells,
-                   "substeps_per_step": w["ncycles"], "substeps_per_launch": sub_per_launch, "integrator": args.integrator, "sort_interval": args.sort_interval, "initial_order": "shuffled" if args.shuffled else "sorted by cell",
+                   "substeps_per_step": w["ncycles"], "substeps_per_launch": sub_per_launch, "integrator": args.integrator, "interpolation": args.interp, "sort_interval": args.sort_interval, "initial_order": "shuffled" if args.shuffled else "sorted by cell",
                    "path": "exact" if args.exact else "filtered",
                    "e2e_path": ("host U -> cpf_update_velocity (copy stream, one step ahead of the sub-steps) -> cpf_advect -> cpf_stats_get" if world == 1
                                 else "rank 0 host U -> H2D -> ncclBroadcast on a side stream, one step ahead of the sub-steps -> cpf_update_velocity(device) -> cpf_advect -> cpf_stats_get + NCCL reduce"),
@@ -443,6 +443,7 @@ def main():
     ap.add_argument("--workload", default="channel1M_1e7", choices=sorted(WORKLOADS))
     ap.add_argument("--sort-interval", type=int, default=50)
     ap.add_argument("--integrator", choices=["euler", "rk2", "rk4"], default="euler", help="BASELINE configs[1] is RK2, configs[3] RK4 (extensions; reference is Euler)")
+    ap.add_argument("--interp", choices=["cell", "vertex"], default="cell", help="vertex = cellPoint-style interpolation (extension; reference default is the cell value)")
     ap.add_argument("--shuffled", action="store_true", help="locality probe (SURVEY 8d): no initial sort by cell; combine with --sort-interval 0")
     ap.add_argument("--fuse", type=int, default=10)
     ap.add_argument("--exact", action="store_true")

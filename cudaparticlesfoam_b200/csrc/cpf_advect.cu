@@ -581,10 +581,13 @@ __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const Part
 // guarded walk from (P, tet) -- a stage walk that ends at a certified wall face stays in that tet, like the exact
 // stage_tet -- and feed the cell velocities of the stages into v_eff; then the move walk runs as for Euler.  A
 // refused stage walk defers the whole sub-step to k_general.
-template <int RNG, int QMODE, int WALL, int INTEG>
-__global__ void __launch_bounds__(128, WALL ? CPF_WALL_MIN_BLOCKS : (INTEG == CPF_RK4 ? CPF_RK_MIN_BLOCKS - 1 : INTEG ? CPF_RK_MIN_BLOCKS : CPF_FAST_MIN_BLOCKS))
+// VERT = 1 (extension): velocities from the vertex (cellPoint-style) interpolation, evaluated in the reference's
+// arithmetic (vertex_velocity_exact) at the particle and at the stage points; only the walks are filtered.
+template <int RNG, int QMODE, int WALL, int INTEG, int VERT>
+__global__ void __launch_bounds__(128, (WALL || VERT) ? CPF_WALL_MIN_BLOCKS : (INTEG == CPF_RK4 ? CPF_RK_MIN_BLOCKS - 1 : INTEG ? CPF_RK_MIN_BLOCKS : CPF_FAST_MIN_BLOCKS))
 k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 {
+    constexpr bool KEEPV = INTEG || VERT; // the reported velocity is not simply U[cell]: carry it
     extern __shared__ float s_xi[];
     unsigned hops = 0, nsteps = 0, refl = 0;
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
@@ -621,7 +624,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
         int leg = 0;
         bool velDone = false;
         int stage = 0;                        // INTEG: 0 = move walk, 1..3 = walk to the stage point of k2..k4
-        D3 vel{ 0.0, 0.0, 0.0 }, k1s = vel, k23 = vel; // INTEG: v_eff (reported velocity), k1, k2 (+ k3)
+        D3 vel{ 0.0, 0.0, 0.0 }, k1s = vel, k23 = vel, Pst = vel; // KEEPV: v_eff (reported velocity); INTEG: k1, k2 (+ k3), stage point
         bool velValid = false;
         WalkF ws;
         int cell = -1, visits = 0; // cell: the cell whose velocity moved the particle in its latest sub-step
@@ -638,7 +641,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                     wallWait = false;
                     const double *uc = m.ucell + 3ll * cell;
                     D3 Eref, u{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
-                    if (INTEG) u = vel;
+                    if (KEEPV) u = vel;
                     if (wall_reflect_on_path(m, tet, ws.path, visits - 1, ws.cur, ws.wall_js, P, disp, Phit, Eref, u)) {
                         disp = Eref;
                         const int js = ws.wall_js, wallTet = ws.cur;
@@ -648,7 +651,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                         visits = 0;
                         leg = 1;
                         // the velocity a particle leaves the call with is the reflected one (reflectInTet's u)
-                        if (INTEG) vel = u;
+                        if (KEEPV) vel = u;
                         else if (sp.writeVel && s == sp.nSub - 1) { st_stream4(pv.vel + i, make_double4(u.x, u.y, u.z, -1.0)); velDone = true; }
                     } else {
                         hops += visits;
@@ -662,15 +665,18 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                 else {
                     cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
                     const double *uc = m.ucell + 3ll * cell;
-                    const double ux = __ldg(uc), uy = __ldg(uc + 1), uz = __ldg(uc + 2);
+                    D3 u0;
+                    if (VERT) u0 = vertex_velocity_exact(m, tet, P);
+                    else u0 = D3{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
                     if (INTEG) { // k1 = v(P, tet); first stage point P + dt/2 * k1 (RK2 midpoint and RK4 alike)
-                        k1s = D3{ ux, uy, uz };
-                        const D3 Pst = axpy3(__dmul_rn(0.5, sp.dt), k1s, P);
+                        k1s = u0;
+                        Pst = axpy3(__dmul_rn(0.5, sp.dt), k1s, P);
                         walkf_begin(ws, O, P, xsub(Pst, P), tet);
                         stage = 1;
                     } else {
-                        disp = D3{ __dsub_rn(__fma_rn(sp.dt, ux, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, uy, P.y), P.y),
-                                   __dsub_rn(__fma_rn(sp.dt, uz, P.z), P.z) };
+                        if (VERT) vel = u0;
+                        disp = D3{ __dsub_rn(__fma_rn(sp.dt, u0.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, u0.y, P.y), P.y),
+                                   __dsub_rn(__fma_rn(sp.dt, u0.z, P.z), P.z) };
                         if (RNG != CPF_RNG_NONE) {
                             disp.x = __fma_rn((double)s_xi[(s * 3 + 0) * 128 + threadIdx.x], sp.randDisp, disp.x);
                             disp.y = __fma_rn((double)s_xi[(s * 3 + 1) * 128 + threadIdx.x], sp.randDisp, disp.y);
@@ -690,16 +696,19 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                     // the stage point lies in ws.cur (or beyond a certified wall face of it): take that cell's velocity
                     hops += visits;
                     visits = 0;
-                    const int scell = m.tetcell ? __ldg(m.tetcell + ws.cur) : f.origin - m.nPoints;
-                    const double *uc = m.ucell + 3ll * scell;
-                    const D3 kx{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+                    D3 kx;
+                    if (VERT) kx = vertex_velocity_exact(m, ws.cur, Pst);
+                    else {
+                        const int scell = m.tetcell ? __ldg(m.tetcell + ws.cur) : f.origin - m.nPoints;
+                        const double *uc = m.ucell + 3ll * scell;
+                        kx = D3{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+                    }
                     if (ws.cur != tet) { // every walk of a sub-step starts from (P, tet)
                         const int stageOrigin = f.origin;
                         f32_load(m, tet, f);
                         if (f.origin != stageOrigin) O = ld_vertex(m.vpos, f.origin);
                     }
                     bool last = true;
-                    D3 Pst = P;
                     if (INTEG == CPF_RK2) vel = kx;
                     else if (stage == 1) { k23 = kx; Pst = axpy3(__dmul_rn(0.5, sp.dt), kx, P); last = false; }
                     else if (stage == 2) { k23 = xadd(k23, kx); Pst = axpy3(sp.dt, kx, P); last = false; }
@@ -747,7 +756,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
             nsteps += (unsigned)(s - sBegin);
             st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
             st_stream_i(pv.tet + i, tet);
-            if (INTEG) {
+            if (KEEPV) {
                 if (sp.writeVel && velValid && deferAt < 0) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
             } else if (sp.writeVel && cell >= 0 && deferAt < 0 && !velDone) {
                 const double *uc = m.ucell + 3ll * cell;
@@ -904,11 +913,11 @@ template <int RNG> __global__ void k_debug_normals(const ParticleView pv, const 
 // Filtered policy (stateless RNG, ConvexPoly locator, cell-constant velocity), integrator I:
 //   lean fast kernel over all particles -> wall-capable fast pass over its refusals
 //   -> [one exact sub-step -> resume fast (wall-capable)]* (Euler only, CPF_MAX_ROUNDS) -> exact finisher.
-template <int I>
+template <int I, int V>
 static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleView &pv, const StepParams &sp, dim3 grid, int nSub, int rng)
 {
     cudaStream_t st = ctx->stream;
-    const int rounds = I == CPF_EULER ? std::max(0, std::min(CPF_MAX_ROUNDS, nSub - 1)) : 0;
+    const int rounds = (I == CPF_EULER && !V) ? std::max(0, std::min(CPF_MAX_ROUNDS, nSub - 1)) : 0;
     CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * 64, st));
     // queue kernels: one resident wave on the 148 SMs of a B200 (grid-stride loops inside)
     const dim3 wgrid(std::min<unsigned>(grid.x, 148u * CPF_WALL_MIN_BLOCKS));
@@ -922,14 +931,14 @@ static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleVi
     };
     auto fast_queue_pass = [&](int q) {
         const StepParams b = queue_params(q, true);
-        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 2, 1, I><<<wgrid, 128, xiBytes, st>>>(m, pv, b);
-        else k_fast<CPF_RNG_NONE, 2, 1, I><<<wgrid, 128, 0, st>>>(m, pv, b);
+        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 2, 1, I, V><<<wgrid, 128, xiBytes, st>>>(m, pv, b);
+        else k_fast<CPF_RNG_NONE, 2, 1, I, V><<<wgrid, 128, 0, st>>>(m, pv, b);
         ctx->launches++;
     };
     StepParams a = sp;
     a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
-    if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0, 0, I><<<grid, 128, xiBytes, st>>>(m, pv, a);
-    else k_fast<CPF_RNG_NONE, 0, 0, I><<<grid, 128, 0, st>>>(m, pv, a);
+    if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0, 0, I, V><<<grid, 128, xiBytes, st>>>(m, pv, a);
+    else k_fast<CPF_RNG_NONE, 0, 0, I, V><<<grid, 128, 0, st>>>(m, pv, a);
     ctx->launches++;
     int q = 0;
     if (CPF_WALL_PASS) fast_queue_pass(q++);
@@ -941,10 +950,10 @@ static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleVi
         fast_queue_pass(q++);
     }
     const StepParams z = queue_params(q, false);
-    if (I == CPF_EULER) {
+    if (I == CPF_EULER && !V) {
         if (rng == CPF_RNG_PHILOX) k_exact_convex<CPF_RNG_PHILOX, 2><<<egrid, 128, 0, st>>>(m, pv, z);
         else k_exact_convex<CPF_RNG_NONE, 2><<<egrid, 128, 0, st>>>(m, pv, z);
-    } else { // RK2 / RK4: the remaining sub-steps of what is still queued, stage walks in the reference's arithmetic
+    } else { // RK2 / RK4 / vertex interpolation: the remaining sub-steps of what is still queued, all in the reference's arithmetic
         if (rng == CPF_RNG_PHILOX) k_general<CPF_RNG_PHILOX, 2><<<egrid, 128, 0, st>>>(m, pv, z);
         else k_general<CPF_RNG_NONE, 2><<<egrid, 128, 0, st>>>(m, pv, z);
     }
@@ -987,9 +996,8 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
     }
     sp.integrator = ctx->cfg.integrator;
     sp.interp = ctx->cfg.interp;
-    const bool filteredOk = ctx->cfg.interp == CPF_INTERP_TET && ctx->cfg.locator == CPF_LOCATOR_CONVEX &&
-                            ctx->cfg.path == CPF_PATH_FILTERED && rng != CPF_RNG_XORWOW;
-    if (ctx->cfg.interp != CPF_INTERP_TET || (ctx->cfg.integrator != CPF_EULER && !filteredOk)) {
+    const bool filteredOk = ctx->cfg.locator == CPF_LOCATOR_CONVEX && ctx->cfg.path == CPF_PATH_FILTERED && rng != CPF_RNG_XORWOW;
+    if ((ctx->cfg.interp != CPF_INTERP_TET || ctx->cfg.integrator != CPF_EULER) && !filteredOk) {
         CPF_RNG_SWITCH(rng, (k_general<R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
         ctx->launches++;
     } else if (ctx->cfg.locator == CPF_LOCATOR_BARY) {
@@ -1003,9 +1011,10 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
         ctx->launches++;
     } else {
         int rc;
-        if (ctx->cfg.integrator == CPF_RK2) rc = launch_filtered<CPF_RK2>(ctx, m, pv, sp, grid, nSub, rng);
-        else if (ctx->cfg.integrator == CPF_RK4) rc = launch_filtered<CPF_RK4>(ctx, m, pv, sp, grid, nSub, rng);
-        else rc = launch_filtered<CPF_EULER>(ctx, m, pv, sp, grid, nSub, rng);
+        const bool vert = ctx->cfg.interp == CPF_INTERP_VERTEX;
+        if (ctx->cfg.integrator == CPF_RK2) rc = vert ? launch_filtered<CPF_RK2, 1>(ctx, m, pv, sp, grid, nSub, rng) : launch_filtered<CPF_RK2, 0>(ctx, m, pv, sp, grid, nSub, rng);
+        else if (ctx->cfg.integrator == CPF_RK4) rc = vert ? launch_filtered<CPF_RK4, 1>(ctx, m, pv, sp, grid, nSub, rng) : launch_filtered<CPF_RK4, 0>(ctx, m, pv, sp, grid, nSub, rng);
+        else rc = vert ? launch_filtered<CPF_EULER, 1>(ctx, m, pv, sp, grid, nSub, rng) : launch_filtered<CPF_EULER, 0>(ctx, m, pv, sp, grid, nSub, rng);
         if (rc) return rc;
     }
     if (ctx->profiling) {
