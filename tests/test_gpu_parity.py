@@ -302,6 +302,35 @@ def test_field_upload_one_step_ahead_of_running_substeps(synth, orc):
     tr.close()
 
 
+@pytest.mark.parametrize("mode", ["filtered", "exact", "bary"])
+def test_reflect_wall_off_freezes_particles_like_the_reference(synth, orc, mode):
+    """reflectWall = false (src/initCuda.H:67): a particle whose walk meets a wall keeps the id -(tet+1), is still moved
+    by S5 and is frozen by S1 of the next sub-step (particles.cu:334-338).  No reflection code runs in any kernel."""
+    from cudaparticlesfoam_b200 import api
+
+    pm, mesh, U, p = make_case(synth, orc, dims=(8, 8, 6), jitter=0.15, n=20000, field=(0.9, 0.5, -0.4))
+    Utet = orc.expand_velocity(mesh, U)
+    tet0 = orc.locate_brute(mesh, p)
+    cl = orc.Cloud.make(p, tet0)
+    convex = mode != "bary"
+    tr = _tracker(reflect_wall=0, path=api.PATH_EXACT if mode == "exact" else api.PATH_FILTERED,
+                  locator=api.LOCATOR_CONVEX if convex else api.LOCATOR_BARY, fuse_substeps=5, sort_interval=6)
+    tr.upload_poly(pm)
+    tr.update_velocity(U)
+    tr.set_particles(p)
+    tr.set_tets(tet0)
+    for chunk in (1, 5, 14):
+        orc.substeps(mesh, cl, Utet, chunk, 0.05, convex=convex, reflect=False)
+        tr.substeps(chunk, 0.05)
+        pp, vv, tt = tr.download()
+        _assert_same_state(pp, vv, tt, cl, f"reflectWall off, {mode}, chunk {chunk}")
+    st = tr.stats()
+    assert st["n_reflections"] == 0
+    assert 0 < st["n_active"] < p.shape[0], "some, not all, particles must have left through a wall"
+    assert st["n_active"] == int((cl.p[:, 3] != 0).sum())
+    tr.close()
+
+
 def test_empty_and_inactive_inputs(synth, orc):
     pm, mesh, U, p = make_case(synth, orc, dims=(4, 4, 4), jitter=0.0, n=64)
     tr = _tracker()
