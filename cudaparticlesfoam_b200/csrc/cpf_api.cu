@@ -396,13 +396,14 @@ int cpf_update_velocity(cpf_context *ctx, const double *U, int on_device)
     const size_t bytes = sizeof(double) * 3 * (size_t)ctx->nCells;
     // double-buffered: sub-steps already enqueued keep reading the previous field
     const int nb = 1 - ctx->ucur;
+    // every refresh marks the end of the kernels that read the buffer in use (they were all enqueued before this call)
+    CPF_CUDA(ctx, cudaEventRecord(ctx->evRead[ctx->ucur], ctx->stream));
     if (on_device) {
         CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ucell[nb], U, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
         // Host field: the upload runs on the copy stream, concurrently with the sub-steps already enqueued on the
         // compute stream (they read the other buffer).  The buffer being overwritten was last read by the kernels
         // enqueued before the PREVIOUS refresh (evRead[nb]); kernels enqueued from now on wait for the copy.
-        CPF_CUDA(ctx, cudaEventRecord(ctx->evRead[ctx->ucur], ctx->stream));
         CPF_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evRead[nb], 0));
         CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_ucell[nb], U, bytes, cudaMemcpyHostToDevice, ctx->copyStream));
         CPF_CUDA(ctx, cudaEventRecord(ctx->evCopy, ctx->copyStream));
