@@ -1,0 +1,159 @@
+/* cpf_filter_model.c -- TEST INFRASTRUCTURE ONLY (included by cpf_oracle.c).
+ *
+ * A CPU model of the product's fp32 guarded walk (cudaparticlesfoam_b200/csrc/cpf_geom.cuh: f32_load,
+ * walkf_begin, visit_fast32; record construction: cpf_mesh.cu k_build_fast), written against the oracle's
+ * mesh tables, so that the SOUNDNESS claim of DESIGN.md section 4.1 can be tested on the CPU over millions of
+ * random and adversarial segments: whenever the filter certifies a walk (no refusal), the tet it ends in must be
+ * the tet the reference's fp64 segment walk (s3_locate_convex) ends in.  The model rounds like the product where
+ * the source spells it (fmaf, one rounding per stored quantity); where nvcc is free to contract a*b+c the model
+ * does not -- the error term of the filter covers either choice, which is exactly what the test is about. */
+
+typedef struct {
+    int link[4];     /* (nbr << 2) | stored slot in nbr, or negative: boundary */
+    float N[3][3];   /* inward normals of the faces opposite stored slots 0..2 (slot 3 = origin = highest id) */
+    int origin;
+    float V6, E;     /* E < 0: stored slots 1/2 exchanged w.r.t. the sorted vertex order */
+} fm_rec;
+
+static void fm_sorted(const orc_mesh *m, int t, int s[4], int perm[4])
+{
+    for (int k = 0; k < 4; ++k) { s[k] = m->idx[4 * t + k]; perm[k] = k; }
+    for (int a = 0; a < 4; ++a)
+        for (int b = a + 1; b < 4; ++b)
+            if (s[b] < s[a]) { int x = s[a]; s[a] = s[b]; s[b] = x; x = perm[a]; perm[a] = perm[b]; perm[b] = x; }
+}
+
+static double fm_sorted_v6(const orc_mesh *m, const int s[4], double X[3][3])
+{
+    const v3 O = ld3(m->pos, s[3]);
+    for (int k = 0; k < 3; ++k) {
+        const v3 p = ld3(m->pos, s[k]);
+        X[k][0] = p.x - O.x; X[k][1] = p.y - O.y; X[k][2] = p.z - O.z;
+    }
+    return X[0][0] * (X[1][1] * X[2][2] - X[1][2] * X[2][1]) + X[0][1] * (X[1][2] * X[2][0] - X[1][0] * X[2][2]) +
+           X[0][2] * (X[1][0] * X[2][1] - X[1][1] * X[2][0]);
+}
+
+/* records for all tets; returns the smallest tet height (for the guard G = max(1e-7, 1e-11 / hmin)) */
+double orc_filter_build(long nTets, MESH_ARGS, void *recsOut)
+{
+    MESH_INIT;
+    fm_rec *recs = (fm_rec *)recsOut;
+    double hmin = 1e300;
+    for (long t = 0; t < nTets; ++t) {
+        int s[4], perm[4];
+        double X[3][3];
+        fm_sorted(&m, (int)t, s, perm);
+        const double v6 = fm_sorted_v6(&m, s, X);
+        const int flip = v6 < 0.0;
+        fm_rec *r = recs + t;
+        for (int j = 0; j < 4; ++j) { /* sorted slot j -> stored slot */
+            const int st = (flip && (j == 1 || j == 2)) ? 3 - j : j;
+            const int f = m.tetfacets[4 * t + perm[j]];
+            const int nbr = other_tet(m.finfo, f, (int)t);
+            if (nbr < 0) { r->link[st] = -1; continue; }
+            int s2[4], perm2[4], ns = -1;
+            double X2[3][3];
+            fm_sorted(&m, nbr, s2, perm2);
+            for (int q = 0; q < 4; ++q)
+                if (m.tetfacets[4 * nbr + perm2[q]] == f) ns = q;
+            if ((ns == 1 || ns == 2) && fm_sorted_v6(&m, s2, X2) < 0.0) ns = 3 - ns;
+            r->link[st] = (nbr << 2) | ns;
+        }
+        if (flip) { for (int c = 0; c < 3; ++c) { const double x = X[1][c]; X[1][c] = X[2][c]; X[2][c] = x; } }
+        float E = 0.f;
+        for (int k = 0; k < 3; ++k)
+            for (int c = 0; c < 3; ++c) E = fmaxf(E, fabsf((float)X[k][c]));
+        E = E * 1.0000002f;
+        r->E = flip ? -E : E;
+        double nmax = 0.0, n3[3] = { 0, 0, 0 };
+        for (int j = 0; j < 3; ++j) {
+            const double *u = X[(j + 1) % 3], *w = X[(j + 2) % 3];
+            const double n[3] = { u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0] };
+            for (int c = 0; c < 3; ++c) { r->N[j][c] = (float)n[c]; n3[c] -= n[c]; }
+            nmax = fmax(nmax, n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        }
+        nmax = fmax(nmax, n3[0] * n3[0] + n3[1] * n3[1] + n3[2] * n3[2]);
+        r->origin = s[3];
+        r->V6 = (float)fabs(v6);
+        const double h = fabs(v6) / sqrt(nmax);
+        if (h < hmin) hmin = h;
+    }
+    return hmin;
+}
+
+/* One sub-step walk of every particle: out[i] = final tet if every visit was certified, -1 if the filter refused
+ * (guard band, wall, no exit, visit cap); visits[i] = tets visited.  errScale scales the rounding-error term of the
+ * guard (1 = the product's; 0 with guard = 0 switches the band off, for the test that shows what it is there for). */
+void orc_filter_walk(long n, const double *p, const double *disp, const int *tet, const void *recsIn, const double *pos,
+                     double guard, double errScale, int *out, int *visits)
+{
+    const fm_rec *recs = (const fm_rec *)recsIn;
+    const float INF = INFINITY, G = (float)guard * 1.0000002f, ES = (float)errScale * 3.814697265625e-6f;
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) {
+        out[i] = -1;
+        visits[i] = 0;
+        int cur = tet[i];
+        if (cur < 0 || p[4 * i + 3] == 0.0) continue;
+        const double *P0 = p + 4 * i, *d = disp + 4 * i;
+        const fm_rec *f = recs + cur;
+        const double *O = pos + 3 * (long)f->origin;
+        float rx = (float)(P0[0] - O[0]), ry = (float)(P0[1] - O[1]), rz = (float)(P0[2] - O[2]);
+        const float dx = (float)d[0], dy = (float)d[1], dz = (float)d[2];
+        const float Dd = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+        float RD3 = 3.f * (fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) + Dd);
+        float t_in = 0.f;
+        int in_j = -1, result = -1;
+        for (int it = 0; it < 48; ++it) {
+            visits[i]++;
+            float a[4], b[4], e[4];
+            for (int j = 0; j < 3; ++j) {
+                a[j] = rx * f->N[j][0] + ry * f->N[j][1] + rz * f->N[j][2];
+                b[j] = dx * f->N[j][0] + dy * f->N[j][1] + dz * f->N[j][2];
+            }
+            const float V = f->V6, E = fabsf(f->E);
+            a[3] = V - a[0] - a[1] - a[2];
+            b[3] = -(b[0] + b[1] + b[2]);
+            const float g = fmaf(G, V, ES * (E * E) * (E + RD3));
+            float c1m = INF, eam = INF, emin = INF;
+            for (int j = 0; j < 4; ++j) {
+                e[j] = a[j] + b[j];
+                const float c1 = (j == in_j) ? INF : fmaf(t_in, b[j], a[j]);
+                c1m = fminf(c1m, c1);
+                eam = fminf(eam, fabsf(e[j]));
+                emin = fminf(emin, e[j]);
+            }
+            if (!(fminf(c1m, eam) >= g) || !(V > 1e-30f)) break;          /* refuse */
+            if (emin > 0.f) { result = cur; break; }                        /* done */
+            float t = INF;
+            int js = -1;
+            for (int j = 0; j < 4; ++j) {
+                if (e[j] < 0.f && j != in_j) {
+                    const float tj = a[j] * (1.0f / -b[j]);
+                    if (tj < t) { t = tj; js = j; }
+                }
+            }
+            if (js < 0) break;
+            float c3m = INF;
+            for (int j = 0; j < 4; ++j)
+                if (j != js) c3m = fminf(c3m, fmaf(t, b[j], a[j]));
+            if (!((c3m >= g) && (t > t_in) && (t <= 1.f))) break;
+            const int link = f->link[js];
+            if (link < 0) break;                                            /* wall: the exact path reflects */
+            cur = link >> 2;
+            in_j = link & 3;
+            t_in = t;
+            const int oldOrigin = f->origin;
+            f = recs + cur;
+            if (f->origin != oldOrigin) {
+                O = pos + 3 * (long)f->origin;
+                rx = (float)(P0[0] - O[0]); ry = (float)(P0[1] - O[1]); rz = (float)(P0[2] - O[2]);
+                RD3 = 3.f * (fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) + Dd);
+            }
+        }
+        out[i] = result;
+    }
+}
+
+int orc_filter_rec_bytes(void) { return (int)sizeof(fm_rec); }

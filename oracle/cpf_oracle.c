@@ -686,3 +686,4 @@ int orc_abi_version(void) { return 1; }
 
 #include "cpf_oracle_ext.c"
 #include "cpf_foamtrack.c"
+#include "cpf_filter_model.c"

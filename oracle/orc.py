@@ -179,6 +179,30 @@ def foamtrack_substeps(mesh: TetMesh, cl: Cloud, Utet: np.ndarray, n_steps: int,
                                         _d(Utet), C.c_int(int(reflect)), C.c_int(int(threads))))
 
 
+class FilterModel:
+    """CPU model of the product's fp32 guarded walk (oracle/cpf_filter_model.c) over the oracle's mesh tables."""
+
+    def __init__(self, mesh: TetMesh):
+        L = lib()
+        L.orc_filter_build.restype = C.c_double
+        L.orc_filter_rec_bytes.restype = C.c_int
+        self.mesh = mesh
+        self.recs = np.zeros(mesh.idx.shape[0] * int(L.orc_filter_rec_bytes()), dtype=np.uint8)
+        self.hmin = float(L.orc_filter_build(C.c_long(mesh.idx.shape[0]), *mesh.args(), self.recs.ctypes.data_as(C.c_void_p)))
+        g = 1e-11 / self.hmin
+        self.guard = g if g > 1e-7 else 1e-7
+
+    def walk(self, p4: np.ndarray, disp4: np.ndarray, tet: np.ndarray, *, guard=None, err_scale=1.0):
+        """-> (final tet or -1 where the filter refused, visits)"""
+        n = p4.shape[0]
+        out = np.empty(n, dtype=np.int32)
+        vis = np.empty(n, dtype=np.int32)
+        lib().orc_filter_walk(C.c_long(n), _d(np.ascontiguousarray(p4)), _d(np.ascontiguousarray(disp4)),
+                              _i(np.ascontiguousarray(tet, dtype=np.int32)), self.recs.ctypes.data_as(C.c_void_p), _d(self.mesh.pos),
+                              C.c_double(self.guard if guard is None else guard), C.c_double(err_scale), _i(out), _i(vis))
+        return out, vis
+
+
 def advect(mesh, cl, U, dt, vertex_velocity=False):
     lib().orc_advect(C.c_long(cl.n), _d(cl.p), _i(cl.tet), _d(cl.vel), _d(cl.disp), C.c_double(dt), *mesh.args(),
                      _d(np.ascontiguousarray(U)), C.c_int(int(vertex_velocity)))

@@ -1,0 +1,123 @@
+"""Soundness of the fp32 guarded walk, tested on the CPU.
+
+oracle/cpf_filter_model.c restates the product's filter (cpf_geom.cuh visit_fast32 + the 64-byte records of
+cpf_mesh.cu k_build_fast) over the oracle's mesh tables.  The property: whenever the filter certifies a walk, it ends
+in the tet the reference's fp64 segment walk ends in -- over random segments and over segments built to graze
+vertices, edges and faces, on regular, skewed, anisotropic and far-from-the-origin meshes.  Refusals cost time, never
+correctness; their rate is bounded where the geometry is benign."""
+import numpy as np
+import pytest
+
+from conftest import make_case  # noqa: F401  (fixtures synth / orc come from conftest)
+
+
+def _cases(synth):
+    yield "regular", synth.box_mesh(9, 8, 7, jitter=0.0), 0.93
+    yield "jittered", synth.box_mesh(9, 8, 7, jitter=0.25), 0.93
+    yield "anisotropic 1:50", synth.box_mesh(8, 8, 8, lo=(0, 0, 0), hi=(1.0, 1.0, 0.02), jitter=0.2), 0.90
+    yield "far from the origin", synth.box_mesh(8, 8, 8, lo=(4096.0, -2048.0, 1024.0), hi=(4097.0, -2047.0, 1025.0), jitter=0.2), 0.90
+    yield "tiny cells", synth.box_mesh(8, 8, 8, lo=(0, 0, 0), hi=(1e-5, 1e-5, 1e-5), jitter=0.2), 0.90
+
+
+def _segments(rng, pm, mesh, orc, n):
+    """start points (random + exactly on vertices / edge midpoints / face centroids) and displacements (random lengths
+    from 1e-6 to ~2 cells, plus segments that end on, or pass exactly through, a vertex / edge midpoint / face centroid)"""
+    span = pm.hi - pm.lo
+    h = span / np.array([8.0, 8.0, 8.0])
+    p = np.ones((n, 4))
+    p[:, :3] = pm.lo + (0.02 + 0.96 * rng.random((n, 3))) * span
+    k = n // 8
+    nt = mesh.idx.shape[0]
+    t = rng.integers(0, nt, size=3 * k)
+    a, b, c = mesh.pos[mesh.idx[t, 0]], mesh.pos[mesh.idx[t, 1]], mesh.pos[mesh.idx[t, 2]]
+    p[:k, :3] = a[:k]
+    p[k:2 * k, :3] = 0.5 * (a[k:2 * k] + b[k:2 * k])
+    p[2 * k:3 * k, :3] = (a[2 * k:] + b[2 * k:] + c[2 * k:]) / 3.0
+    inside = np.all((p[:, :3] > pm.lo) & (p[:, :3] < pm.hi), axis=1)
+    p[~inside, :3] = pm.lo + 0.5 * span
+    length = 10.0 ** rng.uniform(-6.0, 0.3, size=n)
+    d = rng.normal(size=(n, 3))
+    d *= (length / np.linalg.norm(d, axis=1))[:, None]
+    d *= h
+    # aimed segments: end exactly on a feature of a nearby tet, or pass through it (twice the distance)
+    tet0 = orc.locate_brute(mesh, p)
+    aim = np.arange(3 * k, 6 * k)
+    tt = np.clip(tet0[aim], 0, nt - 1)
+    va, vb, vc = mesh.pos[mesh.idx[tt, 1]], mesh.pos[mesh.idx[tt, 2]], mesh.pos[mesh.idx[tt, 3]]
+    target = np.concatenate([va[:k], 0.5 * (va[k:2 * k] + vb[k:2 * k]), (va[2 * k:] + vb[2 * k:] + vc[2 * k:]) / 3.0])
+    through = rng.random(3 * k) < 0.5
+    d[aim] = (target - p[aim, :3]) * np.where(through, 2.0, 1.0)[:, None]
+    disp = np.zeros((n, 4))
+    disp[:, :3] = d
+    return p, disp, tet0
+
+
+def test_fp32_filter_certifies_only_what_the_reference_decides(synth, orc):
+    rng = np.random.default_rng(1591593751)
+    total = certified = 0
+    for name, pm, min_rate in _cases(synth):
+        mesh = orc.tet_mesh_from_poly(pm)
+        fm = orc.FilterModel(mesh)
+        for rep in range(3):
+            p, disp, tet0 = _segments(rng, pm, mesh, orc, 60000)
+            ok = tet0 >= 0
+            p, disp, tet0 = p[ok], disp[ok], tet0[ok]
+            out, vis = fm.walk(p, disp, tet0)
+            cl = orc.Cloud.make(p, tet0)
+            cl.disp[:] = disp
+            orc.locate_convex(mesh, cl)
+            cert = out >= 0
+            wrong = cert & (out != cl.tet)
+            assert not wrong.any(), (name, int(wrong.sum()), p[wrong][:3], disp[wrong][:3], out[wrong][:3], cl.tet[wrong][:3])
+            # benign part of the sample (random starts, random directions): the filter must let almost everything through
+            # that does not end at a wall
+            n = p.shape[0]
+            benign = np.zeros(n, dtype=bool)
+            benign[6 * (60000 // 8):] = True
+            benign = benign[:n] & (cl.tet >= 0)
+            assert cert[benign].mean() > min_rate, (name, cert[benign].mean())
+            assert vis[cert].max() <= 48
+            total += n
+            certified += int(cert.sum())
+    assert total > 800000 and certified > 0.25 * total  # three quarters of the sample are built to be refused or to hit walls
+
+
+def test_filter_model_walks_like_the_exact_walk_visits(synth, orc):
+    """The model is a faithful stand-in: on a benign case the number of tets it visits equals the exact walk's."""
+    pm = synth.box_mesh(8, 8, 8, jitter=0.2)
+    mesh = orc.tet_mesh_from_poly(pm)
+    fm = orc.FilterModel(mesh)
+    rng = np.random.default_rng(7)
+    p = np.ones((20000, 4))
+    p[:, :3] = 0.1 + 0.8 * rng.random((20000, 3))
+    disp = np.zeros((20000, 4))
+    disp[:, :3] = 0.08 * rng.normal(size=(20000, 3))
+    tet0 = orc.locate_brute(mesh, p)
+    out, vis = fm.walk(p, disp, tet0)
+    assert (out >= 0).mean() > 0.95
+    assert 1.5 < vis[out >= 0].mean() < 6.0
+    assert 1e-8 < fm.guard < 1e-3 and fm.hmin > 0
+
+
+def test_the_guard_band_is_what_makes_the_filter_sound(synth, orc):
+    """The same adversarial sample with the band switched off, or with only its geometric part G*V6 (no rounding-error
+    term), produces wrong certifications -- so the property test above can fail, and both parts of g are needed."""
+    rng = np.random.default_rng(1591593751)
+    pm = synth.box_mesh(9, 8, 7, jitter=0.0)
+    mesh = orc.tet_mesh_from_poly(pm)
+    fm = orc.FilterModel(mesh)
+    p, disp, tet0 = _segments(rng, pm, mesh, orc, 60000)
+    ok = tet0 >= 0
+    p, disp, tet0 = p[ok], disp[ok], tet0[ok]
+    cl = orc.Cloud.make(p, tet0)
+    cl.disp[:] = disp
+    orc.locate_convex(mesh, cl)
+
+    def wrong(**kw):
+        out, _ = fm.walk(p, disp, tet0, **kw)
+        return int(((out >= 0) & (out != cl.tet)).sum())
+
+    assert wrong() == 0
+    assert wrong(guard=0.0, err_scale=0.0) > 100   # no band at all
+    assert wrong(err_scale=0.0) > 10               # G*V6 only: fp32 rounding decides some exits
+    assert wrong(err_scale=0.25) == 0              # the derived bound (0.66 of the term) has margin in practice
