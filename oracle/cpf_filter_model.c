@@ -13,6 +13,7 @@ typedef struct {
     float N[3][3];   /* inward normals of the faces opposite stored slots 0..2 (slot 3 = origin = highest id) */
     int origin;
     float V6, E;     /* E < 0: stored slots 1/2 exchanged w.r.t. the sorted vertex order */
+    int face[4];     /* model only: face id behind each stored slot (the product derives it from tetv / tetnrm) */
 } fm_rec;
 
 static void fm_sorted(const orc_mesh *m, int t, int s[4], int perm[4])
@@ -51,6 +52,7 @@ double orc_filter_build(long nTets, MESH_ARGS, void *recsOut)
             const int st = (flip && (j == 1 || j == 2)) ? 3 - j : j;
             const int f = m.tetfacets[4 * t + perm[j]];
             const int nbr = other_tet(m.finfo, f, (int)t);
+            r->face[st] = f;
             if (nbr < 0) { r->link[st] = -1; continue; }
             int s2[4], perm2[4], ns = -1;
             double X2[3][3];
@@ -153,6 +155,144 @@ void orc_filter_walk(long n, const double *p, const double *disp, const int *tet
             }
         }
         out[i] = result;
+    }
+}
+
+
+/* ---- one whole sub-step as the wall-capable queue pass does it (k_fast<.., WALL = 1>, wall_reflect_on_path) ---------- */
+typedef struct { float rx, ry, rz, dx, dy, dz, RD3, Dd, t_in; int in_j, cur; } fm_walk;
+
+static void fm_begin(fm_walk *w, const double *O, v3 P0, v3 d, int tet)
+{
+    w->rx = (float)(P0.x - O[0]); w->ry = (float)(P0.y - O[1]); w->rz = (float)(P0.z - O[2]);
+    w->dx = (float)d.x; w->dy = (float)d.y; w->dz = (float)d.z;
+    w->Dd = fmaxf(fmaxf(fabsf(w->dx), fabsf(w->dy)), fabsf(w->dz));
+    w->RD3 = 3.f * (fmaxf(fmaxf(fabsf(w->rx), fabsf(w->ry)), fabsf(w->rz)) + w->Dd);
+    w->t_in = 0.f; w->in_j = -1; w->cur = tet;
+}
+
+enum { FM_DONE = 0, FM_HOP = 1, FM_REFUSE = 2, FM_WALL = 3 };
+
+static int fm_visit(const fm_rec *recs, const double *pos, v3 P0, fm_walk *w, float G, int *jsOut)
+{
+    const float INF = INFINITY;
+    const fm_rec *f = recs + w->cur;
+    float a[4], b[4], e[4];
+    for (int j = 0; j < 3; ++j) {
+        a[j] = w->rx * f->N[j][0] + w->ry * f->N[j][1] + w->rz * f->N[j][2];
+        b[j] = w->dx * f->N[j][0] + w->dy * f->N[j][1] + w->dz * f->N[j][2];
+    }
+    const float V = f->V6, E = fabsf(f->E);
+    a[3] = V - a[0] - a[1] - a[2];
+    b[3] = -(b[0] + b[1] + b[2]);
+    const float g = fmaf(G, V, 3.814697265625e-6f * (E * E) * (E + w->RD3));
+    float c1m = INF, eam = INF, emin = INF;
+    for (int j = 0; j < 4; ++j) {
+        e[j] = a[j] + b[j];
+        const float c1 = (j == w->in_j) ? INF : fmaf(w->t_in, b[j], a[j]);
+        c1m = fminf(c1m, c1); eam = fminf(eam, fabsf(e[j])); emin = fminf(emin, e[j]);
+    }
+    if (!(fminf(c1m, eam) >= g) || !(V > 1e-30f)) return FM_REFUSE;
+    if (emin > 0.f) return FM_DONE;
+    float t = INF;
+    int js = -1;
+    for (int j = 0; j < 4; ++j)
+        if (e[j] < 0.f && j != w->in_j) {
+            const float tj = a[j] * (1.0f / -b[j]);
+            if (tj < t) { t = tj; js = j; }
+        }
+    if (js < 0) return FM_REFUSE;
+    float c3m = INF;
+    for (int j = 0; j < 4; ++j)
+        if (j != js) c3m = fminf(c3m, fmaf(t, b[j], a[j]));
+    if (!((c3m >= g) && (t > w->t_in) && (t <= 1.f))) return FM_REFUSE;
+    *jsOut = js;
+    const int link = f->link[js];
+    if (link < 0) return FM_WALL;
+    const int oldOrigin = f->origin;
+    w->cur = link >> 2; w->in_j = link & 3; w->t_in = t;
+    f = recs + w->cur;
+    if (f->origin != oldOrigin) {
+        const double *O = pos + 3 * (long)f->origin;
+        w->rx = (float)(P0.x - O[0]); w->ry = (float)(P0.y - O[1]); w->rz = (float)(P0.z - O[2]);
+        w->RD3 = 3.f * (fmaxf(fmaxf(fabsf(w->rx), fabsf(w->ry)), fabsf(w->rz)) + w->Dd);
+    }
+    return FM_HOP;
+}
+
+/* cpf_geom.cuh exact_crossing: the reference's arithmetic for ONE certified face */
+static int fm_exact_crossing(const orc_mesh *m, int tet, int f, v3 E, v3 *S, v3 *A, v3 *n)
+{
+    *n = face_inward_normal(m, f, tet, A);
+    const v3 d = v3_sub(E, *S);
+    const double fd = ref_dot(v3_sub(*A, *S), *n);
+    const double dT = fd / ref_dot(d, *n);
+    if (!(fd < ORC_TOL && dT > ORC_TOL && dT <= 1.0)) return 0;
+    S->x = fma(d.x, dT, S->x); S->y = fma(d.y, dT, S->y); S->z = fma(d.z, dT, S->z);
+    return 1;
+}
+
+/* status[i]: 0 refused (the exact kernel decides), 1 certified without wall contact, 2 certified with one in-place
+ * reflection.  For status > 0: p, vel, tet hold the state after S5, comparable bit for bit with the oracle.
+ * skipReplay != 0 (tests only): take the hit point from the sub-step's start instead of replaying the crossed faces --
+ * what a wall handler WITHOUT the exact replay would compute. */
+void orc_filter_substep(long n, double *p, const double *disp, double *vel, int *tet, const void *recsIn, MESH_ARGS, double guard,
+                        int skipReplay, int *status)
+{
+    MESH_INIT;
+    const fm_rec *recs = (const fm_rec *)recsIn;
+    const float G = (float)guard * 1.0000002f;
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) {
+        status[i] = 0;
+        if (tet[i] < 0 || p[4 * i + 3] == 0.0) continue;
+        const v3 P = { p[4 * i], p[4 * i + 1], p[4 * i + 2] }, dsp = { disp[4 * i], disp[4 * i + 1], disp[4 * i + 2] };
+        v3 u = { vel[4 * i], vel[4 * i + 1], vel[4 * i + 2] };
+        fm_walk w;
+        fm_begin(&w, m.pos + 3 * (long)recs[tet[i]].origin, P, dsp, tet[i]);
+        int pathTet[16], pathSlot[16], visits = 0, leg = 0, done = 0, refused = 0;
+        v3 Phit = P, Eref = P;
+        while (!done && !refused) {
+            int js = -1;
+            ++visits;
+            const int before = w.cur;
+            const int oc = fm_visit(recs, m.pos, leg ? Phit : P, &w, G, &js);
+            if (oc == FM_DONE) done = 1;
+            else if (oc == FM_HOP) {
+                if (visits >= 48) refused = 1;
+                else if (leg == 0 && visits <= 15) { pathTet[visits - 1] = before; pathSlot[visits - 1] = js; }
+            } else if (oc == FM_WALL && leg == 0 && visits <= 15 && w.Dd < 10.f) {
+                /* wall_reflect_on_path: exact replay of the crossed faces, then reflectInTet on the wall face */
+                v3 E = v3_add(P, dsp), S = P, A, nrm;
+                int ok = 1;
+                for (int h = 0; h < visits - 1 && ok && !skipReplay; ++h) ok = fm_exact_crossing(&m, pathTet[h], recs[pathTet[h]].face[pathSlot[h]], E, &S, &A, &nrm);
+                if (ok) ok = fm_exact_crossing(&m, w.cur, recs[w.cur].face[js], E, &S, &A, &nrm);
+                if (ok) ok = fabs(ref_dot(v3_sub(A, S), nrm)) < ORC_TOL;
+                if (!ok) { refused = 1; break; }
+                Phit = S;
+                const v3 r = v3_sub(E, A);
+                double sp = -fma(r.z, nrm.z, fma(r.y, nrm.y, r.x * nrm.x));
+                sp = sp + sp;
+                double sv = -fma(u.z, nrm.z, fma(u.y, nrm.y, u.x * nrm.x));
+                sv = sv + sv;
+                E.x = fma(sp, nrm.x, E.x); E.y = fma(sp, nrm.y, E.y); E.z = fma(sp, nrm.z, E.z);
+                u.x = fma(sv, nrm.x, u.x); u.y = fma(sv, nrm.y, u.y); u.z = fma(sv, nrm.z, u.z);
+                Eref = E;
+                const int wallTet = w.cur;
+                fm_begin(&w, m.pos + 3 * (long)recs[wallTet].origin, Phit, v3_sub(Eref, Phit), wallTet);
+                w.in_j = js;
+                visits = 0;
+                leg = 1;
+            } else refused = 1;
+        }
+        if (refused) continue;
+        v3 Pn;
+        if (leg) { const v3 nd = v3_sub(Eref, Phit); Pn = v3_add(Phit, nd); }
+        else Pn = v3_add(P, dsp);
+        p[4 * i] = Pn.x; p[4 * i + 1] = Pn.y; p[4 * i + 2] = Pn.z;
+        vel[4 * i] = u.x; vel[4 * i + 1] = u.y; vel[4 * i + 2] = u.z;
+        tet[i] = w.cur;
+        status[i] = 1 + leg;
     }
 }
 

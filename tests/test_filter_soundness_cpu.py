@@ -121,3 +121,87 @@ def test_the_guard_band_is_what_makes_the_filter_sound(synth, orc):
     assert wrong(guard=0.0, err_scale=0.0) > 100   # no band at all
     assert wrong(err_scale=0.0) > 10               # G*V6 only: fp32 rounding decides some exits
     assert wrong(err_scale=0.25) == 0              # the derived bound (0.66 of the term) has margin in practice
+
+
+def _wall_segments(rng, pm, mesh, orc, n):
+    """particles in the cells next to the boundary, moving mostly outwards: plain wall hits after 0..3 hops, hits aimed at
+    the edges and corners of the box (two or three walls at once), grazing hits, and hits on the vertices / edge
+    midpoints / centroids of boundary faces"""
+    span = pm.hi - pm.lo
+    h = span / 8.0
+    p = np.ones((n, 4))
+    u = rng.random((n, 3))
+    side = rng.integers(0, 6, size=n)
+    ax, hi_side = side % 3, side >= 3
+    depth = 10.0 ** rng.uniform(-4.0, 0.2, size=n) * h[ax]          # distance from the wall, 1e-4 .. 1.6 cells
+    p[:, :3] = pm.lo + (0.03 + 0.94 * u) * span
+    rows = np.arange(n)
+    p[rows, ax] = np.where(hi_side, pm.hi[ax] - depth, pm.lo[ax] + depth)
+    d = rng.normal(size=(n, 3)) * h * 0.6
+    d[rows, ax] = np.where(hi_side, 1.0, -1.0) * np.abs(d[rows, ax]) * 2.0 + np.where(hi_side, depth, -depth)
+    k = n // 6
+    # into box corners and edges from at most ~1.5 cells away: two or three walls within one sub-step
+    sgn = np.where(rng.random((2 * k, 3)) < 0.5, 0.0, 1.0)
+    corner = pm.lo + sgn * span
+    off = 10.0 ** rng.uniform(-3.0, 0.2, size=(2 * k, 3)) * h * np.where(sgn > 0, -1.0, 1.0)
+    p[:2 * k, :3] = corner + off
+    p[k:2 * k, 0] = pm.lo[0] + (0.1 + 0.8 * rng.random(k)) * span[0]      # second group: an edge, not a corner
+    aim = corner + rng.normal(size=(2 * k, 3)) * h * 10.0 ** rng.uniform(-3.0, -0.3, size=(2 * k, 1))  # near, not at, the corner
+    d[:2 * k] = (aim - p[:2 * k, :3]) * rng.uniform(1.1, 2.0, size=(2 * k, 1))
+    d[k:2 * k, 0] = rng.normal(size=k) * h[0] * 0.3
+    # exactly at features of boundary faces
+    bfaces = np.flatnonzero(mesh.finfo[:, 1] < 0) if hasattr(mesh, "finfo") else np.zeros(0, dtype=np.int64)
+    if bfaces.size:
+        fsel = bfaces[rng.integers(0, bfaces.size, size=k)]
+        tri = mesh.pos[mesh.facets[fsel, :3]]
+        wgt = rng.dirichlet((0.3, 0.3, 0.3), size=k)                      # mass near vertices and edges
+        target = (tri * wgt[:, :, None]).sum(axis=1)
+        d[2 * k:3 * k] = (target - p[2 * k:3 * k, :3]) * rng.uniform(1.0, 2.0, size=(k, 1))
+    disp = np.zeros((n, 4))
+    disp[:, :3] = d
+    return p, disp
+
+
+def test_in_place_wall_reflection_is_the_references_reflection(synth, orc):
+    """The wall-capable fast pass (cpf_advect.cu k_fast<.., WALL = 1>, cpf_geom.cuh wall_reflect_on_path) replays only the
+    certified crossings in fp64 and mirrors the end point about the certified wall face.  Whenever the model of that
+    pass certifies a sub-step -- with or without a wall contact -- position, velocity and tet after S5 must equal the
+    reference's locate + reflect + move bit for bit; edges, corners and grazing hits must be refused or right."""
+    rng = np.random.default_rng(20261017)
+    n_wall = 0
+    for name, pm, _ in _cases(synth):
+        mesh = orc.tet_mesh_from_poly(pm)
+        fm = orc.FilterModel(mesh)
+        for rep in range(2):
+            p, disp = _wall_segments(rng, pm, mesh, orc, 60000)
+            tet0 = orc.locate_brute(mesh, p)
+            ok = tet0 >= 0
+            p, disp, tet0 = p[ok], disp[ok], tet0[ok]
+            v = np.zeros_like(p)
+            v[:, :3] = disp[:, :3] / 0.01
+            ref = orc.Cloud.make(p, tet0)
+            ref.disp[:] = disp
+            ref.vel[:] = v
+            orc.locate_convex(mesh, ref)
+            hit = ref.tet < 0
+            orc.reflect_convex(mesh, ref)
+            orc.move(ref)
+            mod = orc.Cloud.make(p, tet0)
+            mod.vel[:] = v
+            st = fm.substep(mod, disp)
+            c = st > 0
+            assert np.array_equal(mod.tet[c], ref.tet[c]), (name, int((mod.tet[c] != ref.tet[c]).sum()))
+            assert np.array_equal(mod.p[c, :3].view(np.uint64), ref.p[c, :3].view(np.uint64)), name
+            assert np.array_equal(mod.vel[c, :3].view(np.uint64), ref.vel[c, :3].view(np.uint64)), name
+            assert not (st[~hit] == 2).any() and not (st[hit] == 1).any(), "wall contacts must be recognised as such"
+            assert hit.mean() > 0.5, "the sample must be dominated by wall contacts"
+            assert (st[hit] == 2).mean() > 0.35, (name, (st[hit] == 2).mean())
+            n_wall += int((st == 2).sum())
+            if rep == 0 and name == "jittered":
+                # a handler without the exact replay of the crossed faces gets the hit point's last bits wrong
+                bad = orc.Cloud.make(p, tet0)
+                bad.vel[:] = v
+                sb = fm.substep(bad, disp, skip_replay=True)
+                cb = sb == 2
+                assert (bad.p[cb, :3] != ref.p[cb, :3]).any(axis=1).sum() > 5  # rare (last bits), but bit-exactness is the bar
+    assert n_wall > 100000
