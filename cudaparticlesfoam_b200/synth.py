@@ -225,6 +225,80 @@ def polyhex_mesh(nx: int, ny: int, nz: int, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.
     return pm
 
 
+def honeycomb_mesh(nx: int, ny: int, nz: int, R: float = 0.06, hz: float = 0.1, jitter: float = 0.08,
+                   seed: int = 1591593751) -> PolyMesh:
+    """A genuinely polyhedral block (BASELINE config 4 code path): nx x ny hexagonal columns (pointy-top honeycomb of
+    circumradius R) extruded in nz layers of height hz.  Cells are hexagonal prisms -- 8 faces, 12 points, 20 tets --
+    three cells meet at every vertical edge, and the side boundary is a zigzag, not a plane.  Interior honeycomb vertices
+    are displaced by up to ``jitter``*R (all levels alike, so every face stays planar).  Patches: z-, z+, sides."""
+    s3 = np.sqrt(3.0)
+    ang = np.deg2rad(30.0 + 60.0 * np.arange(6))
+    key2id, pts2d, cell_v = {}, [], []
+    centres2d = []
+    for j in range(ny):
+        for i in range(nx):
+            cx, cy = s3 * R * (i + 0.5 * (j & 1)), 1.5 * R * j
+            centres2d.append((cx, cy))
+            ids = []
+            for k in range(6):
+                x, y = cx + R * np.cos(ang[k]), cy + R * np.sin(ang[k])
+                key = (int(round(x / R * 1e6)), int(round(y / R * 1e6)))
+                if key not in key2id:
+                    key2id[key] = len(pts2d)
+                    pts2d.append([x, y])
+                ids.append(key2id[key])
+            cell_v.append(ids)
+    pts2d = np.asarray(pts2d)
+    n2 = pts2d.shape[0]
+    # interior vertices (shared by three columns) get a reproducible in-plane displacement
+    use = np.zeros(n2, dtype=np.int64)
+    for ids in cell_v:
+        use[ids] += 1
+    r = uniform01(seed, n2, stream=301) * jitter * R
+    th = uniform01(seed, n2, stream=302) * 2.0 * np.pi
+    inner = use == 3
+    pts2d[inner, 0] += (r * np.cos(th))[inner]
+    pts2d[inner, 1] += (r * np.sin(th))[inner]
+    points = np.concatenate([np.column_stack([pts2d, np.full(n2, hz * k)]) for k in range(nz + 1)], axis=0)
+
+    def pid(v, k):
+        return v + n2 * k
+
+    ncol = nx * ny
+    faces = {}  # sorted vertex tuple -> [loop as seen from the first (lowest-id) cell, owner, neighbour, kind]
+    order = []
+    for k in range(nz):
+        for col in range(ncol):
+            c = col + ncol * k
+            v = cell_v[col]
+            loops = [([pid(x, k) for x in reversed(v)], 0), ([pid(x, k + 1) for x in v], 1)]
+            for e in range(6):
+                a, b = v[e], v[(e + 1) % 6]
+                loops.append(([pid(a, k), pid(b, k), pid(b, k + 1), pid(a, k + 1)], 2))
+            for loop, kind in loops:
+                key = tuple(sorted(loop))
+                if key in faces:
+                    faces[key][2] = c
+                else:
+                    faces[key] = [loop, c, -1, kind]
+                    order.append(key)
+    internal = sorted((faces[k] for k in order if faces[k][2] >= 0), key=lambda f: (f[1], f[2]))
+    boundary = [faces[k] for k in order if faces[k][2] < 0]
+    groups = [[f for f in boundary if f[3] == kind] for kind in (0, 1, 2)]
+    allf = internal + groups[0] + groups[1] + groups[2]
+    off = np.zeros(len(allf) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(f[0]) for f in allf])
+    verts = np.asarray([x for f in allf for x in f[0]], dtype=np.int32)
+    owner = np.asarray([f[1] for f in allf], dtype=np.int32)
+    neighbour = np.asarray([f[2] for f in internal], dtype=np.int32)
+    starts = np.cumsum([len(internal)] + [len(g) for g in groups]).astype(np.int32)
+    c2 = np.asarray(centres2d)
+    cc = np.concatenate([np.column_stack([c2, np.full(ncol, hz * (k + 0.5))]) for k in range(nz)], axis=0)
+    return PolyMesh(points=np.ascontiguousarray(points), face_offsets=off, face_verts=verts, owner=owner, neighbour=neighbour,
+                    cell_centres=np.ascontiguousarray(cc), patch_starts=starts, patch_names=("z-", "z+", "sides"), dims=(nx, ny, nz),
+                    lo=points.min(axis=0), hi=points.max(axis=0))
+
+
 def channel_mesh(nx=400, ny=50, nz=50, jitter: float = 0.0) -> PolyMesh:
     """BASELINE config 3/5 mesh: 4 x 1 x 1 channel, inlet x-, outlet x+, walls on +-y/+-z."""
     return box_mesh(nx, ny, nz, lo=(0.0, 0.0, 0.0), hi=(4.0, 1.0, 1.0), jitter=jitter)

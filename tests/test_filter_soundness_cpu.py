@@ -17,6 +17,7 @@ def _cases(synth):
     yield "anisotropic 1:50", synth.box_mesh(8, 8, 8, lo=(0, 0, 0), hi=(1.0, 1.0, 0.02), jitter=0.2), 0.90
     yield "far from the origin", synth.box_mesh(8, 8, 8, lo=(4096.0, -2048.0, 1024.0), hi=(4097.0, -2047.0, 1025.0), jitter=0.2), 0.90
     yield "tiny cells", synth.box_mesh(8, 8, 8, lo=(0, 0, 0), hi=(1e-5, 1e-5, 1e-5), jitter=0.2), 0.90
+    yield "honeycomb prisms", synth.honeycomb_mesh(9, 8, 8), 0.85
 
 
 def _segments(rng, pm, mesh, orc, n):
@@ -150,7 +151,7 @@ def _wall_segments(rng, pm, mesh, orc, n):
     d[:2 * k] = (aim - p[:2 * k, :3]) * rng.uniform(1.1, 2.0, size=(2 * k, 1))
     d[k:2 * k, 0] = rng.normal(size=k) * h[0] * 0.3
     # exactly at features of boundary faces
-    bfaces = np.flatnonzero(mesh.finfo[:, 1] < 0) if hasattr(mesh, "finfo") else np.zeros(0, dtype=np.int64)
+    bfaces = np.flatnonzero((mesh.finfo[:, 0] < 0) | (mesh.finfo[:, 1] < 0))
     if bfaces.size:
         fsel = bfaces[rng.integers(0, bfaces.size, size=k)]
         tri = mesh.pos[mesh.facets[fsel, :3]]
