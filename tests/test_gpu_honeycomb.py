@@ -1,9 +1,8 @@
 """BASELINE config 4 code path on a genuinely polyhedral mesh (hexagonal prisms, zigzag side walls): device mesh builder,
 BVH location and the filtered advection against the oracle, through the C ABI.
 
-Written at the end of round 1 after the GPU budget of the round was spent: the CPU side of this case (decomposition,
-topology, oracle tracking, filter model) is covered by tests/test_oracle_cpu.py and tests/test_filter_soundness_cpu.py;
-this file is the GPU half and runs last (file name) so that it cannot mask any other result."""
+The CPU side of this case (decomposition, topology, oracle tracking, filter model) is covered by
+tests/test_oracle_cpu.py and tests/test_filter_soundness_cpu.py; this file is the GPU half."""
 import numpy as np
 import pytest
 
