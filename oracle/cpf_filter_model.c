@@ -86,9 +86,11 @@ double orc_filter_build(long nTets, MESH_ARGS, void *recsOut)
 
 /* One sub-step walk of every particle: out[i] = final tet if every visit was certified, -1 if the filter refused
  * (guard band, wall, no exit, visit cap); visits[i] = tets visited.  errScale scales the rounding-error term of the
- * guard (1 = the product's; 0 with guard = 0 switches the band off, for the test that shows what it is there for). */
+ * guard (1 = the product's; 0 with guard = 0 switches the band off, for the test that shows what it is there for).
+ * skipC1First (may be NULL): per particle, drop the C1 test on the FIRST visit -- a relaxation under study for sub-steps
+ * whose start point was certified as the end point of the previous sub-step. */
 void orc_filter_walk(long n, const double *p, const double *disp, const int *tet, const void *recsIn, const double *pos,
-                     double guard, double errScale, int *out, int *visits)
+                     double guard, double errScale, const unsigned char *skipC1First, int *out, int *visits)
 {
     const fm_rec *recs = (const fm_rec *)recsIn;
     const float INF = INFINITY, G = (float)guard * 1.0000002f, ES = (float)errScale * 3.814697265625e-6f;
@@ -126,6 +128,7 @@ void orc_filter_walk(long n, const double *p, const double *disp, const int *tet
                 eam = fminf(eam, fabsf(e[j]));
                 emin = fminf(emin, e[j]);
             }
+            if (it == 0 && skipC1First && skipC1First[i]) c1m = INF;
             if (!(fminf(c1m, eam) >= g) || !(V > 1e-30f)) break;          /* refuse */
             if (emin > 0.f) { result = cur; break; }                        /* done */
             float t = INF;

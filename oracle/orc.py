@@ -192,14 +192,16 @@ class FilterModel:
         g = 1e-11 / self.hmin
         self.guard = g if g > 1e-7 else 1e-7
 
-    def walk(self, p4: np.ndarray, disp4: np.ndarray, tet: np.ndarray, *, guard=None, err_scale=1.0):
+    def walk(self, p4: np.ndarray, disp4: np.ndarray, tet: np.ndarray, *, guard=None, err_scale=1.0, skip_c1_first=None):
         """-> (final tet or -1 where the filter refused, visits)"""
         n = p4.shape[0]
         out = np.empty(n, dtype=np.int32)
         vis = np.empty(n, dtype=np.int32)
         lib().orc_filter_walk(C.c_long(n), _d(np.ascontiguousarray(p4)), _d(np.ascontiguousarray(disp4)),
                               _i(np.ascontiguousarray(tet, dtype=np.int32)), self.recs.ctypes.data_as(C.c_void_p), _d(self.mesh.pos),
-                              C.c_double(self.guard if guard is None else guard), C.c_double(err_scale), _i(out), _i(vis))
+                              C.c_double(self.guard if guard is None else guard), C.c_double(err_scale),
+                              None if skip_c1_first is None else np.ascontiguousarray(skip_c1_first, dtype=np.uint8).ctypes.data_as(C.POINTER(C.c_ubyte)),
+                              _i(out), _i(vis))
         return out, vis
 
     def substep(self, cl: "Cloud", disp4: np.ndarray, *, skip_replay=False) -> np.ndarray:
