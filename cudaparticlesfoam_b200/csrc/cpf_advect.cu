@@ -123,6 +123,7 @@ template <> struct Rng<CPF_RNG_PHILOX> {
 // exact sub-step tails (S3+S4+S5)
 // ------------------------------------------------------------------------------------------------
 struct Tally { unsigned hops, exact, refl, esc; };
+CPF_DEV double4 vel4(D3 u) { return make_double4(u.x, u.y, u.z, -1.0); }
 
 // Default build: convex line walk + reflector.  The reference's reflector re-walks the segment
 // from the start tet with bit-identical arithmetic (ConvexQuery.cu:343-397 vs :165-200), so the
@@ -259,8 +260,7 @@ CPF_TAIL void tail_bary_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &t
 template <int RNG>
 CPF_DEV D3 displacement(const MeshView &m, const StepParams &sp, Rng<RNG> &rng, int s, int cell, const D3 &P, D3 &vel)
 {
-    const double *uc = m.ucell + 3ll * cell;
-    vel = D3{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+    vel = ld_ucell(m, cell);
     D3 disp{ __dsub_rn(__fma_rn(sp.dt, vel.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, vel.y, P.y), P.y),
              __dsub_rn(__fma_rn(sp.dt, vel.z, P.z), P.z) };
     double x0, x1, x2;
@@ -472,8 +472,7 @@ CPF_DEV D3 velocity_at(const MeshView &m, int interp, int tet, D3 P)
 {
     if (interp == CPF_INTERP_VERTEX) return vertex_velocity_exact(m, tet, P);
     const int cell = tet_cell(m, tet, ld_int4(m.tetv, tet));
-    const double *uc = m.ucell + 3ll * cell;
-    return D3{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+    return ld_ucell(m, cell);
 }
 
 // tet of a stage point: the reference's segment walk from (from, tet); beyond a wall -> last tet
@@ -628,8 +627,16 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
         bool velValid = false;
         WalkF ws;
         int cell = -1, visits = 0; // cell: the cell whose velocity moved the particle in its latest sub-step
+        int org = -1;              // origin vertex id of `tet`
         bool needPro = true;
-        if (active && tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
+        if (active && tet >= 0) {
+            f32_load(m, tet, f);
+            org = first_origin<CPF_CFV_RUNTIME>(m, tet, f);
+            O = ld_vertex(m.vpos, org);
+            // C1, once per particle and launch, all lanes converged: the start point nothing in this kernel has certified
+            // (later sub-steps start where C2 certified the end point, later visits where C3 certified the exit point)
+            if (!start_point_clear(m, f, (float)(P.x - O.x), (float)(P.y - O.y), (float)(P.z - O.z))) { deferAt = s; active = false; }
+        }
         bool wallWait = false; // WALL: certified wall contact, waiting for the warp's next batched reflection
         while (__any_sync(0xffffffffu, active)) {
             if (WALL) {
@@ -639,14 +646,12 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                 const unsigned running = __ballot_sync(0xffffffffu, active && !wallWait);
                 if (wallWait && (__popc(waiting) >= CPF_WALL_BATCH || running == 0u)) {
                     wallWait = false;
-                    const double *uc = m.ucell + 3ll * cell;
-                    D3 Eref, u{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+                    D3 Eref, u = ld_ucell(m, cell);
                     if (KEEPV) u = vel;
                     if (wall_reflect_on_path(m, tet, ws.path, visits - 1, ws.cur, ws.wall_js, P, disp, Phit, Eref, u)) {
                         disp = Eref;
-                        const int js = ws.wall_js, wallTet = ws.cur;
-                        walkf_begin(ws, O, Phit, xsub(Eref, Phit), wallTet); // leg 1: from the hit point, same tet
-                        ws.in_j = js;
+                        const int wallTet = ws.cur;
+                        walkf_begin(ws, O, Phit, xsub(Eref, Phit), wallTet, ws.org, false); // leg 1: from the hit point (certified by C3), same tet
                         hops += visits;
                         visits = 0;
                         leg = 1;
@@ -663,15 +668,14 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
             if (active && !wallWait && needPro) {
                 if (tet < 0) active = false; // S1: left the domain -> frozen (particles.cu:334-338), w := 0 below
                 else {
-                    cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
-                    const double *uc = m.ucell + 3ll * cell;
+                    cell = m.tetcell ? __ldg(m.tetcell + tet) : org - m.nPoints;
                     D3 u0;
                     if (VERT) u0 = vertex_velocity_exact(m, tet, P);
-                    else u0 = D3{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+                    else u0 = ld_ucell(m, cell);
                     if (INTEG) { // k1 = v(P, tet); first stage point P + dt/2 * k1 (RK2 midpoint and RK4 alike)
                         k1s = u0;
                         Pst = axpy3(__dmul_rn(0.5, sp.dt), k1s, P);
-                        walkf_begin(ws, O, P, xsub(Pst, P), tet);
+                        walkf_begin(ws, O, P, xsub(Pst, P), tet, org, false);
                         stage = 1;
                     } else {
                         if (VERT) vel = u0;
@@ -682,7 +686,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                             disp.y = __fma_rn((double)s_xi[(s * 3 + 1) * 128 + threadIdx.x], sp.randDisp, disp.y);
                             disp.z = __fma_rn((double)s_xi[(s * 3 + 2) * 128 + threadIdx.x], sp.randDisp, disp.z);
                         }
-                        walkf_begin(ws, O, P, disp, tet);
+                        walkf_begin(ws, O, P, disp, tet, org, false);
                     }
                     visits = 0;
                     leg = 0;
@@ -691,7 +695,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
             }
             if (active && !wallWait) {
                 ++visits;
-                const int oc = visit_fast32(m, f, O, (WALL && leg) ? Phit : P, ws);
+                const int oc = visit_fast32<false, CPF_CFV_RUNTIME>(m, f, O, (WALL && leg) ? Phit : P, ws);
                 if (INTEG && stage > 0 && (oc == CPF_V_DONE || oc == CPF_V_WALL)) {
                     // the stage point lies in ws.cur (or beyond a certified wall face of it): take that cell's velocity
                     hops += visits;
@@ -699,14 +703,12 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                     D3 kx;
                     if (VERT) kx = vertex_velocity_exact(m, ws.cur, Pst);
                     else {
-                        const int scell = m.tetcell ? __ldg(m.tetcell + ws.cur) : f.origin - m.nPoints;
-                        const double *uc = m.ucell + 3ll * scell;
-                        kx = D3{ __ldg(uc), __ldg(uc + 1), __ldg(uc + 2) };
+                        const int scell = m.tetcell ? __ldg(m.tetcell + ws.cur) : ws.org - m.nPoints;
+                        kx = ld_ucell(m, scell);
                     }
                     if (ws.cur != tet) { // every walk of a sub-step starts from (P, tet)
-                        const int stageOrigin = f.origin;
                         f32_load(m, tet, f);
-                        if (f.origin != stageOrigin) O = ld_vertex(m.vpos, f.origin);
+                        if (ws.org != org) O = ld_vertex(m.vpos, org);
                     }
                     bool last = true;
                     if (INTEG == CPF_RK2) vel = kx;
@@ -725,15 +727,16 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                             disp.y = __fma_rn((double)s_xi[(s * 3 + 1) * 128 + threadIdx.x], sp.randDisp, disp.y);
                             disp.z = __fma_rn((double)s_xi[(s * 3 + 2) * 128 + threadIdx.x], sp.randDisp, disp.z);
                         }
-                        walkf_begin(ws, O, P, disp, tet);
+                        walkf_begin(ws, O, P, disp, tet, org, false);
                         stage = 0;
                     } else {
-                        walkf_begin(ws, O, P, xsub(Pst, P), tet);
+                        walkf_begin(ws, O, P, xsub(Pst, P), tet, org, false);
                         ++stage;
                     }
                 } else if (oc == CPF_V_DONE) {
                     velValid = true;
                     tet = ws.cur;
+                    org = ws.org;
                     if (WALL && leg) { P = xadd(Phit, xsub(disp, Phit)); refl++; } // p = P_hit (S4) then p += E - P_hit (S5)
                     else P = xadd(P, disp);
                     hops += visits;
@@ -759,8 +762,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
             if (KEEPV) {
                 if (sp.writeVel && velValid && deferAt < 0) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
             } else if (sp.writeVel && cell >= 0 && deferAt < 0 && !velDone) {
-                const double *uc = m.ucell + 3ll * cell;
-                st_stream4(pv.vel + i, make_double4(__ldg(uc), __ldg(uc + 1), __ldg(uc + 2), -1.0));
+                st_stream4(pv.vel + i, vel4(ld_ucell(m, cell)));
             }
         }
         // deferral queue: one atomic per warp
@@ -775,6 +777,122 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
         if (!QMODE) break;
     }
     flush_counters(sp, refl, 0u, hops, nsteps);
+}
+
+// k_lean<RNG,CFV>: the all-particles pass of the filtered policy for the reference's own configuration (Euler, cell
+// value) -- k_fast<RNG,0,0,EULER,0> with the per-visit and per-sub-step instruction count cut down, because this is
+// the kernel the step time is made of and it is bound by instruction issue, not by memory:
+//   * thread i = particle i, no queue input, no wall handling, no stage walks: a lane is in one of three modes
+//     (0 = sub-step prologue due, 1 = walking, 2 = finished or deferred), one register;
+//   * C1 once per particle (start_point_clear, all lanes converged), never inside the loop (visit_fast32<false>);
+//   * the cell velocity of the NEXT sub-step is fetched where the final tet of a sub-step becomes known, so the
+//     load is in flight while the other lanes of the warp run their exit-face section;
+//   * CFV (cell id = origin vertex id - nPoints, every OpenFOAM decomposition) is a template parameter.
+#ifndef CPF_LEAN_THREADS
+#define CPF_LEAN_THREADS 128
+#endif
+#ifndef CPF_LEAN_SMEM_STATE
+#define CPF_LEAN_SMEM_STATE 0 /* 1: displacement and activity flag of a lane live in shared memory instead of 8 registers */
+#endif
+#define CPF_LEAN_SMEM_BYTES(nSub, rngOn) ((size_t)CPF_LEAN_THREADS * ((rngOn ? sizeof(float) * 3 * (size_t)(nSub) : 0) + (CPF_LEAN_SMEM_STATE ? 32 : 0)))
+template <int RNG, bool CFV>
+__global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / CPF_LEAN_THREADS) k_lean(const MeshView m, const ParticleView pv, const StepParams sp)
+{
+    constexpr int NT = CPF_LEAN_THREADS;
+    extern __shared__ double s_dyn[];
+    // [disp x | disp y | disp z | w] per thread (CPF_LEAN_SMEM_STATE), then the deviates [sub-step][component][thread]
+    double *sd = s_dyn + threadIdx.x;
+    float *xi = reinterpret_cast<float *>(s_dyn + (CPF_LEAN_SMEM_STATE ? 4 * NT : 0)) + threadIdx.x;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool have = i < pv.n;
+    double4 p4 = make_double4(0.0, 0.0, 0.0, 0.0);
+    int tet = -1;
+    if (have) { p4 = ld_stream4(pv.pos + i); tet = ld_stream_i(pv.tet + i); }
+    D3 P{ p4.x, p4.y, p4.z };
+    double w = p4.w;
+    const bool live = have && (w != 0.0);
+    if (RNG != CPF_RNG_NONE) {
+        Rng<RNG> rng;
+        if (live) rng.open(pv, i, sp);
+        for (int q = 0; q < sp.nSub; ++q) {
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+            if (live) rng.draw(q, x0, x1, x2);
+            xi[(q * 3 + 0) * NT] = (float)x0;
+            xi[(q * 3 + 1) * NT] = (float)x1;
+            xi[(q * 3 + 2) * NT] = (float)x2;
+        }
+    }
+    Fast32 f;
+    D3 O{ 0.0, 0.0, 0.0 }, disp{ 0.0, 0.0, 0.0 }, u0{ 0.0, 0.0, 0.0 };
+    int deferAt = -1, s = 0, mode = 2, cell = -1, visits = 0, org = -1;
+    unsigned hops = 0;
+    constexpr int CF = CFV ? CPF_CFV_YES : CPF_CFV_NO;
+    auto fetch_velocity = [&]() {
+        cell = CFV ? org - m.nPoints : __ldg(m.tetcell + tet);
+        u0 = ld_ucell(m, cell);
+    };
+    if (live) {
+        if (tet < 0) w = 0.0; // S1: left the domain -> frozen (particles.cu:334-338)
+        else {
+            f32_load(m, tet, f);
+            org = first_origin<CF>(m, tet, f);
+            O = ld_vertex(m.vpos, org);
+            if (start_point_clear(m, f, (float)(P.x - O.x), (float)(P.y - O.y), (float)(P.z - O.z))) mode = 0;
+            else deferAt = 0;
+        }
+    }
+    if (CPF_LEAN_SMEM_STATE) sd[3 * NT] = w;
+    WalkF ws;
+    while (__any_sync(0xffffffffu, mode != 2)) {
+        if (mode == 0) {
+            fetch_velocity();
+            disp = D3{ __dsub_rn(__fma_rn(sp.dt, u0.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, u0.y, P.y), P.y),
+                       __dsub_rn(__fma_rn(sp.dt, u0.z, P.z), P.z) };
+            if (RNG != CPF_RNG_NONE) {
+                const float *x = xi + s * (3 * NT);
+                disp.x = __fma_rn((double)x[0], sp.randDisp, disp.x);
+                disp.y = __fma_rn((double)x[NT], sp.randDisp, disp.y);
+                disp.z = __fma_rn((double)x[2 * NT], sp.randDisp, disp.z);
+            }
+            walkf_begin(ws, O, P, disp, tet, org, false);
+            if (CPF_LEAN_SMEM_STATE) { sd[0] = disp.x; sd[NT] = disp.y; sd[2 * NT] = disp.z; }
+            visits = 0;
+            mode = 1;
+        }
+        if (mode == 1) {
+            ++visits;
+            const int oc = visit_fast32<false, CF>(m, f, O, P, ws);
+            if (oc == CPF_V_DONE) {
+                tet = ws.cur;
+                org = ws.org;
+                if (CPF_LEAN_SMEM_STATE) P = xadd(P, D3{ sd[0], sd[NT], sd[2 * NT] });
+                else P = xadd(P, disp);
+                hops += (unsigned)visits;
+                mode = (++s >= sp.nSub) ? 2 : 0;
+            } else if (oc != CPF_V_HOP || visits >= 48) {
+                hops += (unsigned)visits;
+                deferAt = s;
+                mode = 2;
+            }
+        }
+    }
+    if (live) {
+        if (CPF_LEAN_SMEM_STATE) w = sd[3 * NT];
+        st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
+        st_stream_i(pv.tet + i, tet);
+        if (sp.writeVel && cell >= 0 && deferAt < 0) {
+            st_stream4(pv.vel + i, vel4(ld_ucell(m, cell)));
+        }
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, deferAt >= 0); // deferral queue: one atomic per warp
+    if (mask) {
+        const int lane = threadIdx.x & 31;
+        int qb = 0;
+        if (lane == 0) qb = (int)atomicAdd(sp.countOut, (unsigned)__popc(mask));
+        qb = __shfl_sync(0xffffffffu, qb, 0);
+        if (deferAt >= 0) sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
+    }
+    flush_counters(sp, 0u, 0u, hops, (unsigned)s);
 }
 
 // k_fast_inline<RNG,QMODE>: same fast walk with the exact tail inline.  QMODE 0 (thread i = particle
@@ -801,22 +919,23 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_fast_inline(const MeshV
         Fast32 f;
         D3 O{ 0.0, 0.0, 0.0 }, vel{ 0.0, 0.0, 0.0 };
         bool velValid = false;
-        if (tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
+        int org = -1;
+        if (tet >= 0) { f32_load(m, tet, f); org = first_origin<CPF_CFV_RUNTIME>(m, tet, f); O = ld_vertex(m.vpos, org); }
         for (int s = s0; s < sp.nSub; ++s) {
             if (w == 0.0) break;
             if (tet < 0) { w = 0.0; break; }
-            const int cell = m.tetcell ? __ldg(m.tetcell + tet) : f.origin - m.nPoints;
+            const int cell = m.tetcell ? __ldg(m.tetcell + tet) : org - m.nPoints;
             const D3 disp = displacement<RNG>(m, sp, rng, s, cell, P, vel);
             velValid = true;
             nsteps++;
-            const int r = walk_fast32(m, f, O, tet, P, disp, ty.hops);
+            const int r = walk_fast32(m, f, O, org, tet, P, disp, ty.hops);
             if (r >= 0) {
                 tet = r;
                 P = xadd(P, disp);
             } else {
                 ty.exact++;
                 tail_convex_exact(m, P, disp, vel, tet, w, sp.reflect, ty);
-                if (tet >= 0) { f32_load(m, tet, f); O = ld_vertex(m.vpos, f.origin); }
+                if (tet >= 0) { f32_load(m, tet, f); org = first_origin<CPF_CFV_RUNTIME>(m, tet, f); O = ld_vertex(m.vpos, org); }
             }
         }
         rng.close(pv, i);
@@ -830,7 +949,7 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_fast_inline(const MeshV
 // Point values from the cell field (OpenFOAM volPointInterpolation, interior weights 1/|p - C|),
 // then uvert = [point values..., cell values...] for the vertex (cellPoint-style) interpolation.
 __global__ void k_point_interp(int nPoints, int nCells, const int *__restrict__ off, const int *__restrict__ cells,
-                               const double4 *__restrict__ vpos, const double *__restrict__ ucell, double *__restrict__ uvert)
+                               const double4 *__restrict__ vpos, const double4 *__restrict__ ucell, double *__restrict__ uvert)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nPoints) {
@@ -841,16 +960,18 @@ __global__ void k_point_interp(int nPoints, int nCells, const int *__restrict__ 
             const D3 d = xsub(P, ld_vertex(vpos, nPoints + c));
             const double wgt = __drcp_rn(__dsqrt_rn(__fma_rn(d.z, d.z, __fma_rn(d.y, d.y, __dmul_rn(d.x, d.x)))));
             sumw = __dadd_rn(sumw, wgt);
-            ax = __fma_rn(wgt, ucell[3ll * c], ax);
-            ay = __fma_rn(wgt, ucell[3ll * c + 1], ay);
-            az = __fma_rn(wgt, ucell[3ll * c + 2], az);
+            const double4 uc = ucell[c];
+            ax = __fma_rn(wgt, uc.x, ax);
+            ay = __fma_rn(wgt, uc.y, ay);
+            az = __fma_rn(wgt, uc.z, az);
         }
         uvert[3ll * i] = __ddiv_rn(ax, sumw);
         uvert[3ll * i + 1] = __ddiv_rn(ay, sumw);
         uvert[3ll * i + 2] = __ddiv_rn(az, sumw);
     } else if (i < nPoints + nCells) {
         const int c = i - nPoints;
-        uvert[3ll * i] = ucell[3ll * c]; uvert[3ll * i + 1] = ucell[3ll * c + 1]; uvert[3ll * i + 2] = ucell[3ll * c + 2];
+        const double4 uc = ucell[c];
+        uvert[3ll * i] = uc.x; uvert[3ll * i + 1] = uc.y; uvert[3ll * i + 2] = uc.z;
     }
 }
 
@@ -878,8 +999,7 @@ __global__ void __launch_bounds__(128) k_initial_advect(const MeshView m, const 
     if (tet < 0) { p4.w = 0.0; pv.pos[i] = p4; return; }
     const int4 v = ld_int4(m.tetv, tet);
     const int cell = tet_cell(m, tet, v);
-    const double *uc = m.ucell + 3ll * cell;
-    pv.vel[i] = make_double4(uc[0], uc[1], uc[2], -1.0);
+    pv.vel[i] = vel4(ld_ucell(m, cell));
 }
 
 __global__ void k_init_rng(curandState_t *st, long long n, unsigned long long seed)
@@ -937,8 +1057,16 @@ static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleVi
     };
     StepParams a = sp;
     a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
-    if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0, 0, I, V><<<grid, 128, xiBytes, st>>>(m, pv, a);
-    else k_fast<CPF_RNG_NONE, 0, 0, I, V><<<grid, 128, 0, st>>>(m, pv, a);
+    if constexpr (I == CPF_EULER && !V) {
+        const bool cfv = m.tetcell == nullptr;
+        const dim3 lgrid((unsigned)((pv.n + CPF_LEAN_THREADS - 1) / CPF_LEAN_THREADS));
+        const size_t lb = CPF_LEAN_SMEM_BYTES(nSub, rng == CPF_RNG_PHILOX);
+        if (rng == CPF_RNG_PHILOX) { if (cfv) k_lean<CPF_RNG_PHILOX, true><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a); else k_lean<CPF_RNG_PHILOX, false><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a); }
+        else { if (cfv) k_lean<CPF_RNG_NONE, true><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a); else k_lean<CPF_RNG_NONE, false><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a); }
+    } else {
+        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0, 0, I, V><<<grid, 128, xiBytes, st>>>(m, pv, a);
+        else k_fast<CPF_RNG_NONE, 0, 0, I, V><<<grid, 128, 0, st>>>(m, pv, a);
+    }
     ctx->launches++;
     int q = 0;
     if (CPF_WALL_PASS) fast_queue_pass(q++);
@@ -996,14 +1124,14 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
     }
     sp.integrator = ctx->cfg.integrator;
     sp.interp = ctx->cfg.interp;
-    const bool filteredOk = ctx->cfg.locator == CPF_LOCATOR_CONVEX && ctx->cfg.path == CPF_PATH_FILTERED && rng != CPF_RNG_XORWOW;
+    const bool filteredOk = ctx->cfg.locator == CPF_LOCATOR_CONVEX && ctx->cfg.path == CPF_PATH_FILTERED && ctx->filter_ok && rng != CPF_RNG_XORWOW;
     if ((ctx->cfg.interp != CPF_INTERP_TET || ctx->cfg.integrator != CPF_EULER) && !filteredOk) {
         CPF_RNG_SWITCH(rng, (k_general<R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
         ctx->launches++;
     } else if (ctx->cfg.locator == CPF_LOCATOR_BARY) {
         CPF_RNG_SWITCH(rng, (k_exact<CPF_LOCATOR_BARY, R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
         ctx->launches++;
-    } else if (ctx->cfg.path == CPF_PATH_EXACT) {
+    } else if (ctx->cfg.path == CPF_PATH_EXACT || !ctx->filter_ok) {
         CPF_RNG_SWITCH(rng, (k_exact_convex<R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
         ctx->launches++;
     } else if (rng == CPF_RNG_XORWOW) {

@@ -100,7 +100,7 @@ struct MeshView {
     const double4 *__restrict__ tetnrm; // [nTets][3] = 12 doubles: the four reference face normals (exact path)
     const uint16_t *__restrict__ tetcode;
     const int *__restrict__ tetcell;  // [nTets] or nullptr (cell = max vertex id - nPoints)
-    const double *__restrict__ ucell; // [nCells][3]
+    const double4 *__restrict__ ucell; // [nCells] (ux,uy,uz,0): one 256-bit load per velocity fetch
     const double *__restrict__ uvert; // [nVerts][3] (CPF_INTERP_VERTEX)
     const uint8_t *__restrict__ patch_kind; // [nPatches]
     int nPoints;
@@ -110,6 +110,7 @@ struct MeshView {
     float guardf; // the same, rounded up to fp32
 };
 
+CPF_DEV D3 ld_ucell(const MeshView &m, int cell) { return ld_vertex(m.ucell, cell); }
 CPF_DEV int link_at(int4 l, int j) { return j == 0 ? l.x : (j == 1 ? l.y : (j == 2 ? l.z : l.w)); }
 CPF_DEV int idx_at(int4 l, int j) { return link_at(l, j); }
 
@@ -252,9 +253,13 @@ CPF_DEV int sel4(int a, int b, int c, int d, int k)
 // One self-contained 64-byte record per tet: links, the un-normalised inward normals of the three
 // faces through the tet's highest-id vertex (the "origin": for OpenFOAM decompositions the cell
 // centre, so all 12 tets of a cell share it) -- computed in fp64 at build time, rounded once --,
-// the origin's vertex id, 6*volume and the largest |vertex offset| E (its sign bit flags records whose
+// an origin id (below), 6*volume and the largest |vertex offset| E (its sign bit flags records whose
 // slots 1 and 2 were exchanged to make the orientation positive).  A hop is ONE 64-byte load;
-// the fp64 origin position is fetched only when the walk enters another cell.  All predicates run
+// the fp64 origin position is fetched only when the walk enters another cell.  In a cell-centre
+// decomposition the origin changes exactly when the walk leaves through stored slot 3 (the face opposite
+// the centre), so the record carries the origin id of the tet BEHIND that face: the new origin's position
+// is requested together with the next record instead of after it (one dependent memory latency less per
+// cell change); the walk tracks its current origin id itself (WalkF::org, seeded from tetv[tet].w).  All predicates run
 // on the fp32 pipe.  Soundness: every comparison is made against g = G*|V6| + ERR, where
 // ERR = 2^-18 * E^2 * (E + 3(R+D)), R = |r|inf, D = |d|inf, bounds the distance between a computed plane
 // function and its real value.  With u = 2^-24, |N_c| <= 2E^2, V6 <= 6E^3, one rounding on each of N, r, d, V6:
@@ -268,7 +273,7 @@ CPF_DEV int sel4(int a, int b, int c, int d, int k)
 struct Fast32 {
     int4 link;
     float N[3][3];
-    int origin;
+    int aux; // cell-centre decompositions (MeshView::tetcell == nullptr): origin id of the tet BEHIND stored slot 3; else: own origin id
     float V6, E;
 };
 
@@ -285,10 +290,15 @@ CPF_DEV void f32_load(const MeshView &m, int tet, Fast32 &f)
     for (int k = 0; k < 3; ++k)
 #pragma unroll
         for (int c = 0; c < 3; ++c) f.N[k][c] = __uint_as_float(w[4 + 3 * k + c]);
-    f.origin = (int)w[13];
+    f.aux = (int)w[13];
     f.V6 = __uint_as_float(w[14]);
     f.E = __uint_as_float(w[15]);
 }
+
+#ifndef CPF_HOP_PREFETCH
+#define CPF_HOP_PREFETCH 0 /* measured: prefetch at the hop + load at the next visit is 2 % slower than loading at the hop */
+#endif
+CPF_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 CPF_DEV float rcp_ftz(float x)
 {
@@ -296,6 +306,16 @@ CPF_DEV float rcp_ftz(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+
+// Packed fp32 pairs (sm_100a FFMA2 / FADD2 / FMUL2): the plane functions come in pairs (a_j, b_j) = N_j . (r, d), so
+// one packed instruction serves the start-point and the direction term of a face; ptxas folds the {n, n} operand
+// into a scalar broadcast (R.F32).  Each half is an IEEE round-to-nearest operation like its scalar form.
+typedef unsigned long long F2;
+CPF_DEV F2 f2_pack(float lo, float hi) { F2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+CPF_DEV void f2_unpack(F2 v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+CPF_DEV F2 f2_mul(float n, F2 x) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(n, n)), "l"(x)); return r; }
+CPF_DEV F2 f2_fma(float n, F2 x, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(n, n)), "l"(x), "l"(c)); return r; }
+CPF_DEV F2 f2_sub(F2 a, F2 b) { F2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 // ------------------------------------------------------------------------------------------------
 // The walk, one tet visit at a time.  Lanes of a warp need different numbers of tet visits per
@@ -306,84 +326,163 @@ CPF_DEV float rcp_ftz(float x)
 // ------------------------------------------------------------------------------------------------
 struct WalkF {
     float rx, ry, rz, dx, dy, dz, RD3, Dd, t_in;
-    int in_j, cur;
+    int cur;
+    int org;                // origin vertex id of the tet `cur` (the record only names it for generic tet meshes)
+    bool c1;                // C1 still to be checked (first visit of a walk whose start point nothing has certified yet)
     int wall_js, wall_link; // set with CPF_V_WALL
     unsigned path;          // stored exit slot of every hop of this leg, 2 bits each (wall handling)
 };
 // CPF_V_WALL: every check passed and the certified exit face is a boundary face (callers without wall
 // handling treat it like a refusal: oc >= CPF_V_REFUSE)
 enum { CPF_V_DONE = 0, CPF_V_HOP = 1, CPF_V_REFUSE = 2, CPF_V_WALL = 3 };
+// how a kernel learns that the mesh is a cell-centre decomposition: compile time (k_lean) or from the mesh view
+enum { CPF_CFV_NO = 0, CPF_CFV_YES = 1, CPF_CFV_RUNTIME = 2 };
 
-CPF_DEV void walkf_begin(WalkF &ws, const D3 &O, const D3 &P0, const D3 &disp, int tet)
+template <int CFV> CPF_DEV bool mesh_is_cfv(const MeshView &m) { return CFV == CPF_CFV_RUNTIME ? (m.tetcell == nullptr) : (CFV == CPF_CFV_YES); }
+
+// origin id of tet `tet` whose record `f` has just been loaded from scratch (particle start, stage-walk restart)
+template <int CFV> CPF_DEV int first_origin(const MeshView &m, int tet, const Fast32 &f)
+{
+    return mesh_is_cfv<CFV>(m) ? __ldg(reinterpret_cast<const int *>(m.tetv) + 4ll * tet + 3) : f.aux;
+}
+
+// RD3 < 0 marks a start point that still has to be re-expressed relative to the origin just requested (the
+// subtraction is postponed to the next visit so that the warp does not wait for the position in the hop itself)
+CPF_DEV void walkf_rebase(WalkF &ws, const D3 &O, const D3 &P0)
 {
     ws.rx = (float)(P0.x - O.x); ws.ry = (float)(P0.y - O.y); ws.rz = (float)(P0.z - O.z);
+    ws.RD3 = 3.f * (fmaxf(fmaxf(fabsf(ws.rx), fabsf(ws.ry)), fabsf(ws.rz)) + ws.Dd);
+}
+
+CPF_DEV void walkf_begin(WalkF &ws, const D3 &O, const D3 &P0, const D3 &disp, int tet, int org, bool c1)
+{
     ws.dx = (float)disp.x; ws.dy = (float)disp.y; ws.dz = (float)disp.z;
     ws.Dd = fmaxf(fmaxf(fabsf(ws.dx), fabsf(ws.dy)), fabsf(ws.dz));
-    ws.RD3 = 3.f * (fmaxf(fmaxf(fabsf(ws.rx), fabsf(ws.ry)), fabsf(ws.rz)) + ws.Dd);
+    walkf_rebase(ws, O, P0);
     ws.t_in = 0.f;
-    ws.in_j = -1;
+    ws.c1 = c1;
     ws.cur = tet;
+    ws.org = org;
     ws.path = 0u;
 }
 
+// C1 for a start point on its own (the all-particles pass checks it once per launch, with all lanes converged, before
+// the visit loop): every plane function of the start tet at r = P - O must clear g0 = G*V6 + 2^-18 E^2 (E + 3R) -- the
+// error of a_j does not involve the displacement.
+CPF_DEV bool start_point_clear(const MeshView &m, const Fast32 &f, float rx, float ry, float rz)
+{
+    const float (&N)[3][3] = f.N;
+    float a[4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a[j] = rx * N[j][0] + ry * N[j][1] + rz * N[j][2];
+    a[3] = f.V6 - a[0] - a[1] - a[2];
+    const float E = fabsf(f.E);
+    const float g0 = fmaf(m.guardf, f.V6, 3.814697265625e-6f * (E * E) * (E + 3.f * fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz))));
+    return fminf(fminf(a[0], a[1]), fminf(a[2], a[3])) >= g0;
+}
+
+// One tet visit.  Checks, all against g = G*V6 + ERR (header comment above):
+//   C1  start point of the walk clear of every face plane -- FIRST visit only and only while ws.c1 is set (DYN_C1).
+//       Entry points of later visits need no test of their own: they are the exit points C3 certified in the tet
+//       before, and on the shared face the barycentric coordinates w.r.t. its three vertices are the same in both
+//       tets.  Start points of later sub-steps are the end points C2 certified (P + disp in fp64 moves them by
+//       <= 2^-52 |P|, far inside the 0.34 ERR of slack as long as |P| < 5e8 h_min, checked at mesh build).
+//   C2  end point clear of every face plane; all e_j >= g: the walk ends here.
+//   C3  exit point clear of the three other faces (edges/vertices, ties of dT, a wrongly selected exit).
+// The entry face needs no special case: after C2 its e_j is certified positive (the plane function of the face a
+// segment came in through increases along the segment), so it is never an exit candidate.
+template <bool DYN_C1, int CFV>
 CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, WalkF &ws)
 {
     const float INF = __int_as_float(0x7f800000);
+#if CPF_HOP_PREFETCH
+    // Entered through a face in the visit before (t_in > 0): that visit only PREFETCHED this tet's record and, in another
+    // cell, the origin's position -- prefetches name no register, so the warp carries no scoreboard dependency through the
+    // loop tail and the other lanes' sub-step prologue, and the loads below hit L1.
+    if (ws.t_in > 0.f) {
+        f32_load(m, ws.cur, f);
+        if (mesh_is_cfv<CFV>(m)) {
+            if (ws.RD3 < 0.f) { O = ld_vertex(m.vpos, ws.org); walkf_rebase(ws, O, P0); }
+        } else if (f.aux != ws.org) { // generic tet mesh: the record names its own origin
+            ws.org = f.aux;
+            O = ld_vertex(m.vpos, f.aux);
+            walkf_rebase(ws, O, P0);
+        }
+    }
+#else
+    if (ws.RD3 < 0.f) walkf_rebase(ws, O, P0); // entered another cell in the hop before: its origin has arrived by now
+#endif
     const float (&N)[3][3] = f.N;
     const float V = f.V6;
     float a[4], b[4], e[4];
+    {
+        const F2 X = f2_pack(ws.rx, ws.dx), Y = f2_pack(ws.ry, ws.dy), Z = f2_pack(ws.rz, ws.dz);
+        F2 ab[4];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        a[j] = ws.rx * N[j][0] + ws.ry * N[j][1] + ws.rz * N[j][2];
-        b[j] = ws.dx * N[j][0] + ws.dy * N[j][1] + ws.dz * N[j][2];
+        for (int j = 0; j < 3; ++j) ab[j] = f2_fma(N[j][2], Z, f2_fma(N[j][1], Y, f2_mul(N[j][0], X)));
+        ab[3] = f2_sub(f2_sub(f2_sub(f2_pack(V, 0.f), ab[0]), ab[1]), ab[2]); // a_3 = V - a_0 - a_1 - a_2, b_3 = -(b_0 + b_1 + b_2)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f2_unpack(ab[j], a[j], b[j]);
     }
-    a[3] = V - a[0] - a[1] - a[2];
-    b[3] = -(b[0] + b[1] + b[2]);
     const float E = fabsf(f.E);
     const float g = fmaf(m.guardf, V, 3.814697265625e-6f * (E * E) * (E + ws.RD3));
-    // C1 (entry/start point vs the other faces), C2 (end point vs every face plane)
-    float c1m = INF, eam = INF, emin = INF;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        e[j] = a[j] + b[j];
-        const float c1 = (j == ws.in_j) ? INF : fmaf(ws.t_in, b[j], a[j]);
-        c1m = fminf(c1m, c1);
-        eam = fminf(eam, fabsf(e[j]));
-        emin = fminf(emin, e[j]);
+    for (int j = 0; j < 4; ++j) e[j] = a[j] + b[j];
+    if (DYN_C1 && ws.c1) {
+        ws.c1 = false;
+        if (!(fminf(fminf(a[0], a[1]), fminf(a[2], a[3])) >= g)) return CPF_V_REFUSE;
     }
-    if (!(fminf(c1m, eam) >= g) | !(V > 1e-30f)) return CPF_V_REFUSE;
-    if (emin > 0.f) return CPF_V_DONE;
-    // Exit face: smallest crossing parameter among the faces whose plane the end point is behind.
-    // (C1 passed and t_in <= 1, so e_j < 0 implies b_j < 0 and a_j >= g > 0: every t_j is positive, and
-    // positive floats order like their bit patterns -- the face index rides in the two lowest mantissa
-    // bits through one integer min.  A flushed denormal b_j gives t_j = +inf, which fails t <= 1 below.)
+    if (fminf(fminf(e[0], e[1]), fminf(e[2], e[3])) >= g) return CPF_V_DONE; // C2 and "inside" in one
+    if (!(fminf(fminf(fabsf(e[0]), fabsf(e[1])), fminf(fabsf(e[2]), fabsf(e[3]))) >= g)) return CPF_V_REFUSE;
+    // Exit face: smallest crossing parameter among the faces whose plane the end point is behind.  For those the
+    // start/entry point is certified in front (true a_j + t_in b_j >= G V6), so b_j < 0 and t_j > t_in >= 0: positive
+    // floats order like their bit patterns -- the face index rides in the two lowest mantissa bits through one
+    // integer min.  Anything else (flushed denormal b_j -> +inf, a rounding-negative a_j -> sign bit set) fails
+    // t_in < t <= 1 below.
     unsigned key = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const bool cand = (e[j] < 0.f) & (j != ws.in_j);
-        const float tj = cand ? a[j] * rcp_ftz(-b[j]) : INF;
+        const float tj = (e[j] < 0.f) ? a[j] * rcp_ftz(-b[j]) : INF;
         key = min(key, (__float_as_uint(tj) & ~3u) | (unsigned)j);
     }
     const int js = (int)(key & 3u);
     const float t = __uint_as_float(key & ~3u);
     // C3: the exit point must be clear of every other face (edges/vertices, ties of dT)
-    float c3m = INF;
+    float h[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) c3m = fminf(c3m, (j == js) ? INF : fmaf(t, b[j], a[j]));
+    for (int j = 0; j < 4; ++j) h[j] = (j == js) ? INF : fmaf(t, b[j], a[j]);
+    const float c3m = fminf(fminf(h[0], h[1]), fminf(h[2], h[3]));
     const int link = sel4(f.link.x, f.link.y, f.link.z, f.link.w, js);
     if (!((c3m >= g) && (t > ws.t_in) && (t <= 1.f))) return CPF_V_REFUSE; // incl. "no candidate" (t = inf)
     if (link < 0) { ws.wall_js = js; ws.wall_link = link; return CPF_V_WALL; }
     ws.cur = link >> 2;
-    ws.in_j = link & 3;
     ws.t_in = t;
     ws.path = (ws.path << 2) | (unsigned)js;
-    const int oldOrigin = f.origin;
-    f32_load(m, ws.cur, f);
-    if (f.origin != oldOrigin) { // entered another cell: re-express the start point
-        O = ld_vertex(m.vpos, f.origin);
-        ws.rx = (float)(P0.x - O.x); ws.ry = (float)(P0.y - O.y); ws.rz = (float)(P0.z - O.z);
-        ws.RD3 = 3.f * (fmaxf(fmaxf(fabsf(ws.rx), fabsf(ws.ry)), fabsf(ws.rz)) + ws.Dd);
+#if CPF_HOP_PREFETCH
+    prefetch_l1(m.tetfast + 4ll * ws.cur);
+    prefetch_l1(m.tetfast + 4ll * ws.cur + 2);
+    if (mesh_is_cfv<CFV>(m) && js == 3) { // through the face opposite the cell centre: another cell, whose origin id this record names
+        ws.org = f.aux;
+        prefetch_l1(m.vpos + f.aux);
+        ws.RD3 = -1.f;
     }
+#else
+    if (mesh_is_cfv<CFV>(m)) {
+        if (js == 3) { // through the face opposite the cell centre: another cell, whose origin id this record already names
+            ws.org = f.aux;
+            O = ld_vertex(m.vpos, f.aux);
+            ws.RD3 = -1.f;
+        }
+        f32_load(m, ws.cur, f); // after the last use of the old record: the new words land in their loop-carried registers
+    } else {
+        f32_load(m, ws.cur, f);
+        if (f.aux != ws.org) { // generic tet mesh: the record names its own origin
+            ws.org = f.aux;
+            O = ld_vertex(m.vpos, f.aux);
+            walkf_rebase(ws, O, P0);
+        }
+    }
+#endif
     return CPF_V_HOP;
 }
 
@@ -445,14 +544,14 @@ CPF_DEV bool wall_reflect_on_path(const MeshView &m, int startTet, unsigned path
 
 // Whole walk of one sub-step (k_fast_inline).  Returns the final tet (f then holds its record, O its
 // origin) or CPF_NEED_EXACT.
-CPF_DEV int walk_fast32(const MeshView &m, Fast32 &f, D3 &O, int tet0, D3 P0, D3 disp, unsigned &hops)
+CPF_DEV int walk_fast32(const MeshView &m, Fast32 &f, D3 &O, int &org, int tet0, D3 P0, D3 disp, unsigned &hops)
 {
     WalkF ws;
-    walkf_begin(ws, O, P0, disp, tet0);
+    walkf_begin(ws, O, P0, disp, tet0, org, true);
     for (int it = 0; it < 48; ++it) {
         hops++;
-        const int oc = visit_fast32(m, f, O, P0, ws);
-        if (oc == CPF_V_DONE) return ws.cur;
+        const int oc = visit_fast32<true, CPF_CFV_RUNTIME>(m, f, O, P0, ws);
+        if (oc == CPF_V_DONE) { org = ws.org; return ws.cur; }
         if (oc >= CPF_V_REFUSE) break;
     }
     return CPF_NEED_EXACT;

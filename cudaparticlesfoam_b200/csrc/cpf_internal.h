@@ -71,12 +71,14 @@ struct cpf_context {
     int4 *d_tetrec = nullptr;    // [nTets][2]: {links, apex vertex id of the neighbour across each face}
     uint16_t *d_tetcode = nullptr;
     int *d_tetcell = nullptr;
-    double *d_ucell[2] = { nullptr, nullptr }; // double-buffered cell field, solver layout [nCells][3]
+    double4 *d_ucell[2] = { nullptr, nullptr }; // double-buffered cell field, (ux,uy,uz,0) per cell
+    double *d_ustage = nullptr;                 // host uploads land here in the solver's layout [nCells][3] and are repacked
     int ucur = 0;
     double *d_uvert = nullptr;
     int *d_pc_off = nullptr, *d_pc_cells = nullptr; // point -> cells CSR (vertex interpolation from the cell field)
     uint8_t *d_patch_kind = nullptr;
     double guard = 1e-7, hmin = 0.0;
+    bool filter_ok = true; // coordinates small enough against the smallest tet for the filtered walk (cpf_mesh.cu)
     double bbox_lo[3] = { 0, 0, 0 }, bbox_hi[3] = { 0, 0, 0 };
     double *h_pinned = nullptr;
     size_t pinned_bytes = 0;

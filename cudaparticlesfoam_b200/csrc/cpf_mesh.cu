@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cmath>
+
 #include "cpf_internal.h"
 
 namespace cpf {
@@ -170,7 +172,7 @@ CPF_DEV double sorted_v6(const int4 v, const double4 *__restrict__ vpos)
 }
 
 __global__ void k_build_fast(long long nTets, const int4 *__restrict__ tetv, const double4 *__restrict__ vpos,
-                             const int4 *__restrict__ tetrec, uint4 *__restrict__ out)
+                             const int4 *__restrict__ tetrec, uint4 *__restrict__ out, int cellCentreMesh)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nTets) return;
@@ -214,7 +216,11 @@ __global__ void k_build_fast(long long nTets, const int4 *__restrict__ tetv, con
     o[0] = make_uint4((unsigned)lk[0], (unsigned)lk[1], (unsigned)lk[2], (unsigned)lk[3]);
     o[1] = make_uint4(__float_as_uint(Nf[0][0]), __float_as_uint(Nf[0][1]), __float_as_uint(Nf[0][2]), __float_as_uint(Nf[1][0]));
     o[2] = make_uint4(__float_as_uint(Nf[1][1]), __float_as_uint(Nf[1][2]), __float_as_uint(Nf[2][0]), __float_as_uint(Nf[2][1]));
-    o[3] = make_uint4(__float_as_uint(Nf[2][2]), (unsigned)v.w, __float_as_uint((float)fabs(v6)), __float_as_uint(E));
+    // word 13 (Fast32::aux): cell-centre decomposition -> origin id of the tet behind stored slot 3 (the face opposite the
+    // centre: the only way into another cell); generic tet mesh -> this tet's own origin id
+    int aux = v.w;
+    if (cellCentreMesh && lk[3] >= 0) aux = tetv[lk[3] >> 2].w;
+    o[3] = make_uint4(__float_as_uint(Nf[2][2]), (unsigned)aux, __float_as_uint((float)fabs(v6)), __float_as_uint(E));
 }
 
 // reference face normals, once per (tet, sorted face): see face_normal_exact
@@ -254,7 +260,7 @@ int fail(cpf_context *ctx, int code, const char *fmt, ...)
 static void free_mesh(cpf_context *ctx)
 {
     cudaFree(ctx->d_vpos); cudaFree(ctx->d_tetv); cudaFree(ctx->d_tetrec); cudaFree(ctx->d_tetfast); cudaFree(ctx->d_tetnrm); cudaFree(ctx->d_tetcode); cudaFree(ctx->d_tetcell);
-    cudaFree(ctx->d_ucell[0]); cudaFree(ctx->d_ucell[1]); cudaFree(ctx->d_uvert); cudaFree(ctx->d_patch_kind); cudaFree(ctx->d_pc_off); cudaFree(ctx->d_pc_cells);
+    cudaFree(ctx->d_ucell[0]); cudaFree(ctx->d_ucell[1]); cudaFree(ctx->d_ustage); ctx->d_ustage = nullptr; cudaFree(ctx->d_uvert); cudaFree(ctx->d_patch_kind); cudaFree(ctx->d_pc_off); cudaFree(ctx->d_pc_cells);
     ctx->d_vpos = nullptr; ctx->d_tetv = nullptr; ctx->d_tetrec = nullptr; ctx->d_tetfast = nullptr; ctx->d_tetnrm = nullptr; ctx->d_tetcode = nullptr; ctx->d_tetcell = nullptr;
     ctx->d_ucell[0] = ctx->d_ucell[1] = nullptr; ctx->d_uvert = nullptr; ctx->d_patch_kind = nullptr; ctx->d_pc_off = ctx->d_pc_cells = nullptr;
     free_bvh(ctx);
@@ -302,8 +308,8 @@ static int build_device_mesh_impl(cpf_context *ctx, long long nVerts, const doub
     CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetrec, sizeof(int4) * 2 * (size_t)nTets));
     CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetcode, sizeof(uint16_t) * (size_t)nTets));
     for (int b = 0; b < 2; ++b) {
-        CPF_CUDA(ctx, cudaMalloc(&ctx->d_ucell[b], sizeof(double) * 3 * (size_t)nCells));
-        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_ucell[b], 0, sizeof(double) * 3 * (size_t)nCells, st));
+        CPF_CUDA(ctx, cudaMalloc(&ctx->d_ucell[b], sizeof(double4) * (size_t)nCells));
+        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_ucell[b], 0, sizeof(double4) * (size_t)nCells, st));
     }
     ctx->ucur = 0;
     k_pack_positions<<<(unsigned)((nVerts + 255) / 256), 256, 0, st>>>(nVerts, d_xyz, ctx->d_vpos);
@@ -354,7 +360,7 @@ static int build_device_mesh_impl(cpf_context *ctx, long long nVerts, const doub
     k_build_normals<<<(unsigned)((nTets + 127) / 128), 128, 0, st>>>(nTets, ctx->d_tetv, ctx->d_vpos, ctx->d_tetcode, (double *)ctx->d_tetnrm);
     ctx->launches++;
     CPF_CUDA(ctx, cudaMalloc(&ctx->d_tetfast, sizeof(uint4) * 4 * (size_t)nTets));
-    k_build_fast<<<(unsigned)((nTets + 127) / 128), 128, 0, st>>>(nTets, ctx->d_tetv, ctx->d_vpos, ctx->d_tetrec, ctx->d_tetfast);
+    k_build_fast<<<(unsigned)((nTets + 127) / 128), 128, 0, st>>>(nTets, ctx->d_tetv, ctx->d_vpos, ctx->d_tetrec, ctx->d_tetfast, ctx->cellFromVertex ? 1 : 0);
     ctx->launches++;
     CPF_CUDA(ctx, cudaGetLastError());
 
@@ -372,6 +378,13 @@ static int build_device_mesh_impl(cpf_context *ctx, long long nVerts, const doub
     // 1e-13 tolerance measured against the smallest tet height, never below 1e-7
     const double g = 1e-11 / hmin;
     ctx->guard = g > 1e-7 ? g : 1e-7;
+    // The filtered walk checks the start point of a particle once per launch and afterwards relies on "the end point C2
+    // certified is the next start point" (cpf_geom.cuh visit_fast32): P + disp in fp64 moves that point by <= 2^-52 |P|,
+    // which must stay inside the unused part of the error term (0.34 * 2^-18 E^3 against 12 E^2 |P| 2^-53): |P| < 9e8 E.
+    // A mesh whose coordinates exceed 5e8 smallest tet heights (7 decimal digits left inside a tet) runs on the exact path.
+    double amax = 0.0;
+    for (int k = 0; k < 3; ++k) amax = std::max(amax, std::max(std::fabs(ctx->bbox_lo[k]), std::fabs(ctx->bbox_hi[k])));
+    ctx->filter_ok = amax <= 5e8 * hmin;
     ctx->have_mesh = true;
     return build_bvh(ctx);
 }

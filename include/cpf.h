@@ -126,10 +126,11 @@ int cpf_mesh_download_neighbours(cpf_context *ctx, int *nbr /*[nTets][4]*/);
 /* -- flow field ----------------------------------------------------------------------------- */
 /* Replaces the host 12x expansion + cudaUpdateVelocity of src/advect.H:44-57 and
  * cuda/particles.cu:733-749.  U is the solver's cell field [nCells][3] (fp64).  on_device != 0:
- * U is a device pointer (e.g. the NCCL broadcast buffer) and is consumed in place on the
- * library's stream.  on_device == 0: U is host memory; the upload goes to the idle half of a
- * double buffer on a copy stream, so it overlaps sub-steps that are still running, and the
- * sub-steps enqueued afterwards wait for it.  Page-locked host memory is read asynchronously:
+ * U is a device pointer (e.g. the NCCL broadcast buffer); one kernel on the library's stream
+ * repacks it into the idle half of the library's double buffer ((ux,uy,uz,0) per cell), after
+ * which (in stream order) the caller's buffer may be overwritten.  on_device == 0: U is host
+ * memory; upload and repack run on a copy stream, so they overlap sub-steps that are still
+ * running, and the sub-steps enqueued afterwards wait for them.  Page-locked host memory is read asynchronously:
  * keep it unchanged until the next synchronising call (cpf_sync, cpf_stats_get, cpf_download). */
 int cpf_update_velocity(cpf_context *ctx, const double *U, int on_device);
 /* CPF_INTERP_VERTEX: explicit per-vertex field [nVerts][3] (points then centres); if never
@@ -198,7 +199,8 @@ int cpf_checkpoint_save(cpf_context *ctx, const char *path);
 unsigned long long cpf_step_index(cpf_context *ctx);
 int cpf_checkpoint_load(cpf_context *ctx, const char *path);
 long long cpf_num_particles(cpf_context *ctx);
-/* raw device pointers (for torch / NCCL plumbing); valid until the next set/seed/sort call */
+/* raw device pointers (for torch / NCCL plumbing); valid until the next set/seed/sort call;
+ * ucell is the library's current field buffer, (ux,uy,uz,0) per cell */
 int cpf_device_pointers(cpf_context *ctx, void **pos4, void **tet, void **ucell);
 /* parity tooling: the normal deviates the next sub-step will use, [n][3], original order;
  * does not advance the stream */

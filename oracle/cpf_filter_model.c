@@ -87,8 +87,8 @@ double orc_filter_build(long nTets, MESH_ARGS, void *recsOut)
 /* One sub-step walk of every particle: out[i] = final tet if every visit was certified, -1 if the filter refused
  * (guard band, wall, no exit, visit cap); visits[i] = tets visited.  errScale scales the rounding-error term of the
  * guard (1 = the product's; 0 with guard = 0 switches the band off, for the test that shows what it is there for).
- * skipC1First (may be NULL): per particle, drop the C1 test on the FIRST visit -- a relaxation under study for sub-steps
- * whose start point was certified as the end point of the previous sub-step. */
+ * skipC1First (may be NULL): per particle, drop the C1 test of the first visit -- what the product does for every sub-step
+ * whose start point is the end point C2 certified in the sub-step before. */
 void orc_filter_walk(long n, const double *p, const double *disp, const int *tet, const void *recsIn, const double *pos,
                      double guard, double errScale, const unsigned char *skipC1First, int *out, int *visits)
 {
@@ -108,7 +108,7 @@ void orc_filter_walk(long n, const double *p, const double *disp, const int *tet
         const float Dd = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
         float RD3 = 3.f * (fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz)) + Dd);
         float t_in = 0.f;
-        int in_j = -1, result = -1;
+        int result = -1;
         for (int it = 0; it < 48; ++it) {
             visits[i]++;
             float a[4], b[4], e[4];
@@ -120,21 +120,25 @@ void orc_filter_walk(long n, const double *p, const double *disp, const int *tet
             a[3] = V - a[0] - a[1] - a[2];
             b[3] = -(b[0] + b[1] + b[2]);
             const float g = fmaf(G, V, ES * (E * E) * (E + RD3));
-            float c1m = INF, eam = INF, emin = INF;
+            float amin = INF, eam = INF, emin = INF;
             for (int j = 0; j < 4; ++j) {
                 e[j] = a[j] + b[j];
-                const float c1 = (j == in_j) ? INF : fmaf(t_in, b[j], a[j]);
-                c1m = fminf(c1m, c1);
+                amin = fminf(amin, a[j]);
                 eam = fminf(eam, fabsf(e[j]));
                 emin = fminf(emin, e[j]);
             }
-            if (it == 0 && skipC1First && skipC1First[i]) c1m = INF;
-            if (!(fminf(c1m, eam) >= g) || !(V > 1e-30f)) break;          /* refuse */
-            if (emin > 0.f) { result = cur; break; }                        /* done */
+            /* C1: the start point of the sub-step against every face, FIRST visit only (entry points of later visits are
+             * the exit points C3 certified in the tet before: same barycentric coordinates on the shared face) */
+            if (it == 0 && !(skipC1First && skipC1First[i])) { /* cpf_geom.cuh start_point_clear: the error of a_j does not involve d */
+                const float g0 = fmaf(G, V, ES * (E * E) * (E + 3.f * fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz))));
+                if (!(amin >= g0)) break;
+            }
+            if (emin >= g) { result = cur; break; }                         /* C2 + inside: done */
+            if (!(eam >= g)) break;                                         /* C2: refuse */
             float t = INF;
             int js = -1;
             for (int j = 0; j < 4; ++j) {
-                if (e[j] < 0.f && j != in_j) {
+                if (e[j] < 0.f) {
                     const float tj = a[j] * (1.0f / -b[j]);
                     if (tj < t) { t = tj; js = j; }
                 }
@@ -147,7 +151,6 @@ void orc_filter_walk(long n, const double *p, const double *disp, const int *tet
             const int link = f->link[js];
             if (link < 0) break;                                            /* wall: the exact path reflects */
             cur = link >> 2;
-            in_j = link & 3;
             t_in = t;
             const int oldOrigin = f->origin;
             f = recs + cur;
@@ -163,15 +166,15 @@ void orc_filter_walk(long n, const double *p, const double *disp, const int *tet
 
 
 /* ---- one whole sub-step as the wall-capable queue pass does it (k_fast<.., WALL = 1>, wall_reflect_on_path) ---------- */
-typedef struct { float rx, ry, rz, dx, dy, dz, RD3, Dd, t_in; int in_j, cur; } fm_walk;
+typedef struct { float rx, ry, rz, dx, dy, dz, RD3, Dd, t_in; int c1, cur; } fm_walk;
 
-static void fm_begin(fm_walk *w, const double *O, v3 P0, v3 d, int tet)
+static void fm_begin(fm_walk *w, const double *O, v3 P0, v3 d, int tet, int c1)
 {
     w->rx = (float)(P0.x - O[0]); w->ry = (float)(P0.y - O[1]); w->rz = (float)(P0.z - O[2]);
     w->dx = (float)d.x; w->dy = (float)d.y; w->dz = (float)d.z;
     w->Dd = fmaxf(fmaxf(fabsf(w->dx), fabsf(w->dy)), fabsf(w->dz));
     w->RD3 = 3.f * (fmaxf(fmaxf(fabsf(w->rx), fabsf(w->ry)), fabsf(w->rz)) + w->Dd);
-    w->t_in = 0.f; w->in_j = -1; w->cur = tet;
+    w->t_in = 0.f; w->c1 = c1; w->cur = tet;
 }
 
 enum { FM_DONE = 0, FM_HOP = 1, FM_REFUSE = 2, FM_WALL = 3 };
@@ -189,18 +192,22 @@ static int fm_visit(const fm_rec *recs, const double *pos, v3 P0, fm_walk *w, fl
     a[3] = V - a[0] - a[1] - a[2];
     b[3] = -(b[0] + b[1] + b[2]);
     const float g = fmaf(G, V, 3.814697265625e-6f * (E * E) * (E + w->RD3));
-    float c1m = INF, eam = INF, emin = INF;
+    float amin = INF, eam = INF, emin = INF;
     for (int j = 0; j < 4; ++j) {
         e[j] = a[j] + b[j];
-        const float c1 = (j == w->in_j) ? INF : fmaf(w->t_in, b[j], a[j]);
-        c1m = fminf(c1m, c1); eam = fminf(eam, fabsf(e[j])); emin = fminf(emin, e[j]);
+        amin = fminf(amin, a[j]); eam = fminf(eam, fabsf(e[j])); emin = fminf(emin, e[j]);
     }
-    if (!(fminf(c1m, eam) >= g) || !(V > 1e-30f)) return FM_REFUSE;
-    if (emin > 0.f) return FM_DONE;
+    if (w->c1) {
+        const float g0 = fmaf(G, V, 3.814697265625e-6f * (E * E) * (E + 3.f * fmaxf(fmaxf(fabsf(w->rx), fabsf(w->ry)), fabsf(w->rz))));
+        if (!(amin >= g0)) return FM_REFUSE;
+        w->c1 = 0;
+    }
+    if (emin >= g) return FM_DONE;
+    if (!(eam >= g)) return FM_REFUSE;
     float t = INF;
     int js = -1;
     for (int j = 0; j < 4; ++j)
-        if (e[j] < 0.f && j != w->in_j) {
+        if (e[j] < 0.f) {
             const float tj = a[j] * (1.0f / -b[j]);
             if (tj < t) { t = tj; js = j; }
         }
@@ -213,7 +220,7 @@ static int fm_visit(const fm_rec *recs, const double *pos, v3 P0, fm_walk *w, fl
     const int link = f->link[js];
     if (link < 0) return FM_WALL;
     const int oldOrigin = f->origin;
-    w->cur = link >> 2; w->in_j = link & 3; w->t_in = t;
+    w->cur = link >> 2; w->t_in = t;
     f = recs + w->cur;
     if (f->origin != oldOrigin) {
         const double *O = pos + 3 * (long)f->origin;
@@ -252,7 +259,7 @@ void orc_filter_substep(long n, double *p, const double *disp, double *vel, int 
         const v3 P = { p[4 * i], p[4 * i + 1], p[4 * i + 2] }, dsp = { disp[4 * i], disp[4 * i + 1], disp[4 * i + 2] };
         v3 u = { vel[4 * i], vel[4 * i + 1], vel[4 * i + 2] };
         fm_walk w;
-        fm_begin(&w, m.pos + 3 * (long)recs[tet[i]].origin, P, dsp, tet[i]);
+        fm_begin(&w, m.pos + 3 * (long)recs[tet[i]].origin, P, dsp, tet[i], 1);
         int pathTet[16], pathSlot[16], visits = 0, leg = 0, done = 0, refused = 0;
         v3 Phit = P, Eref = P;
         while (!done && !refused) {
@@ -282,8 +289,7 @@ void orc_filter_substep(long n, double *p, const double *disp, double *vel, int 
                 u.x = fma(sv, nrm.x, u.x); u.y = fma(sv, nrm.y, u.y); u.z = fma(sv, nrm.z, u.z);
                 Eref = E;
                 const int wallTet = w.cur;
-                fm_begin(&w, m.pos + 3 * (long)recs[wallTet].origin, Phit, v3_sub(Eref, Phit), wallTet);
-                w.in_j = js;
+                fm_begin(&w, m.pos + 3 * (long)recs[wallTet].origin, Phit, v3_sub(Eref, Phit), wallTet, 0); /* hit point: certified by C3 */
                 visits = 0;
                 leg = 1;
             } else refused = 1;
