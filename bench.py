@@ -1,18 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- particle-steps/s of the fused particle hot path on B200 (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--rng philox|xorwow|none]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one body of the reference's src/advect.H: velocity-field refresh + nCycles fused
-Lagrangian sub-steps over every particle of the rank.  Weak scaling: every rank tracks its own
-particles on a replicated mesh; with N > 1 the per-step velocity field is broadcast from rank 0 over
-NCCL and a statistics vector is reduced back.
+One "step" = one body of the reference's src/advect.H: velocity-field refresh + nCycles fused Lagrangian sub-steps over
+every particle of the rank.  Weak scaling: every rank tracks its own index range of one global cloud on a replicated
+mesh.  With N > 1 the data plane is the library's own (cpf_comm.cu: NCCL broadcast of the field, NCCL sum of the
+statistics slot, both behind the C ABI); torch.distributed (gloo) only carries the 128-byte NCCL id and the final
+max-over-ranks of the timings.
 
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput (U already in HBM), `e2e` =
-the same through the C ABI with the cell field coming from pinned host memory every step and a
-statistics read-back, `roofline` = the fused kernel against the measured HBM copy bandwidth,
-`cpu_baseline` = the oracle port on the host cores over a bounded sample.
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (U already in HBM), `e2e` = the same through the
+C ABI with the cell field coming from pinned host memory every step and a statistics read-back, `roofline` = the
+advect launch sequence against the measured HBM copy bandwidth, `cpu_baseline` = the oracle port on the host cores over
+a bounded sample, `extra` = the other workloads / configurations of BASELINE.json measured the same way (short runs).
 """
 from __future__ import annotations
 
@@ -31,17 +32,41 @@ sys.path.insert(0, ROOT)
 
 B_ALG = 72  # algorithmic bytes per particle-step (double4 position+flag and int32 tet id, read + written)
 
+_CH = dict(mesh="channel", dims=(400, 50, 50), jitter=0.1, n=10_000_000, dt=0.005, ncycles=10, D=1.5e-5, integrator="euler")
 WORKLOADS = {
-    # BASELINE.json configs[2] / north-star target: 1M-cell channel, 1e7 tracers, field refreshed every step
-    "channel1M_1e7": dict(mesh="channel", dims=(400, 50, 50), jitter=0.1, n=10_000_000, dt=0.005, ncycles=10, D=1.5e-5,
-                          field="channel", desc="channel 400x50x50 hex (1e6 cells, 12e6 tets), 1e7 tracers, Euler, cell-constant U "
-                          "refreshed every step, convex walk + specular walls, random walk D=1.5e-5, 10 sub-steps/step"),
+    # BASELINE.json configs[2] / north-star target: 1M-cell channel mesh, 1e7 tracers, field refreshed every step.
+    # Closed recirculating flow: statistically steady under the reference's all-reflecting walls (both arms run it).
+    "channel1M_1e7": dict(_CH, field="recirc",
+                          desc="channel mesh 400x50x50 hex (1e6 cells, 12e6 tets), 1e7 tracers, Euler, cell-constant U refreshed every "
+                               "step (closed recirculating flow: steady state), convex walk + specular walls, random walk D=1.5e-5, "
+                               "10 sub-steps/step"),
+    # round 1's workload: through-flow parks the cloud on the reflecting outlet (throughput drifts down over the run)
+    "channel1M_1e7_throughflow": dict(_CH, field="channel",
+                                      desc="as channel1M_1e7 with a Poiseuille through-flow and an all-reflecting outlet (not a steady state)"),
+    # through-flow with an ESCAPE outlet and continuous re-injection behind the inlet (features the reference lacks)
+    "channel1M_1e7_escape": dict(_CH, field="channel", escape=("x+",), reseed_every=5,
+                                 desc="as channel1M_1e7 with a Poiseuille through-flow, outlet patch ESCAPE, escaped tracers "
+                                      "re-seeded behind the inlet every 5 steps (steady state)"),
+    # BASELINE.json configs[4]: 1e8 particles, 1M cells, random walk, reflecting walls, outlet escape + compaction
+    "channel1M_1e8_escape": dict(_CH, field="channel", escape=("x+",), n=12_500_000, n_single=100_000_000,
+                                 desc="C5: channel 1e6 cells, 1e8 tracers over 8 GPUs (1.25e7 per GPU), through-flow, outlet patch "
+                                      "ESCAPE, escaped tracers compacted away by the counting sort"),
     # BASELINE.json configs[1]
     "box100_1e6": dict(mesh="box", dims=(100, 100, 100), jitter=0.1, n=1_000_000, dt=0.004, ncycles=10, D=0.0, field="vortex",
-                       desc="box 100^3 hex (1e6 cells), 1e6 tracers, frozen uniform+vortex field"),
+                       integrator="rk2", desc="C2: box 100^3 hex (1e6 cells), 1e6 tracers, RK2, frozen uniform+vortex field"),
+    # BASELINE.json configs[0]: pitzDaily stand-in, launch-latency regime (1e5 tracers; a step = one save interval of 10 sub-steps)
+    "pitz_1e5": dict(mesh="pitz", n=100_000, dt=1e-5, ncycles=10, D=5.7e-6, field="pitz", integrator="euler",
+                     desc="C1: pitzDaily-sized block (12 225 hex cells), 1e5 tracers, Euler, frozen flow, random walk, "
+                          "10 sub-steps (one save interval) per step"),
+    # BASELINE.json configs[3]: polyhedral mesh, RK4, 1e8 tracers over 8 GPUs
+    "poly10M_1e8_rk4": dict(mesh="honeycomb", dims=(232, 232, 186), n=12_500_000, dt=0.002, ncycles=10, D=0.0, field="vortex",
+                            integrator="rk4", desc="C4: honeycomb of hexagonal prisms, 1.0e7 polyhedral cells (2.0e8 tets), 1e8 tracers "
+                                                   "over 8 GPUs (1.25e7 per GPU), RK4, frozen uniform+vortex field"),
+    "poly1M_rk4": dict(mesh="honeycomb", dims=(108, 108, 86), n=2_000_000, dt=0.002, ncycles=10, D=0.0, field="vortex",
+                       integrator="rk4", desc="honeycomb of hexagonal prisms, 1.0e6 polyhedral cells (2.0e7 tets), 2e6 tracers, RK4"),
     # small smoke-sized variant (CI / CPU-side sanity)
-    "channel_small": dict(mesh="channel", dims=(80, 20, 20), jitter=0.1, n=200_000, dt=0.02, ncycles=10, D=1.5e-5, field="channel",
-                          desc="channel 80x20x20 hex, 2e5 tracers"),
+    "channel_small": dict(mesh="channel", dims=(80, 20, 20), jitter=0.1, n=200_000, dt=0.02, ncycles=10, D=1.5e-5, field="recirc",
+                          integrator="euler", desc="channel 80x20x20 hex, 2e5 tracers"),
 }
 
 
@@ -99,28 +124,60 @@ class ClockSampler:
             self.proc.terminate()
 
 
-def build_inputs(w, rank, world=1):
-    from cudaparticlesfoam_b200 import parallel, synth
+def partition(n_total, n_ranks, rank):
+    from cudaparticlesfoam_b200 import parallel
+
+    return parallel.partition(n_total, n_ranks, rank)
+
+
+def build_mesh(w):
+    from cudaparticlesfoam_b200 import synth
 
     if w["mesh"] == "channel":
-        nx, ny, nz = w["dims"]
-        pm = synth.box_mesh(nx, ny, nz, lo=(0, 0, 0), hi=(4.0, 1.0, 1.0), jitter=w["jitter"])
-    else:
-        pm = synth.box_mesh(*w["dims"], jitter=w["jitter"])
+        return synth.box_mesh(*w["dims"], lo=(0, 0, 0), hi=(4.0, 1.0, 1.0), jitter=w["jitter"])
+    if w["mesh"] == "pitz":
+        return synth.backward_step_mesh()
+    if w["mesh"] == "honeycomb":
+        return synth.honeycomb_mesh_fast(*w["dims"])
+    return synth.box_mesh(*w["dims"], jitter=w["jitter"])
+
+
+def build_fields(w, pm, nf=4):
+    from cudaparticlesfoam_b200 import synth
+
+    f = w["field"]
+    if f == "recirc":
+        return [synth.field_recirculation(pm.cell_centres, t=0.05 * k, lo=pm.lo, hi=pm.hi) for k in range(nf)]
+    if f == "channel":
+        return [synth.field_channel(pm.cell_centres, t=0.05 * k, lo=pm.lo, hi=pm.hi) for k in range(nf)]
+    if f == "pitz":  # frozen flow of the tutorial: ~10 m/s bulk velocity through a 0.3 m domain, one snapshot
+        return [synth.field_channel(pm.cell_centres, t=0.0, Umax=10.0, eps=0.02, lo=pm.lo, hi=pm.hi)]
+    span = float((pm.hi - pm.lo)[:2].min())
+    return [synth.field_uniform_vortex(pm.cell_centres, omega=2 * np.pi * (1 + 0.02 * k), R=0.2 * span) for k in range(nf)]
+
+
+def build_inputs(w, rank, world=1, n_override=None):
+    from cudaparticlesfoam_b200 import synth
+
+    pm = build_mesh(w)
     span = pm.hi - pm.lo
+    n = int(n_override or w["n"])
     # weak scaling: ONE global cloud of world*n particles, partitioned by contiguous index range; every rank
     # generates only its own slice (same stream as a single big seed_box call would give)
-    start, count = parallel.partition(w["n"] * world, world, rank)
+    start, count = partition(n * world, world, rank)
     lo, hi = pm.lo + 0.02 * span, pm.hi - 0.02 * span
     p = np.empty((count, 4))
     for ax in range(3):
         p[:, ax] = lo[ax] + synth.uniform01(1591593751, start + count, stream=ax)[start:] * (hi[ax] - lo[ax])
     p[:, 3] = 1.0
-    if w["field"] == "channel":
-        fields = [synth.field_channel(pm.cell_centres, t=0.05 * k, lo=pm.lo, hi=pm.hi) for k in range(4)]
-    else:
-        fields = [synth.field_uniform_vortex(pm.cell_centres, omega=2 * np.pi * (1 + 0.02 * k)) for k in range(4)]
-    return pm, p, fields
+    return pm, p, build_fields(w, pm), start
+
+
+def common_config(args, w, pm, n_per_gpu):
+    """The keys BOTH arms print (the driver compares them)."""
+    return {"workload": args.workload, "description": w["desc"], "particles_per_gpu": int(n_per_gpu), "cells": int(pm.n_cells),
+            "substeps_per_step": int(w["ncycles"]), "integrator": args.integrator or w["integrator"], "interpolation": args.interp,
+            "random_walk_D": w["D"]}
 
 
 def structured_seed_tets(pm, p):
@@ -133,140 +190,170 @@ def structured_seed_tets(pm, p):
 
 
 # --------------------------------------------------------------------------------------------------
-def run_ours(args, w, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
+class Rig:
+    """One rank's tracker + the pinned / device copies of the field snapshots + the step functions."""
 
-    from cudaparticlesfoam_b200 import api
+    def __init__(self, args, w, rank, world, local_rank, uid, rng_name, n_override=None):
+        import torch
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    pm, p, fields = build_inputs(w, rank, world)
-    integ = {"euler": api.EULER, "rk2": api.RK2, "rk4": api.RK4}[args.integrator]
-    tr = api.ParticleTracker(device=local_rank, rng=api.RNG_PHILOX if w["D"] > 0 else api.RNG_NONE, diffusion_coeff=w["D"], dt=w["dt"],
-                             sort_interval=args.sort_interval, fuse_substeps=args.fuse, path=api.PATH_EXACT if args.exact else api.PATH_FILTERED,
-                             integrator=integ, interp=api.INTERP_VERTEX if args.interp == "vertex" else api.INTERP_TET)
-    # one explicit non-default stream shared by torch (copies, NCCL, timing events) and the library
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    tr.set_stream(stream.cuda_stream)
-    t0 = time.time()
-    tr.upload_poly(pm)
-    t_mesh = time.time() - t0
-    tr.update_velocity(fields[0])
-    tr.set_particles(p)
-    t0 = time.time()
-    tr.locate_initial()
-    tr.sync()
-    t_loc = time.time() - t0
-    if not args.shuffled:
-        tr.sort()  # seeded positions are uniformly random, i.e. shuffled with respect to the cells
-    ncell = pm.n_cells
-    u_host = [torch.from_numpy(f).pin_memory() for f in fields]
-    u_dev = [torch.from_numpy(f).to(dev) for f in fields]
-    u_stage = torch.empty((ncell, 3), dtype=torch.float64, device=dev)
-    stat_dev = torch.zeros(4, dtype=torch.float64, device=dev)
-    deltaT = w["dt"] * w["ncycles"]
-    h2d = ncell * 24
-    d2h = 0
+        from cudaparticlesfoam_b200 import api
 
-    from cudaparticlesfoam_b200 import parallel
-
-    def bcast(t):
-        parallel.broadcast_field(t, src=0)  # NCCL over NVLink when world > 1, no-op otherwise
-
-    def step_resident(k):
-        src = u_dev[k % len(u_dev)]
+        self.torch, self.api, self.w, self.rank, self.world = torch, api, w, rank, world
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.pm, p, fields, start = build_inputs(w, rank, world, n_override)
+        self.p, self.fields = p, fields
+        integ = {"euler": api.EULER, "rk2": api.RK2, "rk4": api.RK4}[args.integrator or w["integrator"]]
+        rng = {"philox": api.RNG_PHILOX, "xorwow": api.RNG_XORWOW, "none": api.RNG_NONE}[rng_name] if w["D"] > 0 else api.RNG_NONE
+        self.tr = tr = api.ParticleTracker(device=local_rank, rng=rng, diffusion_coeff=w["D"], dt=w["dt"], sort_interval=args.sort_interval,
+                                           fuse_substeps=args.fuse, path=api.PATH_EXACT if args.exact else api.PATH_FILTERED, integrator=integ,
+                                           interp=api.INTERP_VERTEX if args.interp == "vertex" else api.INTERP_TET)
+        # one explicit non-default stream shared by torch (pinned copies, timing events) and the library
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.stream)
+        tr.set_stream(self.stream.cuda_stream)
+        kind = None
+        if w.get("escape"):
+            kind = np.zeros(len(self.pm.patch_starts) - 1, dtype=np.int32)
+            for name in w["escape"]:
+                kind[list(self.pm.patch_names).index(name)] = api.PATCH_ESCAPE
+        t0 = time.time()
+        tr.upload_poly(self.pm, patch_kind=kind)
+        tr.sync()
+        self.t_mesh = time.time() - t0
         if world > 1:
-            if rank == 0:
-                u_stage.copy_(src)
-            bcast(u_stage)
-            src = u_stage
-        tr.update_velocity_ptr(src.data_ptr(), True)
-        tr.advect(None, deltaT)
+            tr.comm_init(uid, rank, world)
+        tr.update_velocity(fields[0])
+        tr.set_particles(p)
+        tr.set_particle_id_base(start)  # random-walk streams keyed by GLOBAL particle id
+        if rng == api.RNG_XORWOW:
+            tr.init_rng()
+        t0 = time.time()
+        tr.locate_initial()
+        tr.sync()
+        self.t_loc = time.time() - t0
+        if not args.shuffled:
+            tr.sort()  # seeded positions are uniformly random, i.e. shuffled with respect to the cells
+        self.u_host = [torch.from_numpy(f).pin_memory() for f in fields]
+        self.u_dev = [torch.from_numpy(f).to(self.dev) for f in fields] if rank == 0 or world == 1 else []
+        self.deltaT = w["dt"] * w["ncycles"]
+        span = self.pm.hi - self.pm.lo
+        self.slab = (self.pm.lo + np.array([0.02, 0.05, 0.05]) * span, self.pm.lo + np.array([0.06, 0.95, 0.95]) * span)
+        self.reseed_every = int(w.get("reseed_every", 0))
+        self.pending = 0
+        self.h2d = self.pm.n_cells * 24
+        self.d2h = 0
 
-    side = torch.cuda.Stream(device=dev)
-    u_stage2 = [torch.empty((ncell, 3), dtype=torch.float64, device=dev) for _ in range(2)]
-    ev_stage = torch.cuda.Event()
-    ev_taken = [torch.cuda.Event(), torch.cuda.Event()]  # the library has copied u_stage2[b] into its own buffer
-
-    def stage_next(k):
-        b = k % 2
-        side.wait_event(ev_taken[b])
-        with torch.cuda.stream(side):
-            if rank == 0:
-                u_stage2[b].copy_(u_host[k % len(u_host)], non_blocking=True)  # H2D from pinned memory
-            bcast(u_stage2[b])
-            ev_stage.record(side)
-
-    def step_e2e(k):
-        nonlocal d2h
-        if world == 1:
-            # through the C ABI with a HOST buffer: cpf_update_velocity uploads on the library's copy stream, so the
-            # field of step k+1 (pinned memory, 24 MB) crosses PCIe while the sub-steps of step k run; every step
-            # still carries exactly one H2D of U and one D2H of the statistics inside the timed region
-            tr.advect(None, deltaT)
-            tr.update_velocity_ptr(u_host[(k + 1) % len(u_host)].data_ptr(), False)
+    # U already resident in HBM (on rank 0; the library broadcasts it over NCCL when world > 1)
+    def step_resident(self, k):
+        tr = self.tr
+        if self.world == 1:
+            tr.update_velocity_ptr(self.u_dev[k % len(self.u_dev)].data_ptr(), True)
         else:
-            # same one-step-ahead pipeline across ranks: while the sub-steps of step k run on the compute stream, rank 0
-            # uploads U(k+1) and NCCL broadcasts it on a side stream; the library then takes it from the device buffer
-            tr.advect(None, deltaT)
-            stage_next(k + 1)
-            stream.wait_event(ev_stage)
-            tr.update_velocity_ptr(u_stage2[(k + 1) % 2].data_ptr(), True)
-            ev_taken[(k + 1) % 2].record(stream)
-        st = tr.stats()  # D2H of the counters (synchronises the stream)
-        d2h = 8 * 11
-        if world > 1:
-            st = parallel.reduce_stats(st, device=dev)  # particle statistics come back over NCCL
+            tr.update_velocity_bcast(self.u_dev[k % len(self.fields)].data_ptr() if self.rank == 0 else None, root=0, on_device=True)
+        tr.advect(None, self.deltaT)
+        if self.reseed_every and (k + 1) % self.reseed_every == 0:
+            tr.reseed_inactive(*self.slab)
+
+    # through the C ABI with HOST buffers: U(k+1) from pinned memory (uploaded / broadcast on the library's copy stream
+    # while the sub-steps of step k run) and a statistics read-back per step, collected one step late (no host stall)
+    def step_e2e(self, k):
+        tr = self.tr
+        tr.advect(None, self.deltaT)
+        nxt = self.u_host[(k + 1) % len(self.u_host)].data_ptr()
+        if self.world == 1:
+            tr.update_velocity_ptr(nxt, False)
+        else:
+            tr.update_velocity_bcast(nxt if self.rank == 0 else None, root=0, on_device=False)
+        if self.reseed_every and (k + 1) % self.reseed_every == 0:
+            tr.reseed_inactive(*self.slab)
+        tr.stats_request(full=False)  # summed over the ranks on the device (NCCL) when world > 1
+        self.pending += 1
+        self.d2h = 16 * 8
+        st = None
+        if self.pending > 1:
+            st = tr.stats_collect()
+            self.pending -= 1
         return st
 
-    def timed(fn, K):
-        if world > 1:
-            dist.barrier()
+    def drain(self):
+        st = None
+        while self.pending:
+            st = self.tr.stats_collect()
+            self.pending -= 1
+        return st
+
+    def timed(self, fn, K, max_over_ranks):
+        torch = self.torch
+        if self.world > 1:
+            max_over_ranks(0.0)  # barrier
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_a = time.time()
-        e0.record(stream)
+        e0.record(self.stream)
         for k in range(K):
             fn(k)
-        e1.record(stream)
+        e1.record(self.stream)
         torch.cuda.synchronize()
-        t_b = time.time()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), t_a, t_b
+        return max_over_ranks(e0.elapsed_time(e1))
 
-    clocks = ClockSampler(local_rank) if rank == 0 else None
-    t_load0 = time.time()
-    for k in range(args.warmup):
-        step_resident(k)
+
+def measure(rig, steps, warmup, max_over_ranks, sum_over_ranks, e2e=True):
+    """-> dict(value, ms, e2e_value, ms_e2e, prof...) for one rig: warm-up, K resident steps, K end-to-end steps."""
+    tr = rig.tr
+    for k in range(warmup):
+        rig.step_resident(k)
     tr.sync()
     st0 = tr.stats()
     launches0 = tr.launch_count()
     tr.profile(True)
-    ms, ta, tb = timed(step_resident, args.steps)
+    ms = rig.timed(rig.step_resident, steps, max_over_ranks)
     nl, prof_ms, prof_max = tr.profile_read()
     tr.profile(False)
     launches = tr.launch_count() - launches0
     st1 = tr.stats()
-    psteps = st1["n_substeps"] - st0["n_substeps"]  # active particle-sub-steps actually executed on this rank
-    if world == 1:
-        tr.update_velocity_ptr(u_host[0].data_ptr(), False)  # primes the one-step-ahead upload of step_e2e
-    else:
-        stage_next(0)
-        stream.wait_event(ev_stage)
-        tr.update_velocity_ptr(u_stage2[0].data_ptr(), True)
-        ev_taken[0].record(stream)
-    for k in range(min(args.warmup, 2)):
-        step_e2e(k)
-    st2 = tr.stats()
-    ms_e2e, _, tb2 = timed(step_e2e, args.steps)
-    st3 = tr.stats()
+    psteps = sum_over_ranks(st1["n_substeps"] - st0["n_substeps"]) if rig.world == 1 else st1["n_substeps"] - st0["n_substeps"]
+    out = {"ms": ms, "psteps": psteps, "value": psteps / (ms * 1e-3), "launches": launches, "nl": nl, "prof_ms": prof_ms, "st0": st0, "st1": st1}
+    if e2e:
+        if rig.world == 1:
+            tr.update_velocity_ptr(rig.u_host[0].data_ptr(), False)  # primes the one-step-ahead upload
+        else:
+            tr.update_velocity_bcast(rig.u_host[0].data_ptr() if rig.rank == 0 else None, root=0, on_device=False)
+        for k in range(min(warmup, 2)):
+            rig.step_e2e(k)
+        rig.drain()
+        st2 = tr.stats()
+        ms_e2e = rig.timed(lambda k: rig.step_e2e(k), steps, max_over_ranks)
+        rig.drain()
+        st3 = tr.stats()
+        ps2 = st3["n_substeps"] - st2["n_substeps"]
+        out.update({"ms_e2e": ms_e2e, "e2e_value": ps2 / (ms_e2e * 1e-3)})
+    return out
+
+
+def run_ours(args, w, rank, world, local_rank):
+    import torch
+
+    from cudaparticlesfoam_b200 import api, parallel
+
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo")  # control plane only: the NCCL id and the max-over-ranks of the timings
+        uid = parallel.share_unique_id(api.ParticleTracker.comm_unique_id if rank == 0 else None)
+
+    def max_over_ranks(x):
+        return parallel.max_over_ranks(x)
+
+    def sum_over_ranks(x):
+        return x  # statistics are already summed over the ranks inside the library (cpf_stats_get is collective)
+
+    n_over = args.particles or (w.get("n_single") if world == 1 and args.full_single else None)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    t_load0 = time.time()
+    rig = Rig(args, w, rank, world, local_rank, uid, args.rng, n_over)
+    tr, pm = rig.tr, rig.pm
+    m = measure(rig, args.steps, args.warmup, max_over_ranks, sum_over_ranks)
     ck = None
     if clocks:
         # nvidia-smi samples every 100 ms; the timed regions are tens of ms, so keep the GPU under the same load until
@@ -274,58 +361,113 @@ def run_ours(args, w, rank, world, local_rank):
         t_hold = time.time()
         k = 0
         while time.time() - t_load0 < 1.2 or time.time() - t_hold < 0.4:
-            tr.advect(None, deltaT); k += 1  # rank-local load only: NO collective here (only rank 0 samples clocks)
+            tr.advect(None, rig.deltaT); k += 1  # rank-local load only: NO collective here (only rank 0 samples clocks)
             if k % 8 == 0:
                 tr.sync()
         tr.sync()
         ck = clocks.window(t_load0, time.time())
         clocks.stop()
-    tot = torch.tensor([float(psteps), float(st3["n_substeps"] - st2["n_substeps"])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot)
-    value = float(tot[0].item()) / (ms * 1e-3)
-    e2e_value = float(tot[1].item()) / (ms_e2e * 1e-3)
+    st0, st1 = m["st0"], m["st1"]
+    psteps = m["psteps"]
     peak, peak_src = _peaks()
+    nl, prof_ms = m["nl"], m["prof_ms"]
     avg_launch_ms = prof_ms / max(nl, 1)
     sub_per_launch = (w["ncycles"] * args.steps) / max(nl, 1)
-    # achieved GB/s = B_alg x particle-steps/s of the fused kernel(s); with k sub-steps fused per launch the
-    # particle state actually crosses HBM once per launch, so measured DRAM traffic (`traffic`) is BELOW the algorithmic bytes
-    achieved = B_ALG * psteps / (prof_ms * 1e-3) / 1e9
-    traffic = None
+    psteps_rank = psteps / world  # the launch timings are this rank's
+    # achieved GB/s = B_alg x particle-steps/s of the advect launch sequence; with k sub-steps fused per launch
+    # the particle state actually crosses HBM once per launch, so the measured DRAM traffic (`traffic`) is BELOW that
+    achieved = B_ALG * psteps_rank / (prof_ms * 1e-3) / 1e9
+    traffic = traffic_src = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         except Exception:
             traffic = None
+    hops = (st1["n_hops"] - st0["n_hops"]) / max(psteps, 1)
+    cfg = common_config(args, w, pm, p_count := rig.p.shape[0])
     out = {
-        "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": w["desc"], "particles_per_gpu": w["n"], "cells": pm.n_cells,
-                   "substeps_per_step": w["ncycles"], "substeps_per_launch": sub_per_launch, "integrator": args.integrator, "interpolation": args.interp, "sort_interval": args.sort_interval, "initial_order": "shuffled" if args.shuffled else "sorted by cell",
-                   "path": "exact" if args.exact else "filtered",
-                   "e2e_path": ("host U -> cpf_update_velocity (copy stream, one step ahead of the sub-steps) -> cpf_advect -> cpf_stats_get" if world == 1
-                                else "rank 0 host U -> H2D -> ncclBroadcast on a side stream, one step ahead of the sub-steps -> cpf_update_velocity(device) -> cpf_advect -> cpf_stats_get + NCCL reduce"),
-                   "l2_hygiene": "working set (particle state + mesh) > 126 MB L2, no flush",
-                   "parallelism": f"particles partitioned over {world} GPU(s), mesh replicated"},
-        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
+        "metric": "particle-steps/s", "value": m["value"], "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg,
+        "details": {"rng": args.rng if w["D"] > 0 else "none", "substeps_per_launch": sub_per_launch, "sort_interval": args.sort_interval,
+                    "initial_order": "shuffled" if args.shuffled else "sorted by cell", "path": "exact" if args.exact else "filtered",
+                    "e2e_path": ("pinned host U -> cpf_update_velocity (H2D + repack on the copy stream, one step ahead of the sub-steps) -> "
+                                 "cpf_advect -> cpf_stats_request / cpf_stats_collect (one step late)" if world == 1 else
+                                 "rank 0 pinned host U -> cpf_update_velocity_bcast (H2D + ncclBroadcast + repack on the copy stream, one step ahead) "
+                                 "-> cpf_advect -> cpf_stats_request (ncclAllReduce of the slot on the device) / cpf_stats_collect"),
+                    "l2_hygiene": "working set (particle state + mesh) > 126 MB L2, no flush",
+                    "parallelism": f"particles partitioned over {world} GPU(s) by index range, mesh replicated; NCCL inside libcpf (cpf_comm.cu)"},
+        "e2e": {"value": m["e2e_value"], "unit": "particle-steps/s", "h2d_bytes_per_step": rig.h2d, "d2h_bytes_per_step": rig.d2h,
+                "ms_per_step": m["ms_e2e"] / args.steps},
+        "gpu_launches": int(m["launches"]),
         "clocks": ck,
-        "roofline": {"bound": "hbm", "kernel": "cpf::k_fast (+ k_exact rounds)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_particle_step": B_ALG,
-                     "algorithmic_bytes_per_launch": B_ALG * psteps / max(nl, 1), "avg_launch_ms": avg_launch_ms, "launches_timed": nl,
-                     "substeps_per_launch": sub_per_launch, "kernel_share_of_step": prof_ms / ms},
-        "stats": {"exact_fraction": (st1["n_exact"] - st0["n_exact"]) / max(psteps, 1), "hops_per_substep": (st1["n_hops"] - st0["n_hops"]) / max(psteps, 1),
-                  "reflections": st1["n_reflections"] - st0["n_reflections"], "active": st1["n_active"], "mesh_build_s": t_mesh, "initial_locate_s": t_loc},
+        "roofline": {"bound": "hbm", "kernel": "advect launch sequence: cpf::k_lean + k_fast<queue,wall> + k_exact_convex<rest>", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src, "algorithmic_bytes_per_particle_step": B_ALG,
+                     "algorithmic_bytes_per_launch": B_ALG * psteps_rank / max(nl, 1), "avg_launch_ms": avg_launch_ms, "launches_timed": nl,
+                     "substeps_per_launch": sub_per_launch, "kernel_share_of_step": prof_ms / m["ms"],
+                     # what the kernel is REALLY limited by (ncu, profiles/r2_summary.md): instruction issue and the L1 data pipe;
+                     # HBM is nearly idle because the particle state stays in registers across the fused sub-steps
+                     "measured_limiter": "instruction issue + L1 data pipe (not HBM)",
+                     "real_dram_frac": (traffic / (avg_launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                     # mesh-inclusive figure: 72 B of state + one 64-byte record per visited tet + the 32-byte
+                     # origin position on ~half of the hops + the 32-byte cell velocity per sub-step
+                     "bytes_per_particle_step_with_mesh": B_ALG + 64.0 * hops + 16.0 * max(hops - 1.0, 0.0) + 32.0},
+        "stats": {"exact_fraction": (st1["n_exact"] - st0["n_exact"]) / max(psteps, 1), "hops_per_substep": hops,
+                  "reflections_per_particle_step": (st1["n_reflections"] - st0["n_reflections"]) / max(psteps, 1),
+                  "escaped": st1["n_escaped"] - st0["n_escaped"], "active": st1["n_active"], "mesh_build_s": rig.t_mesh,
+                  "initial_locate_s": rig.t_loc},
     }
     if rank == 0 and world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(w, pm, p, fields, tr)
+        out["cpu_baseline"] = cpu_baseline(w, pm, rig.p, rig.fields, tr)
     tr.close()
+    del rig
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_extra and args.workload == "channel1M_1e7" and not args.exact:
+        out["extra"] = extras(args, local_rank, max_over_ranks, sum_over_ranks)
     if world > 1:
+        import torch.distributed as dist
+
         dist.destroy_process_group()
     return out
+
+
+def extras(args, local_rank, max_over_ranks, sum_over_ranks):
+    """Short runs of the other configurations BASELINE.json names, measured exactly like the headline (N = 1 only)."""
+    import copy
+
+    import torch
+
+    res = {}
+
+    def one(name, workload, rng, steps, warmup, **over):
+        a = copy.copy(args)
+        a.workload, a.integrator, a.rng = workload, over.get("integrator"), rng
+        try:
+            rig = Rig(a, WORKLOADS[workload], 0, 1, local_rank, None, rng)
+            m = measure(rig, steps, warmup, max_over_ranks, sum_over_ranks)
+            res[name] = {"workload": workload, "rng": rng if WORKLOADS[workload]["D"] > 0 else "none", "integrator": a.integrator or WORKLOADS[workload]["integrator"],
+                         "value": m["value"], "e2e": m["e2e_value"], "ms_per_step": m["ms"] / steps, "steps": steps, "warmup": warmup,
+                         "roofline_frac": B_ALG * m["psteps"] / (m["prof_ms"] * 1e-3) / 1e9 / _peaks()[0],
+                         "substeps_per_launch": WORKLOADS[workload]["ncycles"] * steps / max(m["nl"], 1)}
+            rig.tr.close()
+            del rig
+            torch.cuda.empty_cache()
+        except Exception as e:  # an extra must never take the headline down
+            res[name] = {"unavailable": repr(e)[:300]}
+
+    # the drop-in's DEFAULT configuration: the reference's XORWOW stream, library-default fusing
+    a0 = args.fuse
+    args.fuse = 0
+    one("xorwow_default_config", "channel1M_1e7", "xorwow", 8, 3)
+    args.fuse = a0
+    one("throughflow_all_reflect", "channel1M_1e7_throughflow", "philox", 8, 3)
+    one("throughflow_escape_reseed", "channel1M_1e7_escape", "philox", 10, 3)
+    one("C2_box100_1e6_rk2", "box100_1e6", "none", 8, 3)
+    one("C1_pitz_1e5", "pitz_1e5", "xorwow", 20, 5)
+    return res
 
 
 def cpu_baseline(w, pm, p, fields, tr=None, n_sample=1_000_000, n_sub=20):
@@ -383,7 +525,7 @@ def run_reference(args, w, rank, world, local_rank):
         return None
     from oracle import orc
 
-    pm, p, fields = build_inputs(w, 0)
+    pm, p, fields, _ = build_inputs(w, 0)
     deltaT = w["dt"] * w["ncycles"]
     have_gpu = False
     try:
@@ -394,25 +536,34 @@ def run_reference(args, w, rank, world, local_rank):
         pass
     base = {"metric": "particle-steps/s", "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, "description": w["desc"], "cells": pm.n_cells, "substeps_per_step": w["ncycles"]}}
-    if args.ref_arm == "cuda" and have_gpu and orc.ref_available():
+            "config": common_config(args, w, pm, p.shape[0])}
+    if args.ref_arm == "cuda" and have_gpu and orc.ref_available() and w["integrator"] == "euler" and w["mesh"] != "honeycomb":
         mesh = orc.tet_mesh_from_poly(pm)
-        Utets = [orc.expand_velocity(mesh, f) for f in fields[:2]]
-        rr = orc.RefRun(mesh, Utets[0], p, structured_seed_tets(pm, p), init_rng=w["D"] > 0)
+        rr = orc.RefRun(mesh, orc.expand_velocity(mesh, fields[0]), p, structured_seed_tets(pm, p), init_rng=w["D"] > 0)
         rr.bary_query()
         import torch
 
-        def step(k):
+        t_refresh = t_kernel = 0.0
+
+        def step(k, timed=False):
+            nonlocal t_refresh, t_kernel
+            t0 = time.perf_counter()
             Ut = orc.expand_velocity(mesh, fields[k % len(fields)])  # the glue's 12x host expansion (src/advect.H:44-54)
             rr.update_velocity(Ut)                                   # cudaUpdateVelocity: vector by value + H2D + D2D
-            rr.substeps(w["ncycles"], deltaT / w["ncycles"], convex=True, brownian=w["D"] > 0, D=w["D"], reflect=True)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            # the five kernels per sub-step, CUDA-event time around the whole loop (ref_shim: ref_substeps_timed)
+            ms = rr.substeps_timed(w["ncycles"], deltaT / w["ncycles"], convex=True, brownian=w["D"] > 0, D=w["D"], reflect=True)
+            if timed:
+                t_refresh += t1 - t0
+                t_kernel += ms * 1e-3
 
         for k in range(args.warmup):
             step(k)
         torch.cuda.synchronize()
         t0 = time.time()
         for k in range(args.steps):
-            step(k)
+            step(k, True)
         torch.cuda.synchronize()
         sec = time.time() - t0
         g = rr.download()
@@ -420,12 +571,14 @@ def run_reference(args, w, rank, world, local_rank):
         rr.close()
         val = active * w["ncycles"] * args.steps / sec
         base.update({"value": val, "ms_per_step": sec / args.steps * 1e3,
+                     # where the reference's step goes: host-side 12x expansion + upload vs its five kernels per sub-step
+                     "refresh_ms_per_step": t_refresh / args.steps * 1e3, "kernel_ms_per_step": t_kernel / args.steps * 1e3,
+                     "kernel_only_value": active * w["ncycles"] * args.steps / max(t_kernel, 1e-9),
                      "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": 0, "kind": "reference",
                                       "sample": "full workload; the reference's path exists only as CUDA kernels, so its unmodified kernels "
                                                 "(oracle/_ref, sm_100a) run on cuda:0 in the src/advect.H call order, host velocity expansion "
                                                 "included; wall-clock around the blocking reference calls"},
                      "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        base["config"]["particles"] = int(w["n"])
         return base
     cb = cpu_baseline(w, pm, p, fields, n_sample=min(w["n"], 2_000_000), n_sub=w["ncycles"] * max(1, min(args.steps, 3)))
     base.update({"value": cb["value"], "ms_per_step": None, "cpu_baseline": cb,
@@ -441,13 +594,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-arm", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--workload", default="channel1M_1e7", choices=sorted(WORKLOADS))
+    ap.add_argument("--rng", default="philox", choices=["philox", "xorwow", "none"],
+                    help="random walk stream: philox (stateless) or xorwow (the reference's cuRAND stream, the drop-in's default)")
     ap.add_argument("--sort-interval", type=int, default=50)
-    ap.add_argument("--integrator", choices=["euler", "rk2", "rk4"], default="euler", help="BASELINE configs[1] is RK2, configs[3] RK4 (extensions; reference is Euler)")
+    ap.add_argument("--integrator", choices=["euler", "rk2", "rk4"], default=None, help="default: the workload's (C2 is RK2, C4 RK4; reference is Euler)")
     ap.add_argument("--interp", choices=["cell", "vertex"], default="cell", help="vertex = cellPoint-style interpolation (extension; reference default is the cell value)")
     ap.add_argument("--shuffled", action="store_true", help="locality probe (SURVEY 8d): no initial sort by cell; combine with --sort-interval 0")
-    ap.add_argument("--fuse", type=int, default=10)
+    ap.add_argument("--fuse", type=int, default=10, help="sub-steps per launch sequence (0 = library default)")
+    ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's)")
+    ap.add_argument("--full-single", action="store_true", help="N=1: run the workload's whole multi-GPU cloud on the one GPU")
     ap.add_argument("--exact", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configurations")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -49,10 +49,12 @@ SYMBOLS = {
     "cpf_update_velocity": (C.c_int, [_vp, _vp, C.c_int]),
     "cpf_update_vertex_velocity": (C.c_int, [_vp, _vp, C.c_int]),
     "cpf_seed_box": (C.c_int, [_vp, _ll, _dp, _dp, C.c_ulonglong]),
+    "cpf_seed_box_slice": (C.c_int, [_vp, _ll, _ll, _dp, _dp, C.c_ulonglong]),
     "cpf_set_particles": (C.c_int, [_vp, _ll, _dp]),
     "cpf_set_tets": (C.c_int, [_vp, _ip]),
     "cpf_locate_initial": (C.c_int, [_vp]),
     "cpf_init_rng": (C.c_int, [_vp]),
+    "cpf_reseed_inactive": (C.c_int, [_vp, _dp, _dp, C.c_ulonglong, C.POINTER(_ll)]),
     "cpf_relocate_lost": (C.c_int, [_vp]),
     "cpf_advect": (C.c_int, [_vp, C.c_double, _ip]),
     "cpf_substeps": (C.c_int, [_vp, C.c_int, C.c_double]),
@@ -62,6 +64,14 @@ SYMBOLS = {
     "cpf_download": (C.c_int, [_vp, _dp, _dp, _ip]),
     "cpf_download_cells": (C.c_int, [_vp, _ip]),
     "cpf_stats_get": (C.c_int, [_vp, C.POINTER(CpfStats)]),
+    "cpf_stats_request": (C.c_int, [_vp, C.c_int]),
+    "cpf_stats_collect": (C.c_int, [_vp, C.POINTER(CpfStats)]),
+    "cpf_comm_unique_id": (C.c_int, [_vp, C.c_size_t]),
+    "cpf_comm_init": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int]),
+    "cpf_comm_info": (C.c_int, [_vp, _ip, _ip, _ip]),
+    "cpf_update_velocity_bcast": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "cpf_update_velocity_slices": (C.c_int, [_vp, _ll, _ll, _vp, C.c_int]),
+    "cpf_set_particle_id_base": (C.c_int, [_vp, _ll]),
     "cpf_write_vtu": (C.c_int, [_vp, C.c_char_p, C.c_uint]),
     "cpf_write_vtu_async": (C.c_int, [_vp, C.c_char_p, C.c_uint, C.c_int]),
     "cpf_output_wait": (C.c_int, [_vp]),

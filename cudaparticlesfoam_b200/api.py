@@ -157,6 +157,11 @@ class ParticleTracker:
         hi = np.asarray(hi, dtype=np.float64)
         self._chk(self.lib.cpf_seed_box(self.h, int(n), _dp(lo), _dp(hi), C.c_ulonglong(seed)))
 
+    def seed_box_slice(self, first, count, lo, hi, seed=1591593751):
+        lo = np.asarray(lo, dtype=np.float64)
+        hi = np.asarray(hi, dtype=np.float64)
+        self._chk(self.lib.cpf_seed_box_slice(self.h, int(first), int(count), _dp(lo), _dp(hi), C.c_ulonglong(seed)))
+
     def set_tets(self, tet):
         tet = np.ascontiguousarray(tet, dtype=np.int32)
         self._chk(self.lib.cpf_set_tets(self.h, _ip(tet)))
@@ -166,6 +171,14 @@ class ParticleTracker:
 
     def relocate_lost(self):
         self._chk(self.lib.cpf_relocate_lost(self.h))
+
+    def reseed_inactive(self, lo, hi, seed=1591593751, count=False):
+        """Continuous injection: every inactive particle goes back into the box [lo, hi]; count=True returns how many (synchronises)."""
+        lo = np.asarray(lo, dtype=np.float64)
+        hi = np.asarray(hi, dtype=np.float64)
+        n = C.c_longlong(0)
+        self._chk(self.lib.cpf_reseed_inactive(self.h, _dp(lo), _dp(hi), C.c_ulonglong(seed), C.byref(n) if count else None))
+        return n.value if count else None
 
     def init_rng(self):
         self._chk(self.lib.cpf_init_rng(self.h))
@@ -237,6 +250,56 @@ class ParticleTracker:
         s = CpfStats()
         self._chk(self.lib.cpf_stats_get(self.h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in CpfStats._fields_ if k != "reserved"}
+
+    def stats_request(self, full: bool = False):
+        """Enqueue a statistics read-back (no host synchronisation); collect it later with stats_collect()."""
+        self._chk(self.lib.cpf_stats_request(self.h, int(full)))
+
+    def stats_collect(self) -> dict:
+        """Result of the OLDEST outstanding stats_request (blocks only until that one has arrived)."""
+        s = CpfStats()
+        self._chk(self.lib.cpf_stats_collect(self.h, C.byref(s)))
+        d = {k: getattr(s, k) for k, _ in CpfStats._fields_ if k != "reserved"}
+        d["full"] = bool(s.reserved[0])
+        return d
+
+    # ------------------------------------------------------------------ one rank per GPU (cpf_comm.cu)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """rank 0: ncclGetUniqueId; distribute the bytes to the other ranks with the host's own transport."""
+        buf = C.create_string_buffer(128)
+        rc = _lib.load().cpf_comm_unique_id(buf, 128)
+        if rc:
+            raise CpfError(rc, "cpf_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes | None, rank: int, nranks: int):
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self._chk(self.lib.cpf_comm_init(self.h, buf, 128 if buf is not None else 0, int(rank), int(nranks)))
+
+    def comm_info(self):
+        r, n, v = C.c_int(), C.c_int(), C.c_int()
+        self._chk(self.lib.cpf_comm_info(self.h, C.byref(r), C.byref(n), C.byref(v)))
+        return r.value, n.value, v.value
+
+    def update_velocity_bcast(self, U, root: int = 0, on_device: bool = False):
+        """U: numpy cell field / device pointer on `root`, None elsewhere."""
+        if U is None:
+            self._chk(self.lib.cpf_update_velocity_bcast(self.h, None, 0, int(root)))
+        elif isinstance(U, (int, np.integer)):
+            self._chk(self.lib.cpf_update_velocity_bcast(self.h, C.c_void_p(int(U)), int(on_device), int(root)))
+        else:
+            U = np.ascontiguousarray(U, dtype=np.float64)
+            self._chk(self.lib.cpf_update_velocity_bcast(self.h, C.c_void_p(U.ctypes.data), 0, int(root)))
+            self._keep_U = U
+
+    def update_velocity_slices(self, cell_offset: int, U_local):
+        U_local = np.ascontiguousarray(U_local, dtype=np.float64)
+        self._chk(self.lib.cpf_update_velocity_slices(self.h, int(cell_offset), U_local.shape[0], C.c_void_p(U_local.ctypes.data), 0))
+        self._keep_U = U_local
+
+    def set_particle_id_base(self, base: int):
+        self._chk(self.lib.cpf_set_particle_id_base(self.h, int(base)))
 
     def write_vtu(self, directory: str, step: int):
         self._chk(self.lib.cpf_write_vtu(self.h, directory.encode(), int(step)))

@@ -44,9 +44,14 @@ namespace cpf {
 // ------------------------------------------------------------------------------------------------
 template <int RNG> struct Rng;
 
+// Xi: the type the staged deviates of a chunk are kept in (shared memory); STATEFUL: the stream is a generator state in
+// memory that advances by three normals per EXECUTED sub-step (skip(n): n sub-steps that another kernel has executed).
 template <> struct Rng<CPF_RNG_NONE> {
+    typedef float Xi;
+    static constexpr bool STATEFUL = false;
     CPF_DEV void open(const ParticleView &, long long, const StepParams &) {}
     CPF_DEV bool draw(int, double &, double &, double &) { return false; }
+    CPF_DEV void skip(int) {}
     CPF_DEV void close(const ParticleView &, long long) {}
 };
 
@@ -54,8 +59,14 @@ template <> struct Rng<CPF_RNG_NONE> {
 // curand_normal_double per sub-step (cuda/particles.cu:537,565-567).  The state lives in registers
 // for the whole launch: 48 B in + 48 B out per particle per launch instead of per sub-step.
 template <> struct Rng<CPF_RNG_XORWOW> {
+    typedef double Xi; // the reference adds curand_normal_double deviates: every bit counts
+    static constexpr bool STATEFUL = true;
     curandState_t st;
     CPF_DEV void open(const ParticleView &pv, long long i, const StepParams &) { st = pv.rng[i]; }
+    CPF_DEV void skip(int n)
+    {
+        for (int k = 0; k < 3 * n; ++k) (void)curand_normal_double(&st);
+    }
     CPF_DEV bool draw(int, double &a, double &b, double &c)
     {
         a = curand_normal_double(&st);
@@ -98,11 +109,16 @@ CPF_DEV void box_muller_f32(uint32_t x, uint32_t y, double &n0, double &n1)
     n1 = (double)__fmul_rn(r, mufu_cos(ang));
 }
 template <> struct Rng<CPF_RNG_PHILOX> {
-    uint32_t id, k0, k1;
+    typedef float Xi;
+    static constexpr bool STATEFUL = false;
+    CPF_DEV void skip(int) {}
+    uint32_t id, idhi, k0, k1;
     unsigned long long step0;
     CPF_DEV void open(const ParticleView &pv, long long i, const StepParams &sp)
     {
-        id = (uint32_t)pv.pid[i];
+        // GLOBAL particle id: ranks that track index ranges of one cloud draw disjoint streams (cpf_set_particle_id_base)
+        const unsigned long long gid = sp.idBase + (unsigned long long)pv.pid[i];
+        id = (uint32_t)gid; idhi = (uint32_t)(gid >> 32);
         k0 = (uint32_t)sp.seed; k1 = (uint32_t)(sp.seed >> 32);
         step0 = sp.step0;
     }
@@ -110,7 +126,7 @@ template <> struct Rng<CPF_RNG_PHILOX> {
     {
         const unsigned long long st = step0 + (unsigned long long)s;
         uint32_t o[4];
-        philox4x32_10(id, 0u, (uint32_t)st, (uint32_t)(st >> 32), k0, k1, o);
+        philox4x32_10(id, idhi, (uint32_t)st, (uint32_t)(st >> 32), k0, k1, o);
         double d;
         box_muller_f32(o[0], o[1], a, b);
         box_muller_f32(o[2], o[3], c, d);
@@ -122,7 +138,7 @@ template <> struct Rng<CPF_RNG_PHILOX> {
 // ------------------------------------------------------------------------------------------------
 // exact sub-step tails (S3+S4+S5)
 // ------------------------------------------------------------------------------------------------
-struct Tally { unsigned hops, exact, refl, esc; };
+struct Tally { unsigned hops, exact, refl, esc, frz; };
 CPF_DEV double4 vel4(D3 u) { return make_double4(u.x, u.y, u.z, -1.0); }
 
 // Default build: convex line walk + reflector.  The reference's reflector re-walks the segment
@@ -272,13 +288,16 @@ CPF_DEV D3 displacement(const MeshView &m, const StepParams &sp, Rng<RNG> &rng, 
     return disp;
 }
 
-CPF_DEV void flush_counters(const StepParams &sp, unsigned refl, unsigned exact, unsigned hops, unsigned nsteps, unsigned esc = 0u)
+// frz: particles this kernel froze (S1: negative tet id -> w := 0); with the escapes it lets the host derive the number of
+// active particles from the counters alone (cpf_stats_request light mode)
+CPF_DEV void flush_counters(const StepParams &sp, unsigned refl, unsigned exact, unsigned hops, unsigned nsteps, unsigned esc = 0u, unsigned frz = 0u)
 {
-    unsigned vals[5] = { esc, refl, exact, hops, nsteps };
+    const unsigned vals[6] = { esc, refl, exact, hops, nsteps, frz };
+    constexpr int slot[6] = { CNT_ESCAPED, CNT_REFLECT, CNT_EXACT, CNT_HOPS, CNT_SUBSTEPS, CNT_FROZEN };
 #pragma unroll
-    for (int c = 0; c < 5; ++c) {
+    for (int c = 0; c < 6; ++c) {
         unsigned x = __reduce_add_sync(0xffffffffu, vals[c]);
-        if ((threadIdx.x & 31) == 0 && x) atomicAdd(sp.counters + c, (unsigned long long)x);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(sp.counters + slot[c], (unsigned long long)x);
     }
 }
 
@@ -289,7 +308,7 @@ CPF_DEV void flush_counters(const StepParams &sp, unsigned refl, unsigned exact,
 template <int LOC, int RNG, int QMODE>
 __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact(const MeshView m, const ParticleView pv, const StepParams sp)
 {
-    Tally ty{ 0u, 0u, 0u, 0u };
+    Tally ty{ 0u, 0u, 0u, 0u, 0u };
     unsigned nsteps = 0;
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
     for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
@@ -307,9 +326,10 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact(const MeshView m,
         bool velValid = false;
         Rng<RNG> rng;
         rng.open(pv, i, sp);
+        if (QMODE) rng.skip(s0);
         for (int s = s0; s < s1; ++s) {
             if (w == 0.0) break;
-            if (tet < 0) { w = 0.0; break; } // S1: left the domain -> frozen (particles.cu:334-338)
+            if (tet < 0) { w = 0.0; ty.frz++; break; } // S1: left the domain -> frozen (particles.cu:334-338)
             const int cell = tet_cell(m, tet, ld_int4(m.tetv, tet));
             const D3 disp = displacement<RNG>(m, sp, rng, s, cell, P, vel);
             velValid = true;
@@ -324,7 +344,7 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact(const MeshView m,
         if (sp.writeVel && velValid && s1 == sp.nSub) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
         if (QMODE == 1) sp.queueIn[slot].y = s1;
     }
-    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc);
+    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc, ty.frz);
 }
 
 // k_exact_convex<RNG,QMODE>: k_exact for the default ConvexPoly build as ONE merged loop over tet visits.
@@ -338,7 +358,7 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact(const MeshView m,
 template <int RNG, int QMODE>
 __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact_convex(const MeshView m, const ParticleView pv, const StepParams sp)
 {
-    Tally ty{ 0u, 0u, 0u, 0u };
+    Tally ty{ 0u, 0u, 0u, 0u, 0u };
     unsigned nsteps = 0;
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -359,13 +379,13 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact_convex(const Mesh
         D3 vel{ 0.0, 0.0, 0.0 };
         bool velValid = false;
         Rng<RNG> rng;
-        if (live) rng.open(pv, i, sp);
+        if (live) { rng.open(pv, i, sp); if (QMODE) rng.skip(s); }
         D3 S{ 0.0, 0.0, 0.0 }, E = S, Phit = S;
         int cur = -1, in_j = -1, leg = 0, legHops = 0;
         bool needPro = true;
         while (__any_sync(0xffffffffu, active)) {
             if (active && needPro) {
-                if (tet < 0) { w = 0.0; active = false; } // S1: left the domain -> frozen (particles.cu:334-338)
+                if (tet < 0) { w = 0.0; ty.frz++; active = false; } // S1: left the domain -> frozen (particles.cu:334-338)
                 else {
                     const int cell = tet_cell(m, tet, ld_int4(m.tetv, tet));
                     const D3 disp = displacement<RNG>(m, sp, rng, s, cell, P, vel);
@@ -436,7 +456,7 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact_convex(const Mesh
         }
         if (!QMODE) break;
     }
-    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc);
+    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc, ty.frz);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -500,7 +520,7 @@ CPF_DEV D3 axpy3(double h, D3 k, D3 P) { return D3{ __fma_rn(h, k.x, P.x), __fma
 template <int RNG, int QMODE>
 __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const ParticleView pv, const StepParams sp)
 {
-    Tally ty{ 0u, 0u, 0u, 0u };
+    Tally ty{ 0u, 0u, 0u, 0u, 0u };
     unsigned nsteps = 0;
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
     for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
@@ -517,9 +537,10 @@ __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const Part
         if (w != 0.0) {
             Rng<RNG> rng;
             rng.open(pv, i, sp);
+            if (QMODE) rng.skip(s0);
             for (int s = s0; s < sp.nSub; ++s) {
                 if (w == 0.0) break;
-                if (tet < 0) { w = 0.0; break; }
+                if (tet < 0) { w = 0.0; ty.frz++; break; }
                 const D3 k1 = velocity_at(m, sp.interp, tet, P);
                 vel = k1;
                 if (sp.integrator == CPF_RK2) {
@@ -556,7 +577,7 @@ __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const Part
             if (sp.writeVel && velValid) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
         }
     }
-    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc);
+    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc, ty.frz);
 }
 
 // k_fast<RNG,QMODE,WALL,INTEG>: the kernels of the filtered policy (default ConvexPoly build).
@@ -587,8 +608,14 @@ __global__ void __launch_bounds__(128, (WALL || VERT) ? CPF_WALL_MIN_BLOCKS : (I
 k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 {
     constexpr bool KEEPV = INTEG || VERT; // the reported velocity is not simply U[cell]: carry it
-    extern __shared__ float s_xi[];
-    unsigned hops = 0, nsteps = 0, refl = 0;
+    typedef typename Rng<RNG>::Xi Xi;
+    constexpr bool STATEFUL = Rng<RNG>::STATEFUL;
+    extern __shared__ double s_dyn[];
+    Xi *s_xi = reinterpret_cast<Xi *>(s_dyn);
+    // stateful generator: the state after the whole chunk waits here and is committed only if the particle finishes its
+    // chunk in this kernel -- a deferred particle keeps its chunk-start state in memory, the next kernel re-draws from it
+    curandState_t *stash = reinterpret_cast<curandState_t *>(s_xi + 3 * 128 * (STATEFUL ? sp.nSub : 0)) + threadIdx.x;
+    unsigned hops = 0, nsteps = 0, refl = 0, frz = 0;
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride) { // warp-uniform trip count
@@ -611,11 +638,12 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
             if (live) rng.open(pv, i, sp);
             for (int q = 0; q < sp.nSub; ++q) {
                 double x0 = 0.0, x1 = 0.0, x2 = 0.0;
-                if (live && q >= s) rng.draw(q, x0, x1, x2);
-                s_xi[(q * 3 + 0) * 128 + threadIdx.x] = (float)x0;
-                s_xi[(q * 3 + 1) * 128 + threadIdx.x] = (float)x1;
-                s_xi[(q * 3 + 2) * 128 + threadIdx.x] = (float)x2;
+                if (live && (STATEFUL || q >= s)) rng.draw(q, x0, x1, x2);
+                s_xi[(q * 3 + 0) * 128 + threadIdx.x] = (Xi)x0;
+                s_xi[(q * 3 + 1) * 128 + threadIdx.x] = (Xi)x1;
+                s_xi[(q * 3 + 2) * 128 + threadIdx.x] = (Xi)x2;
             }
+            if constexpr (STATEFUL) { if (live) *stash = rng.st; }
         }
         Fast32 f;
         D3 O{ 0.0, 0.0, 0.0 }, disp{ 0.0, 0.0, 0.0 }; // disp: after an in-place reflection (leg = 1) the reflected END POINT
@@ -755,8 +783,9 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
             }
         }
         if (live) {
-            if (tet < 0 && deferAt < 0) w = 0.0; // frozen in a prologue (tet only turns negative through the exact kernels)
+            if (tet < 0 && deferAt < 0) { w = 0.0; frz++; } // frozen in a prologue (tet only turns negative through the exact kernels)
             nsteps += (unsigned)(s - sBegin);
+            if constexpr (STATEFUL) { if (deferAt < 0 && s >= sp.nSub) pv.rng[i] = *stash; }
             st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
             st_stream_i(pv.tet + i, tet);
             if (KEEPV) {
@@ -776,7 +805,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
         }
         if (!QMODE) break;
     }
-    flush_counters(sp, refl, 0u, hops, nsteps);
+    flush_counters(sp, refl, 0u, hops, nsteps, 0u, frz);
 }
 
 // k_lean<RNG,CFV>: the all-particles pass of the filtered policy for the reference's own configuration (Euler, cell
@@ -794,15 +823,19 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 #ifndef CPF_LEAN_SMEM_STATE
 #define CPF_LEAN_SMEM_STATE 0 /* 1: displacement and activity flag of a lane live in shared memory instead of 8 registers */
 #endif
-#define CPF_LEAN_SMEM_BYTES(nSub, rngOn) ((size_t)CPF_LEAN_THREADS * ((rngOn ? sizeof(float) * 3 * (size_t)(nSub) : 0) + (CPF_LEAN_SMEM_STATE ? 32 : 0)))
+#define CPF_LEAN_SMEM_BYTES(nSub, xiBytes, stateful) ((size_t)CPF_LEAN_THREADS * ((size_t)(xiBytes) * 3 * (size_t)(nSub) + (CPF_LEAN_SMEM_STATE ? 32 : 0) + ((stateful) ? sizeof(curandState_t) : 0)))
 template <int RNG, bool CFV>
 __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / CPF_LEAN_THREADS) k_lean(const MeshView m, const ParticleView pv, const StepParams sp)
 {
     constexpr int NT = CPF_LEAN_THREADS;
+    typedef typename Rng<RNG>::Xi Xi;
+    constexpr bool STATEFUL = Rng<RNG>::STATEFUL;
     extern __shared__ double s_dyn[];
-    // [disp x | disp y | disp z | w] per thread (CPF_LEAN_SMEM_STATE), then the deviates [sub-step][component][thread]
+    // [disp x | disp y | disp z | w] per thread (CPF_LEAN_SMEM_STATE), then the deviates [sub-step][component][thread],
+    // then (stateful generator) the state after the chunk, committed only if the particle finishes its chunk here
     double *sd = s_dyn + threadIdx.x;
-    float *xi = reinterpret_cast<float *>(s_dyn + (CPF_LEAN_SMEM_STATE ? 4 * NT : 0)) + threadIdx.x;
+    Xi *xi = reinterpret_cast<Xi *>(s_dyn + (CPF_LEAN_SMEM_STATE ? 4 * NT : 0)) + threadIdx.x;
+    curandState_t *stash = reinterpret_cast<curandState_t *>(xi - threadIdx.x + 3 * NT * (STATEFUL ? sp.nSub : 0)) + threadIdx.x;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool have = i < pv.n;
     double4 p4 = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -817,22 +850,23 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
         for (int q = 0; q < sp.nSub; ++q) {
             double x0 = 0.0, x1 = 0.0, x2 = 0.0;
             if (live) rng.draw(q, x0, x1, x2);
-            xi[(q * 3 + 0) * NT] = (float)x0;
-            xi[(q * 3 + 1) * NT] = (float)x1;
-            xi[(q * 3 + 2) * NT] = (float)x2;
+            xi[(q * 3 + 0) * NT] = (Xi)x0;
+            xi[(q * 3 + 1) * NT] = (Xi)x1;
+            xi[(q * 3 + 2) * NT] = (Xi)x2;
         }
+        if constexpr (STATEFUL) { if (live) *stash = rng.st; }
     }
     Fast32 f;
     D3 O{ 0.0, 0.0, 0.0 }, disp{ 0.0, 0.0, 0.0 }, u0{ 0.0, 0.0, 0.0 };
     int deferAt = -1, s = 0, mode = 2, cell = -1, visits = 0, org = -1;
-    unsigned hops = 0;
+    unsigned hops = 0, frz = 0;
     constexpr int CF = CFV ? CPF_CFV_YES : CPF_CFV_NO;
     auto fetch_velocity = [&]() {
         cell = CFV ? org - m.nPoints : __ldg(m.tetcell + tet);
         u0 = ld_ucell(m, cell);
     };
     if (live) {
-        if (tet < 0) w = 0.0; // S1: left the domain -> frozen (particles.cu:334-338)
+        if (tet < 0) { w = 0.0; frz = 1u; } // S1: left the domain -> frozen (particles.cu:334-338)
         else {
             f32_load(m, tet, f);
             org = first_origin<CF>(m, tet, f);
@@ -849,7 +883,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
             disp = D3{ __dsub_rn(__fma_rn(sp.dt, u0.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, u0.y, P.y), P.y),
                        __dsub_rn(__fma_rn(sp.dt, u0.z, P.z), P.z) };
             if (RNG != CPF_RNG_NONE) {
-                const float *x = xi + s * (3 * NT);
+                const Xi *x = xi + s * (3 * NT);
                 disp.x = __fma_rn((double)x[0], sp.randDisp, disp.x);
                 disp.y = __fma_rn((double)x[NT], sp.randDisp, disp.y);
                 disp.z = __fma_rn((double)x[2 * NT], sp.randDisp, disp.z);
@@ -878,6 +912,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
     }
     if (live) {
         if (CPF_LEAN_SMEM_STATE) w = sd[3 * NT];
+        if constexpr (STATEFUL) { if (deferAt < 0 && s >= sp.nSub) pv.rng[i] = *stash; }
         st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
         st_stream_i(pv.tet + i, tet);
         if (sp.writeVel && cell >= 0 && deferAt < 0) {
@@ -892,58 +927,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
         qb = __shfl_sync(0xffffffffu, qb, 0);
         if (deferAt >= 0) sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
     }
-    flush_counters(sp, 0u, 0u, hops, (unsigned)s);
-}
-
-// k_fast_inline<RNG,QMODE>: same fast walk with the exact tail inline.  QMODE 0 (thread i = particle
-// i) serves the stateful XORWOW stream, whose generator state cannot be rewound for a deferred
-// sub-step; QMODE 2 finishes whatever is still queued after the last ping-pong round.
-template <int RNG, int QMODE>
-__global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_fast_inline(const MeshView m, const ParticleView pv, const StepParams sp)
-{
-    Tally ty{ 0u, 0u, 0u, 0u };
-    unsigned nsteps = 0;
-    const long long total = QMODE ? (long long)*sp.countIn : pv.n;
-    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
-        long long i = slot;
-        int s0 = 0;
-        if (QMODE) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y; }
-        if (s0 >= sp.nSub) continue;
-        const double4 p4 = ld_stream4(pv.pos + i);
-        int tet = ld_stream_i(pv.tet + i);
-        D3 P{ p4.x, p4.y, p4.z };
-        double w = p4.w;
-        if (w == 0.0) continue;
-        Rng<RNG> rng;
-        rng.open(pv, i, sp);
-        Fast32 f;
-        D3 O{ 0.0, 0.0, 0.0 }, vel{ 0.0, 0.0, 0.0 };
-        bool velValid = false;
-        int org = -1;
-        if (tet >= 0) { f32_load(m, tet, f); org = first_origin<CPF_CFV_RUNTIME>(m, tet, f); O = ld_vertex(m.vpos, org); }
-        for (int s = s0; s < sp.nSub; ++s) {
-            if (w == 0.0) break;
-            if (tet < 0) { w = 0.0; break; }
-            const int cell = m.tetcell ? __ldg(m.tetcell + tet) : org - m.nPoints;
-            const D3 disp = displacement<RNG>(m, sp, rng, s, cell, P, vel);
-            velValid = true;
-            nsteps++;
-            const int r = walk_fast32(m, f, O, org, tet, P, disp, ty.hops);
-            if (r >= 0) {
-                tet = r;
-                P = xadd(P, disp);
-            } else {
-                ty.exact++;
-                tail_convex_exact(m, P, disp, vel, tet, w, sp.reflect, ty);
-                if (tet >= 0) { f32_load(m, tet, f); org = first_origin<CPF_CFV_RUNTIME>(m, tet, f); O = ld_vertex(m.vpos, org); }
-            }
-        }
-        rng.close(pv, i);
-        st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
-        st_stream_i(pv.tet + i, tet);
-        if (sp.writeVel && velValid) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
-    }
-    flush_counters(sp, ty.refl, ty.exact, ty.hops, nsteps, ty.esc);
+    flush_counters(sp, 0u, 0u, hops, (unsigned)s, 0u, frz);
 }
 
 // Point values from the cell field (OpenFOAM volPointInterpolation, interior weights 1/|p - C|),
@@ -989,23 +973,23 @@ int launch_point_interp(cpf_context *ctx)
 
 // src/initCuda.H:184-199: the one cudaAdvect right after seeding; its only lasting effect is to
 // deactivate particles whose initial location failed (tet < 0) and to fill vel for VTU 0.
-__global__ void __launch_bounds__(128) k_initial_advect(const MeshView m, const ParticleView pv)
+__global__ void __launch_bounds__(128) k_initial_advect(const MeshView m, const ParticleView pv, unsigned long long *counters)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pv.n) return;
     double4 p4 = pv.pos[i];
     if (p4.w == 0.0) return;
     const int tet = pv.tet[i];
-    if (tet < 0) { p4.w = 0.0; pv.pos[i] = p4; return; }
+    if (tet < 0) { p4.w = 0.0; pv.pos[i] = p4; atomicAdd(counters + CNT_FROZEN, 1ull); return; }
     const int4 v = ld_int4(m.tetv, tet);
     const int cell = tet_cell(m, tet, v);
     pv.vel[i] = vel4(ld_ucell(m, cell));
 }
 
-__global__ void k_init_rng(curandState_t *st, long long n, unsigned long long seed)
+__global__ void k_init_rng(curandState_t *st, long long n, unsigned long long seed, unsigned long long idBase)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) curand_init(seed, (unsigned long long)i, 0ull, &st[i]); // particles.cu:537
+    if (i < n) curand_init(seed, idBase + (unsigned long long)i, 0ull, &st[i]); // particles.cu:537, subsequence = global particle id
 }
 
 template <int RNG> __global__ void k_debug_normals(const ParticleView pv, const StepParams sp, double *xi)
@@ -1030,19 +1014,23 @@ template <int RNG> __global__ void k_debug_normals(const ParticleView pv, const 
     default: { constexpr int R = CPF_RNG_NONE; CALL; } break;                   \
     }
 
-// Filtered policy (stateless RNG, ConvexPoly locator, cell-constant velocity), integrator I:
+// Filtered policy (ConvexPoly locator), random walk R, integrator I, interpolation V:
 //   lean fast kernel over all particles -> wall-capable fast pass over its refusals
-//   -> [one exact sub-step -> resume fast (wall-capable)]* (Euler only, CPF_MAX_ROUNDS) -> exact finisher.
-template <int I, int V>
-static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleView &pv, const StepParams &sp, dim3 grid, int nSub, int rng)
+//   -> [one exact sub-step -> resume fast (wall-capable)]* (Euler, stateless R only, CPF_MAX_ROUNDS) -> exact finisher.
+// With the stateful XORWOW stream a kernel commits the generator state only for particles that finish their chunk in it;
+// every later kernel re-draws from the chunk-start state (Rng::skip / staged deviates), so the stream stays the reference's.
+template <int R, int I, int V>
+static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleView &pv, const StepParams &sp, dim3 grid, int nSub)
 {
+    typedef typename Rng<R>::Xi Xi;
+    constexpr bool STATEFUL = Rng<R>::STATEFUL;
     cudaStream_t st = ctx->stream;
-    const int rounds = (I == CPF_EULER && !V) ? std::max(0, std::min(CPF_MAX_ROUNDS, nSub - 1)) : 0;
+    const int rounds = (I == CPF_EULER && !V && !STATEFUL) ? std::max(0, std::min(CPF_MAX_ROUNDS, nSub - 1)) : 0;
     CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * 64, st));
     // queue kernels: one resident wave on the 148 SMs of a B200 (grid-stride loops inside)
     const dim3 wgrid(std::min<unsigned>(grid.x, 148u * CPF_WALL_MIN_BLOCKS));
     const dim3 egrid(std::min<unsigned>(grid.x, 148u * 8u));
-    const size_t xiBytes = rng == CPF_RNG_PHILOX ? sizeof(float) * 3 * 128 * (size_t)nSub : 0;
+    const size_t xiBytes = R == CPF_RNG_NONE ? 0 : sizeof(Xi) * 3 * 128 * (size_t)nSub + (STATEFUL ? sizeof(curandState_t) * 128 : 0);
     auto queue_params = [&](int q, bool withOut) { // queue q lives in d_queue[q & 1], its length in d_queue_count[q]
         StepParams x = sp;
         x.queueIn = ctx->d_queue[q & 1]; x.countIn = ctx->d_queue_count + q;
@@ -1051,43 +1039,49 @@ static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleVi
     };
     auto fast_queue_pass = [&](int q) {
         const StepParams b = queue_params(q, true);
-        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 2, 1, I, V><<<wgrid, 128, xiBytes, st>>>(m, pv, b);
-        else k_fast<CPF_RNG_NONE, 2, 1, I, V><<<wgrid, 128, 0, st>>>(m, pv, b);
+        k_fast<R, 2, 1, I, V><<<wgrid, 128, xiBytes, st>>>(m, pv, b);
         ctx->launches++;
     };
     StepParams a = sp;
     a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
     if constexpr (I == CPF_EULER && !V) {
-        const bool cfv = m.tetcell == nullptr;
         const dim3 lgrid((unsigned)((pv.n + CPF_LEAN_THREADS - 1) / CPF_LEAN_THREADS));
-        const size_t lb = CPF_LEAN_SMEM_BYTES(nSub, rng == CPF_RNG_PHILOX);
-        if (rng == CPF_RNG_PHILOX) { if (cfv) k_lean<CPF_RNG_PHILOX, true><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a); else k_lean<CPF_RNG_PHILOX, false><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a); }
-        else { if (cfv) k_lean<CPF_RNG_NONE, true><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a); else k_lean<CPF_RNG_NONE, false><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a); }
+        const size_t lb = CPF_LEAN_SMEM_BYTES(nSub, R == CPF_RNG_NONE ? 0 : sizeof(Xi), STATEFUL);
+        if (m.tetcell == nullptr) k_lean<R, true><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
+        else k_lean<R, false><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
     } else {
-        if (rng == CPF_RNG_PHILOX) k_fast<CPF_RNG_PHILOX, 0, 0, I, V><<<grid, 128, xiBytes, st>>>(m, pv, a);
-        else k_fast<CPF_RNG_NONE, 0, 0, I, V><<<grid, 128, 0, st>>>(m, pv, a);
+        k_fast<R, 0, 0, I, V><<<grid, 128, xiBytes, st>>>(m, pv, a);
     }
     ctx->launches++;
     int q = 0;
     if (CPF_WALL_PASS) fast_queue_pass(q++);
     for (int r = 0; r < rounds; ++r) {
         const StepParams e = queue_params(q, false);
-        if (rng == CPF_RNG_PHILOX) k_exact_convex<CPF_RNG_PHILOX, 1><<<egrid, 128, 0, st>>>(m, pv, e);
-        else k_exact_convex<CPF_RNG_NONE, 1><<<egrid, 128, 0, st>>>(m, pv, e);
+        k_exact_convex<R, 1><<<egrid, 128, 0, st>>>(m, pv, e);
         ctx->launches++;
         fast_queue_pass(q++);
     }
     const StepParams z = queue_params(q, false);
-    if (I == CPF_EULER && !V) {
-        if (rng == CPF_RNG_PHILOX) k_exact_convex<CPF_RNG_PHILOX, 2><<<egrid, 128, 0, st>>>(m, pv, z);
-        else k_exact_convex<CPF_RNG_NONE, 2><<<egrid, 128, 0, st>>>(m, pv, z);
-    } else { // RK2 / RK4 / vertex interpolation: the remaining sub-steps of what is still queued, all in the reference's arithmetic
-        if (rng == CPF_RNG_PHILOX) k_general<CPF_RNG_PHILOX, 2><<<egrid, 128, 0, st>>>(m, pv, z);
-        else k_general<CPF_RNG_NONE, 2><<<egrid, 128, 0, st>>>(m, pv, z);
-    }
+    if (I == CPF_EULER && !V) k_exact_convex<R, 2><<<egrid, 128, 0, st>>>(m, pv, z);
+    else k_general<R, 2><<<egrid, 128, 0, st>>>(m, pv, z); // RK2 / RK4 / vertex interpolation: the rest in the reference's arithmetic
     ctx->launches++;
     return CPF_OK;
 }
+
+template <int R>
+static int launch_filtered_rng(cpf_context *ctx, const MeshView &m, const ParticleView &pv, const StepParams &sp, dim3 grid, int nSub)
+{
+    const bool vert = ctx->cfg.interp == CPF_INTERP_VERTEX;
+    if (ctx->cfg.integrator == CPF_RK2) return vert ? launch_filtered<R, CPF_RK2, 1>(ctx, m, pv, sp, grid, nSub) : launch_filtered<R, CPF_RK2, 0>(ctx, m, pv, sp, grid, nSub);
+    if (ctx->cfg.integrator == CPF_RK4) return vert ? launch_filtered<R, CPF_RK4, 1>(ctx, m, pv, sp, grid, nSub) : launch_filtered<R, CPF_RK4, 0>(ctx, m, pv, sp, grid, nSub);
+    return vert ? launch_filtered<R, CPF_EULER, 1>(ctx, m, pv, sp, grid, nSub) : launch_filtered<R, CPF_EULER, 0>(ctx, m, pv, sp, grid, nSub);
+}
+
+// most sub-steps one launch sequence may fuse: the staged deviates of a chunk must fit the 48 KB of shared memory a
+// kernel gets without opting in (3 x 4 B per sub-step and thread, stateless streams; 3 x 8 B + the 48-byte state, XORWOW)
+int max_fused_substeps(const cpf_context *ctx) { return ctx->cfg.rng == CPF_RNG_XORWOW ? 14 : 16; }
+// library default (cfg.fuse_substeps == 0); XORWOW: 10 sub-steps = 36 KB of staged fp64 deviates + states, 6 CTAs per SM
+int default_fused_substeps(const cpf_context *ctx) { return ctx->cfg.rng == CPF_RNG_XORWOW ? 10 : 16; }
 
 int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
 {
@@ -1102,6 +1096,7 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
     sp.writeVel = writeVel ? 1 : 0;
     sp.seed = ctx->cfg.seed;
     sp.step0 = ctx->step_index;
+    sp.idBase = ctx->id_base;
     sp.counters = ctx->d_counters;
     sp.queueIn = sp.queueOut = nullptr;
     sp.countIn = sp.countOut = nullptr;
@@ -1124,25 +1119,17 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
     }
     sp.integrator = ctx->cfg.integrator;
     sp.interp = ctx->cfg.interp;
-    const bool filteredOk = ctx->cfg.locator == CPF_LOCATOR_CONVEX && ctx->cfg.path == CPF_PATH_FILTERED && ctx->filter_ok && rng != CPF_RNG_XORWOW;
-    if ((ctx->cfg.interp != CPF_INTERP_TET || ctx->cfg.integrator != CPF_EULER) && !filteredOk) {
-        CPF_RNG_SWITCH(rng, (k_general<R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
-        ctx->launches++;
-    } else if (ctx->cfg.locator == CPF_LOCATOR_BARY) {
+    const bool filteredOk = ctx->cfg.locator == CPF_LOCATOR_CONVEX && ctx->cfg.path == CPF_PATH_FILTERED && ctx->filter_ok;
+    if (ctx->cfg.locator == CPF_LOCATOR_BARY) {
         CPF_RNG_SWITCH(rng, (k_exact<CPF_LOCATOR_BARY, R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
         ctx->launches++;
-    } else if (ctx->cfg.path == CPF_PATH_EXACT || !ctx->filter_ok) {
-        CPF_RNG_SWITCH(rng, (k_exact_convex<R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
-        ctx->launches++;
-    } else if (rng == CPF_RNG_XORWOW) {
-        k_fast_inline<CPF_RNG_XORWOW, 0><<<grid, 128, 0, st>>>(m, pv, sp);
+    } else if (!filteredOk) {
+        if (ctx->cfg.interp != CPF_INTERP_TET || ctx->cfg.integrator != CPF_EULER) { CPF_RNG_SWITCH(rng, (k_general<R, 0><<<grid, 128, 0, st>>>(m, pv, sp))); }
+        else { CPF_RNG_SWITCH(rng, (k_exact_convex<R, 0><<<grid, 128, 0, st>>>(m, pv, sp))); }
         ctx->launches++;
     } else {
-        int rc;
-        const bool vert = ctx->cfg.interp == CPF_INTERP_VERTEX;
-        if (ctx->cfg.integrator == CPF_RK2) rc = vert ? launch_filtered<CPF_RK2, 1>(ctx, m, pv, sp, grid, nSub, rng) : launch_filtered<CPF_RK2, 0>(ctx, m, pv, sp, grid, nSub, rng);
-        else if (ctx->cfg.integrator == CPF_RK4) rc = vert ? launch_filtered<CPF_RK4, 1>(ctx, m, pv, sp, grid, nSub, rng) : launch_filtered<CPF_RK4, 0>(ctx, m, pv, sp, grid, nSub, rng);
-        else rc = vert ? launch_filtered<CPF_EULER, 1>(ctx, m, pv, sp, grid, nSub, rng) : launch_filtered<CPF_EULER, 0>(ctx, m, pv, sp, grid, nSub, rng);
+        int rc = CPF_OK;
+        CPF_RNG_SWITCH(rng, (rc = launch_filtered_rng<R>(ctx, m, pv, sp, grid, nSub)));
         if (rc) return rc;
     }
     if (ctx->profiling) {
@@ -1157,7 +1144,7 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
 int launch_initial_advect(cpf_context *ctx, double)
 {
     if (ctx->n == 0) return CPF_OK;
-    k_initial_advect<<<(unsigned)((ctx->n + 127) / 128), 128, 0, ctx->stream>>>(mesh_view(ctx), particle_view(ctx));
+    k_initial_advect<<<(unsigned)((ctx->n + 127) / 128), 128, 0, ctx->stream>>>(mesh_view(ctx), particle_view(ctx), ctx->d_counters);
     ctx->launches++;
     CPF_CUDA(ctx, cudaGetLastError());
     return CPF_OK;
@@ -1169,7 +1156,7 @@ int launch_init_rng(cpf_context *ctx)
         if (!ctx->d_rng[b]) CPF_CUDA(ctx, cudaMalloc(&ctx->d_rng[b], sizeof(curandState_t) * (size_t)ctx->n));
     // states are indexed by ORIGINAL particle id; only valid before any sort or via pid scatter
     if (ctx->permuted) return fail(ctx, CPF_ERR_INVALID, "cpf_init_rng must run before particles are sorted");
-    k_init_rng<<<(unsigned)((ctx->n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_rng[ctx->pcur], ctx->n, ctx->cfg.seed);
+    k_init_rng<<<(unsigned)((ctx->n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_rng[ctx->pcur], ctx->n, ctx->cfg.seed, ctx->id_base);
     ctx->launches++;
     CPF_CUDA(ctx, cudaGetLastError());
     ctx->rng_ready = true;
@@ -1182,6 +1169,7 @@ int launch_debug_normals(cpf_context *ctx, double *d_xi)
     StepParams sp{};
     sp.seed = ctx->cfg.seed;
     sp.step0 = ctx->step_index;
+    sp.idBase = ctx->id_base;
     const unsigned grid = (unsigned)((ctx->n + 127) / 128);
     if (ctx->cfg.rng == CPF_RNG_XORWOW) {
         if (!ctx->rng_ready) { int rc = launch_init_rng(ctx); if (rc) return rc; }

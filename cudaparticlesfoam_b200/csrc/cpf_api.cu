@@ -40,6 +40,7 @@ static void free_particles(cpf_context *ctx)
     cudaFree(ctx->d_queue[0]); cudaFree(ctx->d_queue[1]); cudaFree(ctx->d_queue_count);
     ctx->d_queue[0] = ctx->d_queue[1] = nullptr; ctx->d_queue_count = nullptr;
     ctx->n = 0; ctx->pcur = 0; ctx->permuted = false; ctx->rng_ready = false; ctx->have_tets = false;
+    ctx->statBaseValid = ctx->statScanQueued = false; // the next statistics request scans the new particle set
 }
 
 // solver layout [nCells][3] -> (ux,uy,uz,0) per cell: the hot kernels fetch a cell velocity with ONE 256-bit load
@@ -48,6 +49,39 @@ __global__ void k_pack_velocity(long long nCells, const double *__restrict__ U, 
 {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c < nCells) out[c] = make_double4(U[3 * c], U[3 * c + 1], U[3 * c + 2], 0.0);
+}
+
+// Continuous injection: every inactive particle (escaped through an ESCAPE patch, frozen outside the domain) is put back
+// at a reproducible uniform position of the box, active, tet id unknown (-1: cpf_relocate_lost's BVH pass finds it).
+// The position depends on (seed, sub-step index, GLOBAL particle id) only, not on the storage order.
+__global__ void k_reseed_inactive(long long n, double4 *__restrict__ pos, int *__restrict__ tet, const int *__restrict__ pid,
+                                  double4 *__restrict__ vel, double3 lo, double3 hi, unsigned long long key, unsigned long long idBase,
+                                  unsigned long long *__restrict__ count)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    if (i < n) {
+        const double w = pos[i].w;
+        if (w == 0.0) {
+            hit = true;
+            unsigned long long z = key + (idBase + (unsigned long long)pid[i]) * 0x9E3779B97F4A7C15ull;
+            double u[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                z += 0x9E3779B97F4A7C15ull;
+                unsigned long long x = z;
+                x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+                x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+                x ^= x >> 31;
+                u[c] = (double)(x >> 11) * (1.0 / 9007199254740992.0);
+            }
+            pos[i] = make_double4(lo.x + u[0] * (hi.x - lo.x), lo.y + u[1] * (hi.y - lo.y), lo.z + u[2] * (hi.z - lo.z), 1.0);
+            tet[i] = -1;
+            vel[i] = make_double4(0.0, 0.0, 0.0, -1.0);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(count, (unsigned long long)__popc(m));
 }
 
 __global__ void k_iota_fill(long long n, int *pid0, int *tet0)
@@ -104,8 +138,8 @@ void cpf_default_config(cpf_config *cfg)
     cfg->rng = CPF_RNG_XORWOW;          // usingBrownianMotion = true, src/initCuda.H:66
     cfg->reflect_wall = 1;              // src/initCuda.H:67
     cfg->path = CPF_PATH_FILTERED;
-    cfg->sort_interval = 0;
-    cfg->fuse_substeps = 0;
+    cfg->sort_interval = 50;            // as the glue's sortInterval default (src/initCuda.H)
+    cfg->fuse_substeps = 0;             // library default: 16 sub-steps per launch sequence (10 with the XORWOW stream)
     cfg->dt = 1e-4;                     // src/initCuda.H:55
     cfg->diffusion_coeff = 5.7e-6;      // src/initCuda.H:56
     cfg->seed = 1591593751ull;          // cuda/particles.cu:544
@@ -188,6 +222,8 @@ int cpf_destroy(cpf_context *ctx)
     cudaStreamSynchronize(ctx->stream);
     free_particles(ctx);
     release_mesh(ctx);
+    comm_release(ctx);
+    stats_release(ctx);
     cudaFree(ctx->d_counters); cudaFree(ctx->d_sort_hist); cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evCopy); cudaEventDestroy(ctx->evRead[0]); cudaEventDestroy(ctx->evRead[1]);
@@ -429,6 +465,29 @@ int cpf_update_velocity(cpf_context *ctx, const double *U, int on_device)
     return CPF_OK;
 }
 
+} // extern "C"
+
+namespace cpf {
+// second half of a field refresh whose data already sits in a device staging buffer filled ON THE COPY STREAM
+// (cpf_comm.cu: NCCL broadcast / slice exchange): repack there, then make the compute stream wait
+int update_velocity_staged(cpf_context *ctx, const double *d_stage)
+{
+    const int nb = 1 - ctx->ucur;
+    CPF_CUDA(ctx, cudaEventRecord(ctx->evRead[ctx->ucur], ctx->stream));
+    CPF_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->evRead[nb], 0));
+    k_pack_velocity<<<(unsigned)((ctx->nCells + 255) / 256), 256, 0, ctx->copyStream>>>(ctx->nCells, d_stage, ctx->d_ucell[nb]);
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+    CPF_CUDA(ctx, cudaEventRecord(ctx->evCopy, ctx->copyStream));
+    CPF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evCopy, 0));
+    ctx->ucur = nb;
+    if (ctx->cfg.interp == CPF_INTERP_VERTEX && ctx->d_pc_off) return launch_point_interp(ctx);
+    return CPF_OK;
+}
+} // namespace cpf
+
+extern "C" {
+
 int cpf_update_vertex_velocity(cpf_context *ctx, const double *Uvert, int on_device)
 {
     if (!ctx || !ctx->have_mesh || !Uvert) return fail(ctx, CPF_ERR_INVALID, "cpf_update_vertex_velocity: no mesh or null field");
@@ -453,20 +512,29 @@ int cpf_set_particles(cpf_context *ctx, long long n, const double *xyzw)
     return CPF_OK;
 }
 
-int cpf_seed_box(cpf_context *ctx, long long n, const double lo[3], const double hi[3], unsigned long long seed)
+int cpf_seed_box_slice(cpf_context *ctx, long long first, long long count, const double lo[3], const double hi[3], unsigned long long seed)
 {
-    if (!ctx || n < 0 || !lo || !hi) return fail(ctx, CPF_ERR_INVALID, "cpf_seed_box: bad arguments");
-    std::vector<double> p((size_t)n * 4);
+    if (!ctx || first < 0 || count < 0 || !lo || !hi) return fail(ctx, CPF_ERR_INVALID, "cpf_seed_box_slice: bad arguments");
+    std::vector<double> p;
+    try { p.resize((size_t)count * 4); } catch (const std::bad_alloc &) { return fail(ctx, CPF_ERR_NOMEM, "cpf_seed_box_slice: out of host memory"); }
     for (int ax = 0; ax < 3; ++ax) {
         const unsigned long long key = splitmix64(seed ^ ((unsigned long long)ax * 0xD1342543DE82EF95ull));
-        for (long long i = 0; i < n; ++i) {
-            const unsigned long long bits = splitmix64((unsigned long long)i * 0x2545F4914F6CDD1Dull + key);
+        for (long long k = 0; k < count; ++k) {
+            const unsigned long long bits = splitmix64((unsigned long long)(first + k) * 0x2545F4914F6CDD1Dull + key); // keyed by GLOBAL index
             const double u = (double)(bits >> 11) * (1.0 / 9007199254740992.0);
-            p[(size_t)i * 4 + ax] = lo[ax] + u * (hi[ax] - lo[ax]); // lower + r*(upper-lower), particles.cu:88-91
+            p[(size_t)k * 4 + ax] = lo[ax] + u * (hi[ax] - lo[ax]); // lower + r*(upper-lower), particles.cu:88-91
         }
     }
-    for (long long i = 0; i < n; ++i) p[(size_t)i * 4 + 3] = 1.0;
-    return cpf_set_particles(ctx, n, p.data());
+    for (long long k = 0; k < count; ++k) p[(size_t)k * 4 + 3] = 1.0;
+    int rc = cpf_set_particles(ctx, count, p.data());
+    if (rc) return rc;
+    ctx->id_base = (unsigned long long)first;
+    return CPF_OK;
+}
+
+int cpf_seed_box(cpf_context *ctx, long long n, const double lo[3], const double hi[3], unsigned long long seed)
+{
+    return cpf_seed_box_slice(ctx, 0, n, lo, hi, seed);
 }
 
 int cpf_set_tets(cpf_context *ctx, const int *tet)
@@ -495,6 +563,35 @@ int cpf_relocate_lost(cpf_context *ctx)
     return locate_particles(ctx, true);
 }
 
+int cpf_reseed_inactive(cpf_context *ctx, const double lo[3], const double hi[3], unsigned long long seed, long long *nReseeded)
+{
+    if (!ctx || !lo || !hi) return fail(ctx, CPF_ERR_INVALID, "cpf_reseed_inactive: bad arguments");
+    if (!ctx->have_mesh || !ctx->have_tets) return fail(ctx, CPF_ERR_INVALID, "cpf_reseed_inactive: mesh and located particles are required");
+    if (nReseeded) *nReseeded = 0;
+    if (ctx->n == 0) return CPF_OK;
+    cudaSetDevice(ctx->device);
+    int rc = ensure_scratch(ctx, 64);
+    if (rc) return rc;
+    unsigned long long *d_n = (unsigned long long *)ctx->d_scratch;
+    CPF_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), ctx->stream));
+    const int a = ctx->pcur;
+    k_reseed_inactive<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n, ctx->d_pos[a], ctx->d_tet[a], ctx->d_pid[a], ctx->d_vel[a],
+                                                                               make_double3(lo[0], lo[1], lo[2]), make_double3(hi[0], hi[1], hi[2]),
+                                                                               splitmix64(seed ^ ctx->step_index), ctx->id_base, d_n);
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+    rc = locate_particles(ctx, true); // BVH location of exactly the particles just re-seeded (active, negative tet id)
+    if (rc) return rc;
+    ctx->statBaseValid = ctx->statScanQueued = false; // the counters no longer explain n_active: the next statistics request scans
+    if (nReseeded) {
+        unsigned long long h = 0;
+        CPF_CUDA(ctx, cudaMemcpyAsync(&h, d_n, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *nReseeded = (long long)h;
+    }
+    return CPF_OK;
+}
+
 int cpf_init_rng(cpf_context *ctx)
 {
     if (!ctx || ctx->n == 0) return fail(ctx, CPF_ERR_INVALID, "cpf_init_rng: no particles");
@@ -518,14 +615,17 @@ int cpf_substeps(cpf_context *ctx, int n, double dt)
         return fail(ctx, CPF_ERR_INVALID, "vertex interpolation: no vertex field (cpf_update_velocity after an upload with interp = VERTEX, or cpf_update_vertex_velocity)");
     cudaSetDevice(ctx->device);
     CPF_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    const int fuse = std::min(ctx->cfg.fuse_substeps > 0 ? ctx->cfg.fuse_substeps : 1, 16); // k_fast stages 3 floats per fused sub-step in smem
+    // cfg.fuse_substeps == 0: library default; the glue chunks at save boundaries, so fusing never skips an output
+    const int fuse = std::min(ctx->cfg.fuse_substeps > 0 ? ctx->cfg.fuse_substeps : default_fused_substeps(ctx), max_fused_substeps(ctx));
     int done = 0;
     while (done < n) {
         if (ctx->cfg.sort_interval > 0 && ctx->since_sort >= ctx->cfg.sort_interval) {
             int rc = sort_particles_by_cell(ctx);
             if (rc) return rc;
         }
-        int k = std::min(fuse, n - done);
+        // balanced chunks: 10 sub-steps with at most 8 per launch sequence run as 5 + 5, not 8 + 2
+        const int left = n - done;
+        int k = (left + (left + fuse - 1) / fuse - 1) / ((left + fuse - 1) / fuse);
         if (ctx->cfg.sort_interval > 0) k = std::min(k, std::max(1, ctx->cfg.sort_interval - ctx->since_sort));
         int rc = launch_substeps(ctx, k, dt, done + k == n);
         if (rc) return rc;
@@ -610,11 +710,32 @@ int cpf_download_cells(cpf_context *ctx, int *cell)
     return CPF_OK;
 }
 
+int cpf_stats_request(cpf_context *ctx, int full)
+{
+    if (!ctx) return CPF_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return stats_request(ctx, full != 0);
+}
+
+int cpf_stats_collect(cpf_context *ctx, cpf_stats *out)
+{
+    if (!ctx || !out) return CPF_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return stats_collect(ctx, out);
+}
+
 int cpf_stats_get(cpf_context *ctx, cpf_stats *out)
 {
     if (!ctx || !out) return CPF_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    return reduce_stats(ctx, out);
+    cpf_stats tmp;
+    while (ctx->statHead != ctx->statTail) { // results nobody collected: drop them, oldest first
+        int rc = stats_collect(ctx, &tmp);
+        if (rc) return rc;
+    }
+    int rc = stats_request(ctx, true);
+    if (rc) return rc;
+    return stats_collect(ctx, out);
 }
 
 long long cpf_num_particles(cpf_context *ctx) { return ctx ? ctx->n : 0; }
@@ -669,7 +790,7 @@ int cpf_write_vtu(cpf_context *ctx, const char *dir, unsigned step)
     fprintf(fp, "<DataArray NumberOfComponents='1' type='Int32' Name='ParticleType' format='ascii'>\n");
     for (long long i = 0; i < n; ++i) fprintf(fp, "%d\n", (int)p[4 * i + 3]);
     fprintf(fp, "</DataArray>\n<DataArray NumberOfComponents='1' type='Int32' Name='ParticleID' format='ascii'>\n");
-    for (long long i = 0; i < n; ++i) fprintf(fp, "%lld\n", i);
+    for (long long i = 0; i < n; ++i) fprintf(fp, "%lld\n", (long long)ctx->id_base + i); // global id (one rank per GPU: index ranges of one cloud)
     fprintf(fp, "</DataArray>\n<DataArray NumberOfComponents='1' type='Int32' Name='ParticleTetID' format='ascii'>\n");
     for (long long i = 0; i < n; ++i) fprintf(fp, "%d\n", tet[(size_t)i]);
     fprintf(fp, "</DataArray>\n<DataArray NumberOfComponents='1' type='Int32' Name='ConvexTetID' format='ascii'>\n");

@@ -542,19 +542,4 @@ CPF_DEV bool wall_reflect_on_path(const MeshView &m, int startTet, unsigned path
     return true;
 }
 
-// Whole walk of one sub-step (k_fast_inline).  Returns the final tet (f then holds its record, O its
-// origin) or CPF_NEED_EXACT.
-CPF_DEV int walk_fast32(const MeshView &m, Fast32 &f, D3 &O, int &org, int tet0, D3 P0, D3 disp, unsigned &hops)
-{
-    WalkF ws;
-    walkf_begin(ws, O, P0, disp, tet0, org, true);
-    for (int it = 0; it < 48; ++it) {
-        hops++;
-        const int oc = visit_fast32<true, CPF_CFV_RUNTIME>(m, f, O, P0, ws);
-        if (oc == CPF_V_DONE) { org = ws.org; return ws.cur; }
-        if (oc >= CPF_V_REFUSE) break;
-    }
-    return CPF_NEED_EXACT;
-}
-
 } // namespace cpf

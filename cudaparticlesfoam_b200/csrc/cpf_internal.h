@@ -12,7 +12,7 @@
 
 namespace cpf {
 
-enum Counter { CNT_ESCAPED = 0, CNT_REFLECT, CNT_EXACT, CNT_HOPS, CNT_SUBSTEPS, CNT_LOST, CNT_COUNT = 8 };
+enum Counter { CNT_ESCAPED = 0, CNT_REFLECT, CNT_EXACT, CNT_HOPS, CNT_SUBSTEPS, CNT_LOST, CNT_FROZEN, CNT_COUNT = 8 };
 
 struct ParticleView {
     double4 *pos;        // [n] x,y,z,w (w != 0 => active), reference layout (cuda/common.h:26)
@@ -32,6 +32,7 @@ struct StepParams {
     int integrator, interp;
     unsigned long long seed;
     unsigned long long step0; // global sub-step index of the first fused sub-step (Philox counter)
+    unsigned long long idBase; // global id of this context's particle 0 (Philox counter / XORWOW subsequence)
     unsigned long long *counters;
     int2 *queueIn, *queueOut;          // deferral queues: (particle slot, sub-step to resume at)
     unsigned *countIn, *countOut;
@@ -42,7 +43,7 @@ struct BvhLevel { float4 *lo; float4 *hi; long long n; };
 
 } // namespace cpf
 
-namespace cpf { struct OutputState; }
+namespace cpf { struct OutputState; struct CommState; }
 
 struct cpf_context {
     cpf_config cfg;
@@ -102,12 +103,25 @@ struct cpf_context {
     bool rng_ready = false;
     bool have_tets = false;
     unsigned long long step_index = 0; // global sub-step counter
+    unsigned long long id_base = 0;    // global id of particle 0 (cpf_set_particle_id_base): random-walk streams are keyed by global id
+    cpf::CommState *comm = nullptr;    // NCCL communicator + staging (cpf_comm.cu), created by cpf_comm_init
     int since_sort = 0;
     int *d_sort_hist = nullptr;
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
 
     unsigned long long *d_counters = nullptr;
+    // asynchronous statistics (cpf_stats_request / cpf_stats_collect): ring of page-locked slots, one event each
+    static constexpr int STAT_SLOTS = 4, STAT_WORDS = 16;
+    unsigned long long *h_stat = nullptr;      // [STAT_SLOTS][STAT_WORDS] page-locked
+    double *d_stat = nullptr;                  // [STAT_WORDS] device staging (fp64: one NCCL sum reduces it across ranks)
+    cudaEvent_t evStat[STAT_SLOTS] = { nullptr, nullptr, nullptr, nullptr };
+    bool statFull[STAT_SLOTS] = { false, false, false, false };
+    int statHead = 0, statTail = 0;            // requests [statTail, statHead) are outstanding
+    bool statBaseValid = false;                // a full scan has been collected since the particle set last changed
+    bool statScanQueued = false;               // ... or at least requested
+    long long statBaseActive = 0, statBaseNeg = 0, statBaseEsc = 0, statBaseFrz = 0;
+    double statBaseKe = 0.0;
     int2 *d_queue[2] = { nullptr, nullptr }; // [n] ping-pong deferral queues of the filtered policy
     cpf::OutputState *output = nullptr;      // asynchronous VTU writer (cpf_output.cu), created on first use
     unsigned *d_queue_count = nullptr;       // [64]: queue lengths, one per queue of a launch sequence
@@ -140,13 +154,22 @@ int output_wait(cpf_context *ctx);      // drain the asynchronous writer; report
 void output_shutdown(cpf_context *ctx); // drain, join, free
 // cpf_advect.cu
 int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel);
+int max_fused_substeps(const cpf_context *ctx);
+int default_fused_substeps(const cpf_context *ctx);
 int launch_initial_advect(cpf_context *ctx, double dt);
 int launch_debug_normals(cpf_context *ctx, double *d_xi);
 int launch_init_rng(cpf_context *ctx);
 int launch_point_interp(cpf_context *ctx);
+// cpf_api.cu
+int update_velocity_staged(cpf_context *ctx, const double *d_stage);
+// cpf_comm.cu
+int comm_reduce_stats(cpf_context *ctx, double *d_slot, int words);
+void comm_release(cpf_context *ctx);
 // cpf_sort.cu
 int sort_particles_by_cell(cpf_context *ctx);
 int gather_original_order(cpf_context *ctx, double4 *d_pos_out, double4 *d_vel_out, int *d_tet_out);
-int reduce_stats(cpf_context *ctx, cpf_stats *out);
+int stats_request(cpf_context *ctx, bool full);
+int stats_collect(cpf_context *ctx, cpf_stats *out);
+void stats_release(cpf_context *ctx);
 
 } // namespace cpf

@@ -439,6 +439,7 @@ int cpf_checkpoint_load(cpf_context *ctx, const char *path)
     CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_counters, h.counters, sizeof(unsigned long long) * CNT_COUNT, cudaMemcpyHostToDevice, ctx->stream));
     CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->step_index = h.step_index;
+    ctx->statBaseValid = ctx->statScanQueued = false; // counters and particle set replaced: the next statistics request scans
     ctx->since_sort = ctx->cfg.sort_interval > 0 ? ctx->cfg.sort_interval : 0; // re-sort by cell before the next sub-step
     return CPF_OK;
 }

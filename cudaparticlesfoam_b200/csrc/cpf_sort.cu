@@ -123,32 +123,111 @@ __global__ void __launch_bounds__(256) k_stats(long long n, const double4 *__res
     }
 }
 
-int reduce_stats(cpf_context *ctx, cpf_stats *out)
+// slot layout (fp64 on the device so that ONE ncclAllReduce(sum) reduces a slot across ranks; every count is < 2^53)
+enum { ST_N = 0, ST_ACTIVE, ST_NEG, ST_ESC, ST_REFL, ST_EXACT, ST_HOPS, ST_SUB, ST_KE, ST_FRZ, ST_LOST, ST_FULL };
+
+__global__ void k_stats_pack(long long n, const unsigned long long *__restrict__ counters, const unsigned long long *__restrict__ scan,
+                             const double *__restrict__ scanKe, int full, double *__restrict__ out)
 {
-    memset(out, 0, sizeof *out);
-    out->n_particles = ctx->n;
-    int rc = ensure_scratch(ctx, 64);
+    if (threadIdx.x || blockIdx.x) return;
+    out[ST_N] = (double)n;
+    out[ST_ACTIVE] = full ? (double)scan[0] : 0.0;
+    out[ST_NEG] = full ? (double)scan[1] : 0.0;
+    out[ST_KE] = full ? *scanKe : 0.0;
+    out[ST_ESC] = (double)counters[CNT_ESCAPED];
+    out[ST_REFL] = (double)counters[CNT_REFLECT];
+    out[ST_EXACT] = (double)counters[CNT_EXACT];
+    out[ST_HOPS] = (double)counters[CNT_HOPS];
+    out[ST_SUB] = (double)counters[CNT_SUBSTEPS];
+    out[ST_FRZ] = (double)counters[CNT_FROZEN];
+    out[ST_LOST] = (double)counters[CNT_LOST];
+    out[ST_FULL] = full ? 1.0 : 0.0;
+}
+
+static int stats_init(cpf_context *ctx)
+{
+    if (ctx->h_stat) return CPF_OK;
+    CPF_CUDA(ctx, cudaMallocHost(&ctx->h_stat, sizeof(double) * cpf_context::STAT_SLOTS * cpf_context::STAT_WORDS));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_stat, sizeof(double) * cpf_context::STAT_WORDS * cpf_context::STAT_SLOTS));
+    for (int k = 0; k < cpf_context::STAT_SLOTS; ++k) CPF_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evStat[k], cudaEventDisableTiming));
+    return CPF_OK;
+}
+
+void stats_release(cpf_context *ctx)
+{
+    if (ctx->h_stat) cudaFreeHost(ctx->h_stat);
+    cudaFree(ctx->d_stat);
+    for (int k = 0; k < cpf_context::STAT_SLOTS; ++k) if (ctx->evStat[k]) cudaEventDestroy(ctx->evStat[k]);
+    ctx->h_stat = nullptr; ctx->d_stat = nullptr;
+}
+
+// Enqueue one statistics read-back behind everything submitted so far; no host synchronisation.  full: scan the particle
+// arrays (exact n_active / n_negative_tet / kinetic energy at that point); light: the cumulative counters only (64 bytes).
+// With a communicator (cpf_comm_init) the slot is summed over the ranks on the device before it crosses PCIe.
+int stats_request(cpf_context *ctx, bool full)
+{
+    int rc = stats_init(ctx);
+    if (rc) return rc;
+    if (ctx->statHead - ctx->statTail >= cpf_context::STAT_SLOTS) return fail(ctx, CPF_ERR_INVALID, "cpf_stats_request: %d requests outstanding, collect one first", cpf_context::STAT_SLOTS);
+    if (!ctx->statBaseValid && !ctx->statScanQueued) full = true; // nothing to derive the light numbers from yet
+    if (full) ctx->statScanQueued = true;                        // results are collected in order: the scan arrives first
+    const int slot = ctx->statHead % cpf_context::STAT_SLOTS;
+    cudaStream_t st = ctx->stream;
+    rc = ensure_scratch(ctx, 64);
     if (rc) return rc;
     unsigned long long *d_c = (unsigned long long *)ctx->d_scratch;
     double *d_ke = (double *)(d_c + 2);
-    CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 64, ctx->stream));
-    if (ctx->n) {
-        const int a = ctx->pcur;
-        k_stats<<<(unsigned)std::min<long long>((ctx->n + 255) / 256, 148 * 8), 256, 0, ctx->stream>>>(ctx->n, ctx->d_pos[a], ctx->d_tet[a], ctx->d_vel[a], d_c, d_ke);
-        ctx->launches++;
+    if (full) {
+        CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 64, st));
+        if (ctx->n) {
+            const int a = ctx->pcur;
+            k_stats<<<(unsigned)std::min<long long>((ctx->n + 255) / 256, 148 * 8), 256, 0, st>>>(ctx->n, ctx->d_pos[a], ctx->d_tet[a], ctx->d_vel[a], d_c, d_ke);
+            ctx->launches++;
+        }
     }
-    unsigned long long h[3] = { 0, 0, 0 }, cnt[CNT_COUNT] = { 0 };
-    CPF_CUDA(ctx, cudaMemcpyAsync(h, d_c, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-    CPF_CUDA(ctx, cudaMemcpyAsync(cnt, ctx->d_counters, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    out->n_active = (long long)h[0];
-    out->n_negative_tet = (long long)h[1];
-    memcpy(&out->kinetic_energy, &h[2], sizeof(double));
-    out->n_escaped = (long long)cnt[CNT_ESCAPED];
-    out->n_reflections = (long long)cnt[CNT_REFLECT];
-    out->n_exact = (long long)cnt[CNT_EXACT];
-    out->n_hops = (long long)cnt[CNT_HOPS];
-    out->n_substeps = (long long)cnt[CNT_SUBSTEPS];
+    double *d_slot = ctx->d_stat + slot * cpf_context::STAT_WORDS;
+    k_stats_pack<<<1, 32, 0, st>>>(ctx->n, ctx->d_counters, d_c, d_ke, full ? 1 : 0, d_slot);
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+    rc = comm_reduce_stats(ctx, d_slot, cpf_context::STAT_WORDS);
+    if (rc) return rc;
+    CPF_CUDA(ctx, cudaMemcpyAsync(ctx->h_stat + slot * cpf_context::STAT_WORDS, d_slot, sizeof(double) * cpf_context::STAT_WORDS, cudaMemcpyDeviceToHost, st));
+    CPF_CUDA(ctx, cudaEventRecord(ctx->evStat[slot], st));
+    ctx->statFull[slot] = full;
+    ctx->statHead++;
+    return CPF_OK;
+}
+
+// Wait for the OLDEST outstanding request only (a request made one step ago has long arrived: no pipeline bubble).
+int stats_collect(cpf_context *ctx, cpf_stats *out)
+{
+    memset(out, 0, sizeof *out);
+    if (ctx->statHead == ctx->statTail) return fail(ctx, CPF_ERR_INVALID, "cpf_stats_collect: no outstanding cpf_stats_request");
+    const int slot = ctx->statTail % cpf_context::STAT_SLOTS;
+    CPF_CUDA(ctx, cudaEventSynchronize(ctx->evStat[slot]));
+    ctx->statTail++;
+    const double *h = reinterpret_cast<const double *>(ctx->h_stat) + slot * cpf_context::STAT_WORDS;
+    out->n_particles = (long long)h[ST_N];
+    out->n_escaped = (long long)h[ST_ESC];
+    out->n_reflections = (long long)h[ST_REFL];
+    out->n_exact = (long long)h[ST_EXACT];
+    out->n_hops = (long long)h[ST_HOPS];
+    out->n_substeps = (long long)h[ST_SUB];
+    const long long frz = (long long)h[ST_FRZ];
+    if (h[ST_FULL] != 0.0) {
+        out->n_active = (long long)h[ST_ACTIVE];
+        out->n_negative_tet = (long long)h[ST_NEG];
+        out->kinetic_energy = h[ST_KE];
+        ctx->statBaseValid = true;
+        ctx->statBaseActive = out->n_active; ctx->statBaseNeg = out->n_negative_tet; ctx->statBaseKe = out->kinetic_energy;
+        ctx->statBaseEsc = out->n_escaped; ctx->statBaseFrz = frz;
+    } else {
+        // light: every particle that stopped being active since the last scan was counted as an escape or as a freeze
+        out->n_active = ctx->statBaseActive - (out->n_escaped - ctx->statBaseEsc) - (frz - ctx->statBaseFrz);
+        out->n_negative_tet = ctx->statBaseNeg;
+        out->kinetic_energy = ctx->statBaseKe;
+    }
+    out->reserved[0] = h[ST_FULL];
     return CPF_OK;
 }
 

@@ -1,21 +1,15 @@
-"""Host-side multi-GPU plumbing (one process per GPU, torch.distributed).
+"""Host-side helpers for one-rank-per-GPU runs.
 
-The path shards trivially: tracers do not interact, so particles are partitioned by
-contiguous index range, the mesh is replicated, and the only per-step communication is
-  * the solver's cell velocity field: rank 0 -> everyone (NCCL broadcast into a device buffer that
-    `cpf_update_velocity(on_device=1)` consumes on the same stream), and
-  * a fixed-size statistics vector: everyone -> rank 0 (gather) / all (all-reduce).
-The reference funnels everything to the MPI master and a single GPU
-(/root/reference/src/advect.H:59-89, Pstream::gatherList).  Works with the gloo backend on CPU
-tensors too, which is how the CPU test-suite exercises it.
+The multi-GPU DATA plane lives behind the C ABI (csrc/cpf_comm.cu: ncclBroadcast of the cell field, ncclAllReduce of the
+statistics slot, both inside libcpf).  What is left for the host is what the reference's host does with Pstream
+(/root/reference/src/advect.H:59-89, src/initCuda.H:207-270): decide which index range of the particle cloud a rank
+tracks, and carry the 128-byte NCCL id from rank 0 to the others.  torch.distributed (gloo works, no GPU needed) is
+used for that control plane only, which is also how the CPU test-suite exercises it with world_size 2.
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
-
-STAT_KEYS = ("n_particles", "n_active", "n_negative_tet", "n_escaped", "n_reflections", "n_exact", "n_hops", "n_substeps",
-             "kinetic_energy")
 
 
 def world() -> tuple[int, int]:
@@ -33,43 +27,34 @@ def partition(n_total: int, n_ranks: int, rank: int) -> tuple[int, int]:
     return start, base + (1 if rank < extra else 0)
 
 
-def broadcast_field(buf: torch.Tensor, src: int = 0) -> torch.Tensor:
-    """Per-step velocity field fan-out; `buf` is [nCells,3] float64 on every rank (device for NCCL)."""
-    if buf.dtype != torch.float64 or buf.dim() != 2 or buf.shape[1] != 3:
-        raise ValueError("cell field must be float64 [nCells,3]")
-    if world()[1] > 1:
-        dist.broadcast(buf, src=src)
-    return buf
-
-
-def stats_vector(stats: dict, device=None) -> torch.Tensor:
-    return torch.tensor([float(stats.get(k, 0)) for k in STAT_KEYS], dtype=torch.float64, device=device)
-
-
-def reduce_stats(stats: dict, device=None) -> dict:
-    """Sum of every rank's counters, available on all ranks."""
-    v = stats_vector(stats, device)
-    if world()[1] > 1:
-        dist.all_reduce(v, op=dist.ReduceOp.SUM)
-    out = {k: (float(x) if k == "kinetic_energy" else int(round(float(x)))) for k, x in zip(STAT_KEYS, v.tolist())}
+def cell_slices(cells_per_rank) -> list[tuple[int, int]]:
+    """(offset, count) of every rank's cells in the merged global numbering of a decomposed solver run: ranks in order,
+    each rank's cells in its local order (the numbering src/initCuda.H builds when it merges the processor meshes)."""
+    out, off = [], 0
+    for c in cells_per_rank:
+        out.append((off, int(c)))
+        off += int(c)
     return out
 
 
-def gather_stats(stats: dict, device=None, dst: int = 0):
-    """Per-rank counters gathered on `dst` (list of dicts there, None elsewhere)."""
+def share_unique_id(make_id=None, src: int = 0) -> bytes:
+    """rank `src` calls make_id() (cpf_comm_unique_id) and every rank returns the same 128 bytes."""
     rank, n = world()
-    v = stats_vector(stats, device)
     if n == 1:
-        return [dict(zip(STAT_KEYS, v.tolist()))]
-    bucket = [torch.empty_like(v) for _ in range(n)] if rank == dst else None
-    dist.gather(v, bucket, dst=dst)
-    if rank != dst:
-        return None
-    return [dict(zip(STAT_KEYS, b.tolist())) for b in bucket]
+        return make_id()
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if rank == src:
+        raw = make_id()
+        if len(raw) != 128:
+            raise ValueError("the NCCL unique id is 128 bytes")
+        buf = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+    dist.broadcast(buf, src=src)
+    return bytes(buf.tolist())
 
 
-def max_over_ranks(x: float, device=None) -> float:
-    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+def max_over_ranks(x: float) -> float:
+    """Timings are reported as the max over ranks (a CPU tensor: works on gloo; also serves as a barrier)."""
+    t = torch.tensor([float(x)], dtype=torch.float64)
     if world()[1] > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())

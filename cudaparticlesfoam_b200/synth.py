@@ -299,6 +299,84 @@ def honeycomb_mesh(nx: int, ny: int, nz: int, R: float = 0.06, hz: float = 0.1, 
                     lo=points.min(axis=0), hi=points.max(axis=0))
 
 
+def honeycomb_mesh_fast(nx: int, ny: int, nz: int, R: float = 0.06, hz: float = 0.1, jitter: float = 0.08,
+                        seed: int = 1591593751) -> PolyMesh:
+    """The same honeycomb of hexagonal prisms as honeycomb_mesh, built with array operations only (1e7 cells in well under
+    a minute instead of hours): vertices are made unique by sorting quantised coordinates, vertical faces by sorting the
+    2-D edges of the columns.  Vertex / face numbering differs from the loop version; geometry and topology do not."""
+    s3 = np.sqrt(3.0)
+    ang = np.deg2rad(30.0 + 60.0 * np.arange(6))
+    jj, ii = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    cx = (s3 * R * (ii + 0.5 * (jj & 1))).ravel()
+    cy = (1.5 * R * jj).ravel().astype(np.float64)
+    ncol = nx * ny
+    vx = cx[:, None] + R * np.cos(ang)[None, :]
+    vy = cy[:, None] + R * np.sin(ang)[None, :]
+    kx = np.rint(vx / R * 1e6).astype(np.int64) + (1 << 20)
+    ky = np.rint(vy / R * 1e6).astype(np.int64) + (1 << 20)
+    key = (kx << 34) | ky
+    _, first, inv = np.unique(key.ravel(), return_index=True, return_inverse=True)
+    n2 = first.shape[0]
+    cell_v = inv.reshape(ncol, 6).astype(np.int64)
+    pts2d = np.column_stack([vx.ravel()[first], vy.ravel()[first]])
+    use = np.bincount(inv, minlength=n2)
+    r = uniform01(seed, n2, stream=301) * jitter * R
+    th = uniform01(seed, n2, stream=302) * 2.0 * np.pi
+    inner = use == 3  # shared by three columns: reproducible in-plane displacement, all levels alike (faces stay planar)
+    pts2d[inner, 0] += (r * np.cos(th))[inner]
+    pts2d[inner, 1] += (r * np.sin(th))[inner]
+    points = np.empty((n2 * (nz + 1), 3))
+    for k in range(nz + 1):
+        points[n2 * k:n2 * (k + 1), :2] = pts2d
+        points[n2 * k:n2 * (k + 1), 2] = hz * k
+    col = np.arange(ncol, dtype=np.int64)
+    # ---- 2-D edges of the columns -> vertical quads (shared by two columns, or on the zigzag side boundary)
+    ea = cell_v.ravel()
+    eb = np.roll(cell_v, -1, axis=1).ravel()
+    ecol = np.repeat(col, 6)
+    ekey = (np.minimum(ea, eb) << 32) | np.maximum(ea, eb)
+    order = np.lexsort((ecol, ekey))           # by edge, then by column: the first entry of an edge is its lower column
+    ek, ea_s, eb_s, ec_s = ekey[order], ea[order], eb[order], ecol[order]
+    head = np.ones(ek.shape[0], dtype=bool)
+    head[1:] = ek[1:] != ek[:-1]
+    hidx = np.flatnonzero(head)
+    cnt = np.diff(np.append(hidx, ek.shape[0]))
+    e_a, e_b, e_own = ea_s[hidx], eb_s[hidx], ec_s[hidx]     # loop orientation as seen from the owner column
+    e_nbr = np.where(cnt == 2, ec_s[np.minimum(hidx + 1, ek.shape[0] - 1)], -1)
+    vint, vbnd = np.flatnonzero(e_nbr >= 0), np.flatnonzero(e_nbr < 0)
+
+    def quads(sel, k):
+        a, b = e_a[sel], e_b[sel]
+        q = np.full((sel.shape[0], 6), -1, dtype=np.int64)
+        q[:, 0], q[:, 1], q[:, 2], q[:, 3] = a + n2 * k, b + n2 * k, b + n2 * (k + 1), a + n2 * (k + 1)
+        return q
+
+    loops, owner, nbr = [], [], []
+    for k in range(nz):                         # internal vertical faces of layer k
+        loops.append(quads(vint, k)); owner.append(e_own[vint] + ncol * k); nbr.append(e_nbr[vint] + ncol * k)
+    for k in range(1, nz):                      # internal horizontal faces: top of (col, k-1) = bottom of (col, k)
+        loops.append(cell_v + n2 * k); owner.append(col + ncol * (k - 1)); nbr.append(col + ncol * k)
+    loops, owner, nbr = np.concatenate(loops), np.concatenate(owner), np.concatenate(nbr)
+    o = np.lexsort((nbr, owner))                # OpenFOAM's upper-triangular order
+    loops, owner, nbr = loops[o], owner[o], nbr[o]
+    n_int = owner.shape[0]
+    b_loops = [cell_v[:, ::-1] + 0, cell_v + n2 * nz] + [quads(vbnd, k) for k in range(nz)]
+    b_owner = [col, col + ncol * (nz - 1)] + [e_own[vbnd] + ncol * k for k in range(nz)]
+    starts = np.cumsum([n_int, ncol, ncol, vbnd.shape[0] * nz]).astype(np.int32)
+    loops = np.concatenate([loops] + b_loops)
+    owner = np.concatenate([owner] + b_owner)
+    size = (loops >= 0).sum(axis=1)
+    off = np.zeros(loops.shape[0] + 1, dtype=np.int32)
+    off[1:] = np.cumsum(size)
+    verts = loops[loops >= 0].astype(np.int32)  # row-major: the loop order of every face is kept
+    cc = np.empty((ncol * nz, 3))
+    for k in range(nz):
+        cc[ncol * k:ncol * (k + 1), 0], cc[ncol * k:ncol * (k + 1), 1], cc[ncol * k:ncol * (k + 1), 2] = cx, cy, hz * (k + 0.5)
+    return PolyMesh(points=np.ascontiguousarray(points), face_offsets=off, face_verts=verts, owner=owner.astype(np.int32),
+                    neighbour=nbr.astype(np.int32), cell_centres=np.ascontiguousarray(cc), patch_starts=starts,
+                    patch_names=("z-", "z+", "sides"), dims=(nx, ny, nz), lo=points.min(axis=0), hi=points.max(axis=0))
+
+
 def channel_mesh(nx=400, ny=50, nz=50, jitter: float = 0.0) -> PolyMesh:
     """BASELINE config 3/5 mesh: 4 x 1 x 1 channel, inlet x-, outlet x+, walls on +-y/+-z."""
     return box_mesh(nx, ny, nz, lo=(0.0, 0.0, 0.0), hi=(4.0, 1.0, 1.0), jitter=jitter)
@@ -340,6 +418,25 @@ def field_channel(x: np.ndarray, t: float = 0.0, Umax=1.0, eps=0.05, lo=(0, 0, 0
     U[:, 0] = Umax * prof
     U[:, 1] = eps * Umax * np.sin(ph) * np.sin(np.pi * Y)
     U[:, 2] = eps * Umax * np.cos(ph) * np.sin(np.pi * Z)
+    return U
+
+
+def field_recirculation(x: np.ndarray, t: float = 0.0, Umax=1.4, eps=0.05, lo=(0, 0, 0), hi=(4, 1, 1)) -> np.ndarray:
+    """Closed circulation in the x-y plane of a channel-shaped box: stream function psi = A S(X) S(Y), S(s) = sin^2(pi s),
+    so that (u, v) = (d psi/dy, -d psi/dx) is divergence free and vanishes on all four x/y walls -- no through-flow, hence
+    a statistically steady particle distribution under the reference's all-reflecting boundary (a through-flow parks the
+    cloud on the outlet).  A small travelling z-perturbation makes the field differ from step to step."""
+    x = np.asarray(x, dtype=np.float64)
+    Lx, Ly = hi[0] - lo[0], hi[1] - lo[1]
+    X = (x[:, 0] - lo[0]) / Lx
+    Y = (x[:, 1] - lo[1]) / Ly
+    Z = (x[:, 2] - lo[2]) / (hi[2] - lo[2])
+    SX, SY = np.sin(np.pi * X) ** 2, np.sin(np.pi * Y) ** 2
+    A = Umax * Ly / np.pi
+    U = np.empty_like(x)
+    U[:, 0] = A * SX * np.pi * np.sin(2.0 * np.pi * Y) / Ly
+    U[:, 1] = -A * np.pi * np.sin(2.0 * np.pi * X) * SY / Lx
+    U[:, 2] = eps * Umax * np.sin(2.0 * np.pi * (X - t)) * np.sin(np.pi * Z)
     return U
 
 

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define CPF_ABI_VERSION 2
+#define CPF_ABI_VERSION 3
 
 typedef struct cpf_context cpf_context;
 
@@ -31,7 +31,8 @@ enum cpf_status {
     CPF_ERR_CUDA = 2,         /* CUDA runtime error (message via cpf_last_error)                 */
     CPF_ERR_MESH = 3,         /* degenerate / inverted / non-manifold tet mesh                   */
     CPF_ERR_NOMEM = 4,
-    CPF_ERR_NO_DEVICE = 5     /* no CUDA device: there is NO CPU fallback                        */
+    CPF_ERR_NO_DEVICE = 5,    /* no CUDA device: there is NO CPU fallback                        */
+    CPF_ERR_COMM = 6          /* NCCL not loadable / collective failed                            */
 };
 
 /* src/initCuda.H:72 VelocityInterpMethod ("TetVelocity" is what the glue uses;
@@ -62,8 +63,9 @@ typedef struct cpf_config {
     int rng;                  /* enum cpf_rng           (default CPF_RNG_XORWOW, as the glue)     */
     int reflect_wall;         /* src/initCuda.H:67 reflectWall (default 1)                        */
     int path;                 /* enum cpf_path          (default CPF_PATH_FILTERED)               */
-    int sort_interval;        /* re-sort particles by cell every N sub-steps (0 = never)          */
-    int fuse_substeps;        /* max sub-steps fused into one launch (0 = library default)        */
+    int sort_interval;        /* re-sort particles by cell every N sub-steps (0 = never; default 50) */
+    int fuse_substeps;        /* max sub-steps fused into one launch sequence (0 = library default: 16,
+                               * 10 with the XORWOW stream; clamped to 16 / 14)                      */
     double dt;                /* "dt" Lagrangian step (default 1e-4)                              */
     double diffusion_coeff;   /* "diffusionCoeff" (default 5.7e-6)                                */
     unsigned long long seed;  /* RNG seed (default 1591593751, cuda/particles.cu:544)             */
@@ -141,6 +143,10 @@ int cpf_update_vertex_velocity(cpf_context *ctx, const double *Uvert, int on_dev
 /* cudaInitParticles (cuda/particles.cu:100-108) with an explicit, reproducible host-side stream */
 int cpf_seed_box(cpf_context *ctx, long long n, const double lo[3], const double hi[3],
                  unsigned long long seed);
+/* particles [first, first + count) of that stream (one rank per GPU: the index range this rank
+ * tracks); also sets the particle id base to `first` */
+int cpf_seed_box_slice(cpf_context *ctx, long long first, long long count, const double lo[3],
+                       const double hi[3], unsigned long long seed);
 /* cudaInitParticles(fileName) analogue: xyzw[n][4] = (x,y,z,active) */
 int cpf_set_particles(cpf_context *ctx, long long n, const double *xyzw);
 /* optional: caller-supplied start tets (skips cpf_locate_initial) */
@@ -152,6 +158,12 @@ int cpf_locate_initial(cpf_context *ctx);
  * (e.g. after five failed reflections) are re-located with the BVH instead of being frozen on the
  * next sub-step as the reference does (cuda/particles.cu:334-338).  Call between cpf_substeps. */
 int cpf_relocate_lost(cpf_context *ctx);
+/* Continuous injection (extension; the reference seeds once, src/initCuda.H:141-150): every inactive
+ * particle -- escaped through an ESCAPE patch or frozen outside the domain -- is re-seeded uniformly in
+ * the box [lo, hi] (e.g. a slab behind the inlet), activated and located with the BVH.  Positions depend
+ * on (seed, sub-step index, global particle id) only.  *nReseeded (may be NULL; non-NULL synchronises). */
+int cpf_reseed_inactive(cpf_context *ctx, const double lo[3], const double hi[3], unsigned long long seed,
+                        long long *nReseeded);
 /* initRandomGenerator (cuda/particles.cu:541-548) */
 int cpf_init_rng(cpf_context *ctx);
 
@@ -169,13 +181,49 @@ int cpf_sort_particles(cpf_context *ctx);
 /* last kernel timing: milliseconds of the most recent cpf_advect/cpf_substeps on the device */
 int cpf_last_step_ms(cpf_context *ctx, float *ms);
 
+/* -- one rank per GPU ---------------------------------------------------------------- */
+/* Replaces the gather-to-master parallel branch of src/initCuda.H:207-270 and src/advect.H:59-89
+ * (Pstream::gatherList of points/cells/velocities to rank 0, ONE GPU for the whole MPI job;
+ * third_party/RTXAdvect/optix/OptixTetQuery.cpp:154 hard-codes device 0): every rank owns a context on
+ * its own GPU, tracks an index range of the particle cloud on a replica of the mesh, and the two
+ * per-step exchanges run over NCCL on the context's stream.  NCCL is bound at run time
+ * (dlopen libnccl.so.2); a communicator of one rank needs no NCCL.
+ * cpf_comm_unique_id: rank 0 creates the id (ncclGetUniqueId) and the HOST distributes its bytes with
+ * whatever it has (Pstream::broadcast / MPI_Bcast / a file); CPF_COMM_ID_BYTES bytes. */
+#define CPF_COMM_ID_BYTES 128
+int cpf_comm_unique_id(void *id, size_t bytes);
+int cpf_comm_init(cpf_context *ctx, const void *id, size_t bytes, int rank, int nranks);
+int cpf_comm_info(cpf_context *ctx, int *rank, int *nranks, int *ncclVersion);
+/* The coupled solver's per-step field: `root` passes the whole cell field (host or device memory), the
+ * others pass NULL; ncclBroadcast + repack on the context's stream (src/advect.H:44-57 + 59-89). */
+int cpf_update_velocity_bcast(cpf_context *ctx, const double *U, int on_device, int root);
+/* Decomposed solver runs: every rank passes only the nLocal cells it owns, as global
+ * cell ids [cellOffset, cellOffset + nLocal) of the replicated mesh; the slices are exchanged
+ * rank-to-rank (grouped ncclBroadcast), nothing is gathered to a master. */
+int cpf_update_velocity_slices(cpf_context *ctx, long long cellOffset, long long nLocal, const double *Ulocal, int on_device);
+/* Global id of this context's particle 0.  The random-walk streams are keyed by GLOBAL particle id
+ * (Philox counter, XORWOW subsequence = curand_init(seed, id), cuda/particles.cu:537), so N ranks
+ * tracking index ranges of one cloud reproduce the single-GPU run bit for bit.  Call before
+ * cpf_init_rng / the first sub-step. */
+int cpf_set_particle_id_base(cpf_context *ctx, long long base);
+
 /* -- results -------------------------------------------------------------------------------- */
 /* replaces the D2H copies of writeParticles2VTU (cuda/utils.cpp:144-170); any pointer may be
  * NULL; arrays are in ORIGINAL particle order: xyzw[n][4], vel[n][4], tet[n] */
 int cpf_download(cpf_context *ctx, double *xyzw, double *vel, int *tet);
 int cpf_download_cells(cpf_context *ctx, int *cell);
-/* cudaReportParticles + the kinetic-energy print of writeParticles2VTU */
+/* cudaReportParticles + the kinetic-energy print of writeParticles2VTU: full scan, blocks until it has arrived
+ * (= cpf_stats_request(ctx, 1) + cpf_stats_collect).  With a communicator: summed over the ranks (collective). */
 int cpf_stats_get(cpf_context *ctx, cpf_stats *out);
+/* The same without stalling the pipeline: cpf_stats_request enqueues the read-back behind everything
+ * submitted so far and returns at once (up to 4 outstanding); cpf_stats_collect waits for the OLDEST
+ * outstanding request only -- ask for step k's numbers after submitting step k+1.  full != 0 scans the
+ * particle arrays (exact n_active, n_negative_tet, kinetic energy); full == 0 moves the 11 cumulative
+ * counters only: n_active is derived from them (every particle that stops being active is counted as an
+ * escape or as a freeze), n_negative_tet and kinetic_energy repeat the last full scan.  reserved[0] = 1
+ * for a full result. */
+int cpf_stats_request(cpf_context *ctx, int full);
+int cpf_stats_collect(cpf_context *ctx, cpf_stats *out);
 /* writeParticles2VTU (cuda/utils.cpp:144-283): particle_%04d.vtu in `dir` */
 int cpf_write_vtu(cpf_context *ctx, const char *dir, unsigned step);
 /* The same file name, arrays and array names, but written without stalling the advection

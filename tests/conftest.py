@@ -14,6 +14,23 @@ def pytest_configure(config):
 
 
 def _have_gpu() -> bool:
+    """Ask the product itself (cpf_create probes the CUDA runtime): no PyTorch needed to see a device."""
+    import ctypes as C
+
+    lib_path = os.path.join(ROOT, "cudaparticlesfoam_b200", "libcpf.so")
+    if os.path.exists(lib_path):
+        try:
+            lib = C.CDLL(lib_path)
+            h = C.c_void_p()
+            lib.cpf_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+            rc = lib.cpf_create(None, C.byref(h))
+            if rc == 0:
+                lib.cpf_destroy.argtypes = [C.c_void_p]
+                lib.cpf_destroy(h)
+                return True
+            return False
+        except OSError:
+            pass
     try:
         import torch
 
@@ -25,9 +42,32 @@ def _have_gpu() -> bool:
 HAVE_GPU = _have_gpu()
 
 
+def n_gpus() -> int:
+    import ctypes as C
+
+    for name in ("libcudart.so", "libcudart.so.12", "libcudart.so.13"):
+        try:
+            rt = C.CDLL(name)
+            n = C.c_int(0)
+            if rt.cudaGetDeviceCount(C.byref(n)) == 0:
+                return n.value
+        except OSError:
+            continue
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 1 if HAVE_GPU else 0
+
+
 def pytest_collection_modifyitems(config, items):
     if HAVE_GPU:
         return
+    expr = (config.getoption("-m") or "").strip()
+    if expr == "gpu":
+        # the GPU suite was asked for explicitly: a green run of 0 tests would hide that nothing was checked
+        raise pytest.UsageError("-m gpu requested but libcpf sees no CUDA device (cpf_create -> CPF_ERR_NO_DEVICE)")
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for it in items:
         if "gpu" in it.keywords:

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in _declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.cpf_abi_version() == 2
+    assert lib.cpf_abi_version() == 3
 
 
 def test_config_struct_layout():

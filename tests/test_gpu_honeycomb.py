@@ -16,11 +16,13 @@ def _assert_same(p, v, t, cl, what):
     assert np.array_equal(v[live, :3].view(np.uint64), cl.vel[live, :3].view(np.uint64)), f"{what}: velocities differ"
 
 
-@pytest.mark.parametrize("integrator", [0, 1], ids=["euler", "rk2"])
-def test_honeycomb_prisms_match_the_oracle(synth, orc, integrator):
+@pytest.mark.parametrize("integrator,gen", [(0, "honeycomb_mesh"), (1, "honeycomb_mesh"), (4, "honeycomb_mesh_fast")], ids=["euler", "rk2", "rk4-C4"])
+def test_honeycomb_prisms_match_the_oracle(synth, orc, integrator, gen):
+    """rk4-C4: the oracle sample of BASELINE config 4 (bench.py poly10M_1e8_rk4: the same generator, cell shape, integrator
+    and field family at a size the oracle finishes in seconds)."""
     from cudaparticlesfoam_b200 import api
 
-    pm = synth.honeycomb_mesh(9, 8, 6)
+    pm = getattr(synth, gen)(9, 8, 6)
     mesh = orc.tet_mesh_from_poly(pm)
     rng = np.random.default_rng(5)
     n = 30000

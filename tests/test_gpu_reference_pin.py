@@ -92,7 +92,8 @@ def test_reference_brownian_stream_and_product_xorwow(case, orc):
     cl = orc.Cloud.make(p, tet0)
     orc.substeps(mesh, cl, Utet, nsteps, dt, xi=xi, D=D)
     assert np.array_equal(g.tet, cl.tet) and _same(g.p, cl.p), "oracle vs reference with random walk"
-    for kw in (dict(), dict(fuse_substeps=4, sort_interval=5), dict(path=api.PATH_EXACT)):
+    # dict(): the drop-in's default configuration (library default fuse, sort every 50); all on the filtered 3-pass pipeline
+    for kw in (dict(), dict(fuse_substeps=4, sort_interval=5), dict(fuse_substeps=10, sort_interval=7), dict(fuse_substeps=14, sort_interval=0), dict(path=api.PATH_EXACT)):
         tr = api.ParticleTracker(rng=api.RNG_XORWOW, diffusion_coeff=D, **kw)
         tr.upload_poly(pm)
         tr.update_velocity(U)
