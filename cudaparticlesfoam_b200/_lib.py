@@ -32,6 +32,7 @@ class CpfStats(C.Structure):
 _vp, _ip, _dp, _ll = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_longlong
 SYMBOLS = {
     "cpf_abi_version": (C.c_int, []),
+    "cpf_device_count": (C.c_int, [_ip]),
     "cpf_default_config": (None, [C.POINTER(CpfConfig)]),
     "cpf_create": (C.c_int, [C.POINTER(CpfConfig), C.POINTER(_vp)]),
     "cpf_destroy": (C.c_int, [_vp]),

@@ -128,6 +128,15 @@ extern "C" {
 
 int cpf_abi_version(void) { return CPF_ABI_VERSION; }
 
+int cpf_device_count(int *n)
+{
+    if (!n) return CPF_ERR_INVALID;
+    *n = 0;
+    const cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess || *n == 0) { *n = 0; return CPF_ERR_NO_DEVICE; }
+    return CPF_OK;
+}
+
 void cpf_default_config(cpf_config *cfg)
 {
     memset(cfg, 0, sizeof *cfg);

@@ -200,8 +200,10 @@ int cpf_update_velocity_bcast(cpf_context *ctx, const double *U, int on_device, 
     if (rc) return rc;
     // upload (root), broadcast and repack run on the copy stream with their own communicator: they overlap the sub-steps
     // already enqueued on the compute stream (which read the other half of the double buffer)
-    rc = field_exchange_begin(ctx);
-    if (rc) return rc;
+    // a DEVICE source is ready in compute-stream order: the copy stream waits for "now" there.  A host source needs no
+    // such wait (that wait would put the exchange of step k+1 behind the sub-steps of step k instead of beside them);
+    // the staging buffer itself is only ever touched on the copy stream.
+    if (c->rank == root && on_device) { rc = field_exchange_begin(ctx); if (rc) return rc; }
     const double *src = c->d_stage;
     if (c->rank == root) {
         if (on_device) src = U; // broadcast straight out of the caller's device buffer (ready in compute-stream order)
@@ -223,8 +225,7 @@ int cpf_update_velocity_slices(cpf_context *ctx, long long cellOffset, long long
     int rc = ensure_stage(ctx, bytes);
     if (rc) return rc;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    rc = field_exchange_begin(ctx);
-    if (rc) return rc;
+    if (on_device) { rc = field_exchange_begin(ctx); if (rc) return rc; }
     if (nLocal) CPF_CUDA(ctx, cudaMemcpyAsync(c->d_stage + 3 * cellOffset, Ulocal, sizeof(double) * 3 * (size_t)nLocal, kind, ctx->copyStream));
     if (c->nranks > 1) {
         // the slice table is exchanged once (and again whenever this rank's slice changes): 2 x 8 bytes per rank

@@ -377,6 +377,59 @@ def honeycomb_mesh_fast(nx: int, ny: int, nz: int, R: float = 0.06, hz: float = 
                     patch_names=("z-", "z+", "sides"), dims=(nx, ny, nz), lo=points.min(axis=0), hi=points.max(axis=0))
 
 
+def processor_meshes(pm: PolyMesh, nproc: int) -> list:
+    """What decomposePar hands the ranks of a decomposed run: rank r owns the contiguous cell range [c0, c1) and sees a
+    self-contained polyMesh of those cells -- local point / face / cell numbering, the original patches restricted to
+    its cells, and one extra patch of processor faces (faces whose other cell lives on another rank; on the neighbour
+    side they are stored reversed, starting from the same vertex, as OpenFOAM does)."""
+    n = pm.n_cells
+    off, nint, nf = pm.face_offsets, pm.n_internal, pm.n_faces
+    owner, nbr = pm.owner, pm.neighbour
+    out = []
+    for r in range(nproc):
+        c0, c1 = r * n // nproc, (r + 1) * n // nproc
+        own_in = (owner >= c0) & (owner < c1)
+        nb_in = np.zeros(nf, dtype=bool)
+        nb_in[:nint] = (nbr >= c0) & (nbr < c1)
+        internal = np.flatnonzero(own_in[:nint] & nb_in[:nint])
+        groups = []
+        for p0, p1 in zip(pm.patch_starts[:-1], pm.patch_starts[1:]):
+            f = np.arange(p0, p1)
+            groups.append((f[own_in[p0:p1]], False))
+        proc_own = np.flatnonzero(own_in[:nint] & ~nb_in[:nint])
+        proc_nbr = np.flatnonzero(~own_in[:nint] & nb_in[:nint])
+        loops, fo, fn = [], [], []
+
+        def loop(f, flip):
+            v = pm.face_verts[off[f]:off[f + 1]]
+            return np.concatenate([v[:1], v[:0:-1]]) if flip else v
+
+        for f in internal:
+            loops.append(loop(f, False)); fo.append(owner[f] - c0); fn.append(nbr[f] - c0)
+        starts = [len(loops)]
+        for fs, _ in groups:
+            for f in fs:
+                loops.append(loop(f, False)); fo.append(owner[f] - c0)
+            starts.append(len(loops))
+        for f in proc_own:
+            loops.append(loop(f, False)); fo.append(owner[f] - c0)
+        for f in proc_nbr:
+            loops.append(loop(f, True)); fo.append(nbr[f] - c0)
+        starts.append(len(loops))
+        used = np.unique(np.concatenate(loops))
+        remap = -np.ones(pm.n_points, dtype=np.int64)
+        remap[used] = np.arange(used.shape[0])
+        fv = remap[np.concatenate(loops)].astype(np.int32)
+        fo_ = np.zeros(len(loops) + 1, dtype=np.int32)
+        fo_[1:] = np.cumsum([len(l) for l in loops])
+        pts = np.ascontiguousarray(pm.points[used])
+        out.append(PolyMesh(points=pts, face_offsets=fo_, face_verts=fv, owner=np.asarray(fo, dtype=np.int32),
+                            neighbour=np.asarray(fn, dtype=np.int32), cell_centres=np.ascontiguousarray(pm.cell_centres[c0:c1]),
+                            patch_starts=np.asarray(starts, dtype=np.int32), patch_names=tuple(pm.patch_names) + ("procBoundary",),
+                            dims=pm.dims, lo=pts.min(axis=0), hi=pts.max(axis=0)))
+    return out
+
+
 def channel_mesh(nx=400, ny=50, nz=50, jitter: float = 0.0) -> PolyMesh:
     """BASELINE config 3/5 mesh: 4 x 1 x 1 channel, inlet x-, outlet x+, walls on +-y/+-z."""
     return box_mesh(nx, ny, nz, lo=(0.0, 0.0, 0.0), hi=(4.0, 1.0, 1.0), jitter=jitter)

@@ -89,6 +89,8 @@ typedef struct cpf_stats {
 
 /* -- lifecycle ------------------------------------------------------------------------------ */
 int cpf_abi_version(void);
+/* CUDA devices visible to this process (one rank per GPU: device = rank % count); CPF_ERR_NO_DEVICE if none */
+int cpf_device_count(int *n);
 void cpf_default_config(cpf_config *cfg);
 /* replaces the ~35 locals + cudaMalloc block of src/initCuda.H:33-72, 141-150 */
 int cpf_create(const cpf_config *cfg, cpf_context **out);

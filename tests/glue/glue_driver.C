@@ -13,9 +13,9 @@
 
 using namespace Foam;
 
-// the parallel branch of initCuda.H is compiled but never executed in the shim (nProcs() == 1)
-triFace Foam::tetIndices::faceTriIs(const fvMesh &) const { return triFace{{0, 0, 0}}; }
-List<tetIndices> Foam::polyMeshTetDecomposition::cellTetIndices(const fvMesh &, label) { return List<tetIndices>(); }
+// Decomposed runs: start one process per rank with CPF_SHIM_NPROCS / CPF_SHIM_RANK / CPF_SHIM_DIR set and give every
+// rank the case file of ITS processor mesh (tests/test_glue.py splits the global mesh); the shim's Pstream carries the
+// gathers through files, the field and the statistics travel over NCCL inside libcpf.
 
 template <class T> static void rd(std::ifstream &f, T *p, size_t n) { f.read(reinterpret_cast<char *>(p), sizeof(T) * n); }
 
@@ -42,6 +42,10 @@ int main(int argc, char **argv)
     for (int p = 0; p < nPatches; ++p) mesh.patches_[p] = polyPatch{"patch" + std::to_string(p), ps[p], ps[p + 1] - ps[p]};
     mesh.tetBase_ = labelList(nFaces, 0);
     mesh.cells_.setSize(nCells);
+    for (int f = 0; f < nFaces; ++f) {
+        mesh.cells_[mesh.owner_[f]].v.push_back(f);
+        if (f < nInternal) mesh.cells_[mesh.neighbour_[f]].v.push_back(f);
+    }
 
     IOdictionary cudaParticleAdvectionDict;
     cudaParticleAdvectionDict.kv["numParticles"] = std::to_string(h[5]);
@@ -50,6 +54,15 @@ int main(int argc, char **argv)
     { std::ostringstream o; o.precision(17); o << d[1]; cudaParticleAdvectionDict.kv["dt"] = o.str(); }
     { std::ostringstream o; o.precision(17); o << d[2]; cudaParticleAdvectionDict.kv["diffusionCoeff"] = o.str(); }
     cudaParticleAdvectionDict.boxes.emplace("seedingBox", boundBox(point(d[3], d[4], d[5]), point(d[6], d[7], d[8])));
+    if (const char *extra = std::getenv("CPF_SHIM_DICT")) { // "key=value;key=value": further dictionary entries
+        std::istringstream is(extra);
+        std::string kv;
+        while (std::getline(is, kv, ';')) {
+            const size_t eq = kv.find('=');
+            if (eq != std::string::npos) cudaParticleAdvectionDict.kv[kv.substr(0, eq)] = kv.substr(eq + 1);
+        }
+    }
+    if (h[7] < 0) cudaParticleAdvectionDict.kv.erase("randomWalk"); // the stock dictionary: no optional key at all
 
     Time runTime;
     runTime.dT = d[0];
@@ -77,6 +90,9 @@ int main(int argc, char **argv)
     out.write(reinterpret_cast<const char *>(v.data()), sizeof(double) * v.size());
     out.write(reinterpret_cast<const char *>(tet.data()), sizeof(int) * tet.size());
     out.write(reinterpret_cast<const char *>(&step), sizeof step);
+    std::vector<int> cell(n);   // global cell ids: comparable between a serial run and a decomposed one
+    CPF_GLUE_CHECK(cpf_download_cells(cpf, cell.data()));
+    out.write(reinterpret_cast<const char *>(cell.data()), sizeof(int) * cell.size());
     cpf_destroy(cpf);
     return 0;
 }

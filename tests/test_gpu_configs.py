@@ -88,7 +88,7 @@ def test_config2_channel_1e7_filtered_equals_exact_and_oracle_sample(synth, orc)
     import bench
 
     w = bench.WORKLOADS["channel1M_1e7"]
-    pm, p, fields = bench.build_inputs(w, 0, 1)
+    pm, p, fields, _ = bench.build_inputs(w, 0, 1)
     res = []
     xis = None
     for path in (api.PATH_FILTERED, api.PATH_EXACT):
