@@ -82,6 +82,7 @@ SYMBOLS = {
     "cpf_num_particles": (_ll, [_vp]),
     "cpf_device_pointers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "cpf_debug_next_normals": (C.c_int, [_vp, _dp]),
+    "cpf_debug_normals": (C.c_int, [_vp, C.c_int, _dp]),
     "cpf_launch_count": (_ll, [_vp]),
 }
 

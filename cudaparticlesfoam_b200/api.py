@@ -324,6 +324,12 @@ class ParticleTracker:
         self._chk(self.lib.cpf_debug_next_normals(self.h, _dp(xi)))
         return xi
 
+    def normals(self, k: int):
+        """Deviates of the next k sub-steps, [k, n, 3] in original particle order (does not advance the stream)."""
+        xi = np.empty((int(k), self.n, 3))
+        self._chk(self.lib.cpf_debug_normals(self.h, int(k), _dp(xi)))
+        return xi
+
     def device_pointers(self):
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._chk(self.lib.cpf_device_pointers(self.h, C.byref(a), C.byref(b), C.byref(c)))

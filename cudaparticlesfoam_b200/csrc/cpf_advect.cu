@@ -992,16 +992,20 @@ __global__ void k_init_rng(curandState_t *st, long long n, unsigned long long se
     if (i < n) curand_init(seed, idBase + (unsigned long long)i, 0ull, &st[i]); // particles.cu:537, subsequence = global particle id
 }
 
-template <int RNG> __global__ void k_debug_normals(const ParticleView pv, const StepParams sp, double *xi)
+// parity tooling: the deviates of the next k sub-steps, [k][n][3] in ORIGINAL particle order; the stream is not advanced
+template <int RNG> __global__ void k_debug_normals(const ParticleView pv, const StepParams sp, int k, double *xi)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pv.n) return;
     Rng<RNG> rng;
     rng.open(pv, i, sp);
-    double a = 0, b = 0, c = 0;
-    rng.draw(0, a, b, c);
     const long long o = pv.pid[i];
-    xi[3 * o] = a; xi[3 * o + 1] = b; xi[3 * o + 2] = c;
+    for (int q = 0; q < k; ++q) {
+        double a = 0, b = 0, c = 0;
+        rng.draw(q, a, b, c);
+        double *dst = xi + 3 * ((long long)q * pv.n + o);
+        dst[0] = a; dst[1] = b; dst[2] = c;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1163,7 +1167,7 @@ int launch_init_rng(cpf_context *ctx)
     return CPF_OK;
 }
 
-int launch_debug_normals(cpf_context *ctx, double *d_xi)
+int launch_debug_normals(cpf_context *ctx, int k, double *d_xi)
 {
     const ParticleView pv = particle_view(ctx);
     StepParams sp{};
@@ -1173,11 +1177,11 @@ int launch_debug_normals(cpf_context *ctx, double *d_xi)
     const unsigned grid = (unsigned)((ctx->n + 127) / 128);
     if (ctx->cfg.rng == CPF_RNG_XORWOW) {
         if (!ctx->rng_ready) { int rc = launch_init_rng(ctx); if (rc) return rc; }
-        k_debug_normals<CPF_RNG_XORWOW><<<grid, 128, 0, ctx->stream>>>(particle_view(ctx), sp, d_xi);
+        k_debug_normals<CPF_RNG_XORWOW><<<grid, 128, 0, ctx->stream>>>(particle_view(ctx), sp, k, d_xi);
     } else if (ctx->cfg.rng == CPF_RNG_PHILOX) {
-        k_debug_normals<CPF_RNG_PHILOX><<<grid, 128, 0, ctx->stream>>>(pv, sp, d_xi);
+        k_debug_normals<CPF_RNG_PHILOX><<<grid, 128, 0, ctx->stream>>>(pv, sp, k, d_xi);
     } else {
-        CPF_CUDA(ctx, cudaMemsetAsync(d_xi, 0, sizeof(double) * 3 * (size_t)ctx->n, ctx->stream));
+        CPF_CUDA(ctx, cudaMemsetAsync(d_xi, 0, sizeof(double) * 3 * (size_t)ctx->n * (size_t)k, ctx->stream));
     }
     ctx->launches++;
     CPF_CUDA(ctx, cudaGetLastError());

@@ -758,21 +758,21 @@ int cpf_device_pointers(cpf_context *ctx, void **pos4, void **tet, void **ucell)
     return CPF_OK;
 }
 
-int cpf_debug_next_normals(cpf_context *ctx, double *xi)
+int cpf_debug_normals(cpf_context *ctx, int k, double *xi)
 {
-    if (!ctx || !xi || ctx->n == 0) return fail(ctx, CPF_ERR_INVALID, "cpf_debug_next_normals: bad arguments");
+    if (!ctx || !xi || ctx->n == 0 || k < 1 || k > 4096) return fail(ctx, CPF_ERR_INVALID, "cpf_debug_normals: bad arguments");
     cudaSetDevice(ctx->device);
-    double *d = nullptr;
-    CPF_CUDA(ctx, cudaMalloc(&d, sizeof(double) * 3 * (size_t)ctx->n));
-    int rc = launch_debug_normals(ctx, d);
-    if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(xi, d, sizeof(double) * 3 * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, CPF_ERR_CUDA, "download of normals failed: %s", cudaGetErrorString(e));
-    }
-    cudaFree(d);
-    return rc;
+    const size_t bytes = sizeof(double) * 3 * (size_t)ctx->n * (size_t)k;
+    int rc = ensure_scratch(ctx, bytes); // the context's scratch buffer: no allocation per call
+    if (rc) return rc;
+    rc = launch_debug_normals(ctx, k, (double *)ctx->d_scratch);
+    if (rc) return rc;
+    CPF_CUDA(ctx, cudaMemcpyAsync(xi, ctx->d_scratch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CPF_OK;
 }
+
+int cpf_debug_next_normals(cpf_context *ctx, double *xi) { return cpf_debug_normals(ctx, 1, xi); }
 
 long long cpf_launch_count(cpf_context *ctx) { return ctx ? ctx->launches : 0; }
 

@@ -157,7 +157,7 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel);
 int max_fused_substeps(const cpf_context *ctx);
 int default_fused_substeps(const cpf_context *ctx);
 int launch_initial_advect(cpf_context *ctx, double dt);
-int launch_debug_normals(cpf_context *ctx, double *d_xi);
+int launch_debug_normals(cpf_context *ctx, int k, double *d_xi);
 int launch_init_rng(cpf_context *ctx);
 int launch_point_interp(cpf_context *ctx);
 // cpf_api.cu

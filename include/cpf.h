@@ -255,6 +255,8 @@ int cpf_device_pointers(cpf_context *ctx, void **pos4, void **tet, void **ucell)
 /* parity tooling: the normal deviates the next sub-step will use, [n][3], original order;
  * does not advance the stream */
 int cpf_debug_next_normals(cpf_context *ctx, double *xi);
+/* the same for the next k sub-steps, xi[k][n][3]: lets a test replay a FUSED chunk through the oracle */
+int cpf_debug_normals(cpf_context *ctx, int k, double *xi);
 /* Device timing of the fused sub-step kernel: while enabled, a CUDA-event pair brackets every
  * launch on the launching stream; cpf_profile_read returns and resets the totals (replaces the
  * commented-out Adv/Dfs/Qry/Rft/Mov breakdown of src/advect.H:186-203). */

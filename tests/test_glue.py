@@ -172,3 +172,30 @@ def test_glue_decomposed_run_one_rank_per_gpu(tmp_path, synth, orc, rw):
     for rank in range(2):
         files = sorted(f for f in os.listdir(par / f"processor{rank}") if f.startswith("particle_"))
         assert files and files[0] == "particle_0000.vtu"
+
+
+@pytest.mark.gpu
+def test_glue_optional_keys_reach_the_library(tmp_path, synth, orc):
+    """relocateLost / integrator / fuseSubSteps from the dictionary: RK2 through the glue equals the oracle extension, and
+    relocateLost = true (cpf_relocate_lost after every chunk) changes nothing when no particle loses its tet."""
+    pm, mesh, U, _ = make_case(synth, orc, dims=(8, 7, 6), jitter=0.15, n=1)
+    n, dt, deltaT, nsteps, save = 5000, 0.004, 0.02, 2, 5
+    lo, hi = (0.05, 0.05, 0.05), (0.95, 0.95, 0.95)
+    fields = [synth.field_uniform_vortex(pm.cell_centres, R=0.3, omega=2 * np.pi * (1 + 0.2 * k)) for k in range(nsteps)]
+    _write_case(tmp_path / "case.bin", pm, fields, n, save, 0, deltaT, dt, 0.0, lo, hi)
+    exe = _build_driver(tmp_path, True)
+    outs = {}
+    for tag, extra in (("rk2", "integrator=rk2;fuseSubSteps=3"), ("rk2_relocate", "integrator=rk2;fuseSubSteps=3;relocateLost=1")):
+        env = dict(os.environ, CPF_SHIM_DICT=extra)
+        r = subprocess.run([exe, str(tmp_path / "case.bin"), str(tmp_path / f"{tag}.bin"), str(nsteps)], cwd=tmp_path, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs[tag] = _read_out(tmp_path / f"{tag}.bin", n)
+    pp, vv, tt, step, cc = outs["rk2"]
+    ncyc = int(max(np.ceil(deltaT / dt), 1))
+    p = synth.seed_box(n, lo, hi)
+    cl = orc.Cloud.make(p, orc.locate_brute(mesh, p))
+    for k in range(nsteps):
+        orc.ext_substeps(mesh, cl, orc.expand_velocity(mesh, fields[k]), ncyc, deltaT / ncyc, integrator=1)
+    assert np.array_equal(tt, cl.tet) and np.array_equal(pp.view(np.uint64), cl.p.view(np.uint64))
+    p2, v2, t2, _, _ = outs["rk2_relocate"]
+    assert np.array_equal(t2, tt) and np.array_equal(p2.view(np.uint64), pp.view(np.uint64))
