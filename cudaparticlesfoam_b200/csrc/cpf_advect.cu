@@ -53,6 +53,7 @@ template <> struct Rng<CPF_RNG_NONE> {
     CPF_DEV bool draw(int, double &, double &, double &) { return false; }
     CPF_DEV void skip(int) {}
     CPF_DEV void close(const ParticleView &, long long) {}
+    CPF_DEV void stage(Xi *, int, int, int, bool) {}
 };
 
 // The reference's stream: cuRAND XORWOW, curand_init(1591593751, particle, 0), three successive
@@ -75,6 +76,17 @@ template <> struct Rng<CPF_RNG_XORWOW> {
         return true;
     }
     CPF_DEV void close(const ParticleView &pv, long long i) { pv.rng[i] = st; }
+    // deviates of a whole chunk into xi[(3 q + c) * stride], drawn in sequence from the chunk-start state
+    CPF_DEV void stage(Xi *xi, int stride, int nSub, int, bool live)
+    {
+        for (int q = 0; q < nSub; ++q) {
+            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+            if (live) draw(q, x0, x1, x2);
+            xi[(q * 3 + 0) * stride] = x0;
+            xi[(q * 3 + 1) * stride] = x1;
+            xi[(q * 3 + 2) * stride] = x2;
+        }
+    }
 };
 
 // Stateless counter-based stream: Philox4x32-10 keyed by the seed, counter = (particle id,
@@ -108,6 +120,9 @@ CPF_DEV void box_muller_f32(uint32_t x, uint32_t y, double &n0, double &n1)
     n0 = (double)__fmul_rn(r, mufu_sin(ang));
     n1 = (double)__fmul_rn(r, mufu_cos(ang));
 }
+// The stream of a particle is a sequence of N(0,1) deviates z_0, z_1, ...: block b = Philox4x32-10(counter = (global
+// particle id, b), key = seed) yields z_{4b..4b+3} through two Box-Muller pairs; sub-step t (global index) consumes
+// z_{3t}, z_{3t+1}, z_{3t+2}.  All four outputs of a block are used (3 blocks serve 4 sub-steps).
 template <> struct Rng<CPF_RNG_PHILOX> {
     typedef float Xi;
     static constexpr bool STATEFUL = false;
@@ -122,17 +137,44 @@ template <> struct Rng<CPF_RNG_PHILOX> {
         k0 = (uint32_t)sp.seed; k1 = (uint32_t)(sp.seed >> 32);
         step0 = sp.step0;
     }
+    CPF_DEV void block(unsigned long long b, double z[4])
+    {
+        uint32_t o[4];
+        philox4x32_10(id, idhi, (uint32_t)b, (uint32_t)(b >> 32), k0, k1, o);
+        box_muller_f32(o[0], o[1], z[0], z[1]);
+        box_muller_f32(o[2], o[3], z[2], z[3]);
+    }
     CPF_DEV bool draw(int s, double &a, double &b, double &c)
     {
-        const unsigned long long st = step0 + (unsigned long long)s;
-        uint32_t o[4];
-        philox4x32_10(id, idhi, (uint32_t)st, (uint32_t)(st >> 32), k0, k1, o);
-        double d;
-        box_muller_f32(o[0], o[1], a, b);
-        box_muller_f32(o[2], o[3], c, d);
+        const unsigned long long m = 3ull * (step0 + (unsigned long long)s);
+        const int r = (int)(m & 3ull);
+        double z[8];
+        block(m >> 2, z);
+        if (r > 1) block((m >> 2) + 1ull, z + 4);
+        a = r == 0 ? z[0] : (r == 1 ? z[1] : (r == 2 ? z[2] : z[3]));
+        b = r == 0 ? z[1] : (r == 1 ? z[2] : (r == 2 ? z[3] : z[4]));
+        c = r == 0 ? z[2] : (r == 1 ? z[3] : (r == 2 ? z[4] : z[5]));
         return true;
     }
     CPF_DEV void close(const ParticleView &, long long) {}
+    // deviates of the sub-steps [sFrom, nSub) of a chunk into xi[(3 q + c) * stride]: block by block, every output used
+    CPF_DEV void stage(Xi *xi, int stride, int nSub, int sFrom, bool live)
+    {
+        const unsigned long long m0 = 3ull * step0;
+        const long long lo = 3ll * sFrom, hi = 3ll * nSub;              // wanted slots, relative to m0
+        const unsigned long long b0 = (m0 + (unsigned long long)lo) >> 2, b1 = (m0 + (unsigned long long)hi - 1ull) >> 2;
+        if (!live || sFrom >= nSub) return;
+        for (unsigned long long b = b0; b <= b1; ++b) {
+            double z[4];
+            block(b, z);
+            const long long base = (long long)(4ull * b - m0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long slot = base + j;
+                if (slot >= lo && slot < hi) xi[slot * stride] = (Xi)z[j];
+            }
+        }
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -636,13 +678,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
         if (RNG != CPF_RNG_NONE) {
             Rng<RNG> rng;
             if (live) rng.open(pv, i, sp);
-            for (int q = 0; q < sp.nSub; ++q) {
-                double x0 = 0.0, x1 = 0.0, x2 = 0.0;
-                if (live && (STATEFUL || q >= s)) rng.draw(q, x0, x1, x2);
-                s_xi[(q * 3 + 0) * 128 + threadIdx.x] = (Xi)x0;
-                s_xi[(q * 3 + 1) * 128 + threadIdx.x] = (Xi)x1;
-                s_xi[(q * 3 + 2) * 128 + threadIdx.x] = (Xi)x2;
-            }
+            rng.stage(s_xi + threadIdx.x, 128, sp.nSub, s, live);
             if constexpr (STATEFUL) { if (live) *stash = rng.st; }
         }
         Fast32 f;
@@ -847,13 +883,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
     if (RNG != CPF_RNG_NONE) {
         Rng<RNG> rng;
         if (live) rng.open(pv, i, sp);
-        for (int q = 0; q < sp.nSub; ++q) {
-            double x0 = 0.0, x1 = 0.0, x2 = 0.0;
-            if (live) rng.draw(q, x0, x1, x2);
-            xi[(q * 3 + 0) * NT] = (Xi)x0;
-            xi[(q * 3 + 1) * NT] = (Xi)x1;
-            xi[(q * 3 + 2) * NT] = (Xi)x2;
-        }
+        rng.stage(xi, NT, sp.nSub, 0, live);
         if constexpr (STATEFUL) { if (live) *stash = rng.st; }
     }
     Fast32 f;
@@ -895,7 +925,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
         }
         if (mode == 1) {
             ++visits;
-            const int oc = visit_fast32<false, CF>(m, f, O, P, ws);
+            const int oc = visit_fast32<false, CF>(m, f, O, P, ws, visits >= 48);
             if (oc == CPF_V_DONE) {
                 tet = ws.cur;
                 org = ws.org;
@@ -903,7 +933,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
                 else P = xadd(P, disp);
                 hops += (unsigned)visits;
                 mode = (++s >= sp.nSub) ? 2 : 0;
-            } else if (oc != CPF_V_HOP || visits >= 48) {
+            } else if (oc != CPF_V_HOP) {
                 hops += (unsigned)visits;
                 deferAt = s;
                 mode = 2;

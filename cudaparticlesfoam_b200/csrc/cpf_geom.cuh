@@ -283,8 +283,18 @@ CPF_DEV void f32_load(const MeshView &m, int tet, Fast32 &f)
     const uint4 *p = m.tetfast + 4ll * tet;
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+#if CPF_REC_SPLIT
+    asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]) : "l"(p + 2));
+    asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "l"(p + 3));
+#else
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "l"(p + 2));
+#endif
+#if CPF_REC_SCALAR_E
+    // word 15 (E) again on its own: ptxas keeps E's loop-carried home outside the vector-load registers and would copy it
+    // there right behind the load (a wait for the record inside the hop); the scalar load lands in the home register
+    asm("ld.global.nc.u32 %0, [%1+60];" : "=r"(w[15]) : "l"(p));
+#endif
     f.link = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
 #pragma unroll
     for (int k = 0; k < 3; ++k)
@@ -295,6 +305,12 @@ CPF_DEV void f32_load(const MeshView &m, int tet, Fast32 &f)
     f.E = __uint_as_float(w[15]);
 }
 
+#ifndef CPF_REC_SCALAR_E
+#define CPF_REC_SCALAR_E 0
+#endif
+#ifndef CPF_REC_SPLIT
+#define CPF_REC_SPLIT 0
+#endif
 #ifndef CPF_HOP_PREFETCH
 #define CPF_HOP_PREFETCH 0 /* measured: prefetch at the hop + load at the next visit is 2 % slower than loading at the hop */
 #endif
@@ -391,8 +407,11 @@ CPF_DEV bool start_point_clear(const MeshView &m, const Fast32 &f, float rx, flo
 //   C3  exit point clear of the three other faces (edges/vertices, ties of dT, a wrongly selected exit).
 // The entry face needs no special case: after C2 its e_j is certified positive (the plane function of the face a
 // segment came in through increases along the segment), so it is never an exit candidate.
+// lastVisit: the caller's visit cap is reached -- a hop out of this tet is refused BEFORE the next record is requested
+// (keeps every use of the caller's state ahead of the loads: nothing in the hop path then touches a register the
+// loads write, which ptxas otherwise resolves with a copy right behind them, i.e. a wait for the record inside the hop)
 template <bool DYN_C1, int CFV>
-CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, WalkF &ws)
+CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, WalkF &ws, bool lastVisit = false)
 {
     const float INF = __int_as_float(0x7f800000);
 #if CPF_HOP_PREFETCH
@@ -455,6 +474,7 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
     const int link = sel4(f.link.x, f.link.y, f.link.z, f.link.w, js);
     if (!((c3m >= g) && (t > ws.t_in) && (t <= 1.f))) return CPF_V_REFUSE; // incl. "no candidate" (t = inf)
     if (link < 0) { ws.wall_js = js; ws.wall_link = link; return CPF_V_WALL; }
+    if (lastVisit) return CPF_V_REFUSE;
     ws.cur = link >> 2;
     ws.t_in = t;
     ws.path = (ws.path << 2) | (unsigned)js;

@@ -3,6 +3,6 @@
 TAG=$1; shift
 for v in "$@"; do
   if [ "$v" = base ]; then unset CPF_LIB; else export CPF_LIB=build/$v/libcpf.so; fi
-  python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_$v.json 2> gpurun_out/${TAG}_$v.err
+  python bench.py --steps 20 --warmup 5 --no-cpu --no-extra > gpurun_out/${TAG}_$v.json 2> gpurun_out/${TAG}_$v.err
   python tools/pr.py gpurun_out/${TAG}_$v.json
 done

@@ -9,7 +9,7 @@ cp $ROOT/cudaparticlesfoam_b200/csrc/*.cu $ROOT/cudaparticlesfoam_b200/csrc/*.cu
 cp $ROOT/include/cpf.h $OUT/include/
 sed -i 's#"../../include/cpf.h"#"../include/cpf.h"#' $OUT/csrc/cpf_internal.h
 cd $OUT/csrc
-for f in cpf_api cpf_mesh cpf_locate cpf_advect cpf_sort cpf_output; do
+for f in cpf_api cpf_mesh cpf_locate cpf_advect cpf_sort cpf_output cpf_comm; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O2 "$@" -c $f.cu -o $f.o &
 done
 wait
