@@ -43,6 +43,7 @@ SYMBOLS = {
     "cpf_profile_read": (C.c_int, [_vp, _ip, _dp, _dp]),
     "cpf_set_config": (C.c_int, [_vp, C.POINTER(CpfConfig)]),
     "cpf_mesh_upload_poly": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _ip, _ip, _ip, C.c_int, _ip, C.c_int, _dp, _ip, C.c_int, _ip, _ip]),
+    "cpf_set_patch_restitution": (C.c_int, [_vp, C.c_int, _dp]),
     "cpf_mesh_upload_tets": (C.c_int, [_vp, C.c_int, _dp, _ll, _ip, _ip, C.c_int]),
     "cpf_mesh_info": (C.c_int, [_vp, C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_ll)]),
     "cpf_mesh_download_tets": (C.c_int, [_vp, _ip, _ip]),

@@ -109,6 +109,11 @@ class ParticleTracker:
             pm.n_internal, _ip(pm.neighbour), pm.n_cells, _dp(pm.cell_centres), _ip(tb) if tb is not None else None, npatch,
             _ip(pm.patch_starts), _ip(pk) if pk is not None else None))
 
+    def set_patch_restitution(self, e):
+        """Rebound model: restitution coefficient in (0, 1] per boundary patch (1 = specular, the reference)."""
+        e = np.ascontiguousarray(e, dtype=np.float64)
+        self._chk(self.lib.cpf_set_patch_restitution(self.h, e.shape[0], _dp(e)))
+
     def upload_tets(self, pos, tets, tet_cell=None, n_cells=0):
         pos = np.ascontiguousarray(pos, dtype=np.float64)
         tets = np.ascontiguousarray(tets, dtype=np.int32)

@@ -247,7 +247,7 @@ CPF_TAIL void tail_convex_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int 
             return;
         }
         ty.refl++;
-        reflect_exact(T, Phit, E, vel);
+        reflect_exact(m, T, Phit, E, vel);
     }
     const D3 nd = xsub(E, Phit);
     tet = next;
@@ -296,10 +296,11 @@ CPF_TAIL void tail_bary_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &t
             // specularReflect (query/RTQuery.cu:92-107) on face fj of tet bd (= T)
             D3 A;
             const D3 n = face_normal_exact(T, fj, A);
+            const double gain = face_gain(m, T, fj);
             double sp = xdot(xsub(R, A), n);
-            sp = __dadd_rn(sp, sp);
+            sp = __dmul_rn(gain, sp);
             double sv = xdot(vel, n);
-            sv = __dadd_rn(sv, sv);
+            sv = __dmul_rn(gain, sv);
             R = D3{ __fma_rn(-sp, n.x, R.x), __fma_rn(-sp, n.y, R.y), __fma_rn(-sp, n.z, R.z) };
             vel = D3{ __fma_rn(-sv, n.x, vel.x), __fma_rn(-sv, n.y, vel.y), __fma_rn(-sv, n.z, vel.z) };
             ty.refl++;
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact_convex(const Mesh
                     } else { // S4: convexReflector, up to 5 wall hits
                         Phit = S;
                         ty.refl++;
-                        reflect_exact(T, Phit, E, vel);
+                        reflect_exact(m, T, Phit, E, vel);
                         legHops = 0;
                         if (++leg >= 5) { // fifth hit: no further walk, the particle is lost (next == -1)
                             tet = -1;
@@ -712,7 +713,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                     wallWait = false;
                     D3 Eref, u = ld_ucell(m, cell);
                     if (KEEPV) u = vel;
-                    if (wall_reflect_on_path(m, tet, ws.path, visits - 1, ws.cur, ws.wall_js, P, disp, Phit, Eref, u)) {
+                    if (wall_reflect_on_path(m, tet, ws.path, visits - 1, ws.cur, ws.wall_js, ws.wall_link, P, disp, Phit, Eref, u)) {
                         disp = Eref;
                         const int wallTet = ws.cur;
                         walkf_begin(ws, O, Phit, xsub(Eref, Phit), wallTet, ws.org, false); // leg 1: from the hit point (certified by C3), same tet

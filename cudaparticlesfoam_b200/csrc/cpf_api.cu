@@ -2,6 +2,7 @@
 // point validates, enqueues work on the context's stream and returns a status code.
 #include <algorithm>
 #include <cmath>
+#include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -12,6 +13,19 @@ using namespace cpf;
 
 namespace cpf {
 void release_mesh(cpf_context *ctx);
+
+int fail(cpf_context *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+
 
 ParticleView particle_view(const cpf_context *ctx)
 {
@@ -84,6 +98,14 @@ __global__ void k_reseed_inactive(long long n, double4 *__restrict__ pos, int *_
     if (m && (threadIdx.x & 31) == 0) atomicAdd(count, (unsigned long long)__popc(m));
 }
 
+__global__ void k_particle_cells(const MeshView m, long long n, const int *__restrict__ tet, const int *__restrict__ pid, int *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = tet[i];
+    out[pid[i]] = t >= 0 ? tet_cell(m, t, ld_int4(m.tetv, t)) : -1;
+}
+
 __global__ void k_iota_fill(long long n, int *pid0, int *tet0)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,6 +145,18 @@ static inline unsigned long long splitmix64(unsigned long long x)
 } // namespace cpf
 
 static std::string g_create_error;
+
+// streams, events and the counter block of a context; safe on a partially constructed one
+static void destroy_handles(cpf_context *ctx)
+{
+    cudaFree(ctx->d_counters); ctx->d_counters = nullptr;
+    cudaEvent_t *evs[] = { &ctx->ev0, &ctx->ev1, &ctx->evCopy, &ctx->evRead[0], &ctx->evRead[1] };
+    for (cudaEvent_t *ev : evs) if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
+    for (cudaEvent_t ev : ctx->profEvents) cudaEventDestroy(ev);
+    ctx->profEvents.clear();
+    if (ctx->ownStream) { cudaStreamDestroy(ctx->ownStream); ctx->ownStream = nullptr; }
+    if (ctx->copyStream) { cudaStreamDestroy(ctx->copyStream); ctx->copyStream = nullptr; }
+}
 
 extern "C" {
 
@@ -179,6 +213,7 @@ int cpf_create(const cpf_config *cfg, cpf_context **out)
         (e = cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * CNT_COUNT)) != cudaSuccess ||
         (e = cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * CNT_COUNT)) != cudaSuccess) {
         g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
+        destroy_handles(ctx); // whatever was created before the failing call (every handle starts as nullptr)
         delete ctx;
         return CPF_ERR_CUDA;
     }
@@ -233,11 +268,9 @@ int cpf_destroy(cpf_context *ctx)
     release_mesh(ctx);
     comm_release(ctx);
     stats_release(ctx);
-    cudaFree(ctx->d_counters); cudaFree(ctx->d_sort_hist); cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_sort_hist); cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evCopy); cudaEventDestroy(ctx->evRead[0]); cudaEventDestroy(ctx->evRead[1]);
-    for (cudaEvent_t ev : ctx->profEvents) cudaEventDestroy(ev);
-    cudaStreamDestroy(ctx->ownStream); cudaStreamDestroy(ctx->copyStream);
+    destroy_handles(ctx);
     delete ctx;
     return CPF_OK;
 }
@@ -276,9 +309,31 @@ static int upload_patch_kinds(cpf_context *ctx, int nPatches, const int *patchKi
 {
     ctx->nPatches = nPatches > 0 ? nPatches : 1;
     std::vector<uint8_t> k((size_t)ctx->nPatches, (uint8_t)CPF_PATCH_REFLECT);
-    if (patchKind) for (int p = 0; p < nPatches; ++p) k[(size_t)p] = (uint8_t)patchKind[p];
+    if (patchKind)
+        for (int p = 0; p < nPatches; ++p) {
+            if (patchKind[p] != CPF_PATCH_REFLECT && patchKind[p] != CPF_PATCH_ESCAPE) return fail(ctx, CPF_ERR_INVALID, "patchKind[%d] = %d is not a cpf_patch_kind", p, patchKind[p]);
+            k[(size_t)p] = (uint8_t)patchKind[p];
+        }
     CPF_CUDA(ctx, cudaMalloc(&ctx->d_patch_kind, k.size()));
     CPF_CUDA(ctx, cudaMemcpy(ctx->d_patch_kind, k.data(), k.size(), cudaMemcpyHostToDevice));
+    const std::vector<double> gain((size_t)ctx->nPatches, 2.0); // specular everywhere, as the reference
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_patch_gain, sizeof(double) * gain.size()));
+    CPF_CUDA(ctx, cudaMemcpy(ctx->d_patch_gain, gain.data(), sizeof(double) * gain.size(), cudaMemcpyHostToDevice));
+    return CPF_OK;
+}
+
+extern "C" int cpf_set_patch_restitution(cpf_context *ctx, int nPatches, const double *e)
+{
+    if (!ctx || !ctx->have_mesh || !e) return fail(ctx, CPF_ERR_INVALID, "cpf_set_patch_restitution: no mesh or null table");
+    if (nPatches != ctx->nPatches) return fail(ctx, CPF_ERR_INVALID, "cpf_set_patch_restitution: %d coefficients for %d patches", nPatches, ctx->nPatches);
+    std::vector<double> gain((size_t)nPatches);
+    for (int p = 0; p < nPatches; ++p) {
+        if (!(e[p] > 0.0 && e[p] <= 1.0)) return fail(ctx, CPF_ERR_INVALID, "restitution[%d] = %g is outside (0, 1]", p, e[p]);
+        gain[(size_t)p] = 1.0 + e[p];
+    }
+    cudaSetDevice(ctx->device);
+    CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // kernels in flight read the table
+    CPF_CUDA(ctx, cudaMemcpy(ctx->d_patch_gain, gain.data(), sizeof(double) * gain.size(), cudaMemcpyHostToDevice));
     return CPF_OK;
 }
 
@@ -290,6 +345,10 @@ int cpf_mesh_upload_poly(cpf_context *ctx, int nPoints, const double *points, in
     if (!points || !faceOffsets || !faceVerts || !owner || (nInternal > 0 && !neighbour) || !cellCentres || nPoints <= 0 ||
         nFaces <= 0 || nCells <= 0 || nInternal < 0 || nInternal > nFaces)
         return fail(ctx, CPF_ERR_INVALID, "cpf_mesh_upload_poly: bad arguments");
+    if (nPatches < 0 || (nPatches > 0 && !patchStart)) return fail(ctx, CPF_ERR_INVALID, "cpf_mesh_upload_poly: patchStart missing");
+    for (int p = 0; p < nPatches; ++p)
+        if (patchStart[p] < nInternal || patchStart[p] > patchStart[p + 1] || patchStart[p + 1] > nFaces)
+            return fail(ctx, CPF_ERR_INVALID, "patchStart[%d..%d] = %d..%d is not a face range behind the %d internal faces", p, p + 1, patchStart[p], patchStart[p + 1], nInternal);
     cudaSetDevice(ctx->device);
     // --- the glue's decomposition (src/initCuda.H:86-110): cell by cell, face by face of the
     // cell (owned faces ascending, then neighbour faces ascending), one tet per face-fan triangle
@@ -550,6 +609,9 @@ int cpf_set_tets(cpf_context *ctx, const int *tet)
 {
     if (!ctx || !tet || ctx->n == 0) return fail(ctx, CPF_ERR_INVALID, "cpf_set_tets: no particles");
     if (ctx->permuted) return fail(ctx, CPF_ERR_INVALID, "cpf_set_tets after a sort is not supported");
+    if (ctx->have_mesh)
+        for (long long i = 0; i < ctx->n; ++i)
+            if (tet[i] >= ctx->nTets) return fail(ctx, CPF_ERR_INVALID, "cpf_set_tets: tet[%lld] = %d, the mesh has %lld tets", i, tet[i], ctx->nTets);
     cudaSetDevice(ctx->device);
     CPF_CUDA(ctx, cudaMemcpyAsync(ctx->d_tet[ctx->pcur], tet, sizeof(int) * (size_t)ctx->n, cudaMemcpyHostToDevice, ctx->stream));
     CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -709,13 +771,17 @@ int cpf_download(cpf_context *ctx, double *xyzw, double *vel, int *tet)
 int cpf_download_cells(cpf_context *ctx, int *cell)
 {
     if (!ctx || !cell || !ctx->have_mesh) return fail(ctx, CPF_ERR_INVALID, "cpf_download_cells: bad arguments");
-    std::vector<int> tet((size_t)ctx->n);
-    int rc = cpf_download(ctx, nullptr, nullptr, tet.data());
+    if (ctx->n == 0) return CPF_OK;
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)ctx->n;
+    int rc = ensure_scratch(ctx, sizeof(int) * n);
     if (rc) return rc;
-    std::vector<int> tv((size_t)ctx->nTets * 4), tc((size_t)ctx->nTets);
-    rc = cpf_mesh_download_tets(ctx, tv.data(), tc.data());
-    if (rc) return rc;
-    for (long long i = 0; i < ctx->n; ++i) cell[i] = tet[(size_t)i] >= 0 ? tc[(size_t)tet[(size_t)i]] : -1;
+    // tet -> cell on the device, scattered to ORIGINAL particle order (4 bytes per particle cross PCIe, not the tet table)
+    k_particle_cells<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(mesh_view(ctx), ctx->n, ctx->d_tet[ctx->pcur], ctx->d_pid[ctx->pcur], (int *)ctx->d_scratch);
+    ctx->launches++;
+    CPF_CUDA(ctx, cudaGetLastError());
+    CPF_CUDA(ctx, cudaMemcpyAsync(cell, ctx->d_scratch, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CPF_OK;
 }
 

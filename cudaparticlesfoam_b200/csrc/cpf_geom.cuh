@@ -103,6 +103,7 @@ struct MeshView {
     const double4 *__restrict__ ucell; // [nCells] (ux,uy,uz,0): one 256-bit load per velocity fetch
     const double *__restrict__ uvert; // [nVerts][3] (CPF_INTERP_VERTEX)
     const uint8_t *__restrict__ patch_kind; // [nPatches]
+    const double *__restrict__ patch_gain;  // [nPatches] 1 + restitution coefficient of the patch (2 = specular, the reference)
     int nPoints;
     long long nTets;
     int nCells;
@@ -201,7 +202,16 @@ CPF_DEV int trace_exact(const Tet &T, D3 &S, D3 E, int in_j)
 
 // query/ConvexQuery.cu:239-317 reflectInTet.  When no face matches, the source reads uninitialised
 // P_reflect/u_reflect; the compiled reference leaves E and u untouched, as here.
-CPF_DEV void reflect_exact(const Tet &T, D3 Pxf, D3 &E, D3 &u)
+// Rebound model (extension): the mirrored part is scaled by the restitution coefficient e of the patch the
+// matching face lies on, sp = -(1 + e) (E - A).n; e = 1 (gain 2) is the reference's specular reflection bit for bit
+// (2 s == s + s).  Faces that are not boundary faces (the reference may match one in degenerate cases) reflect specularly.
+CPF_DEV double face_gain(const MeshView &m, const Tet &T, int j)
+{
+    const int link = link_at(T.link, j);
+    return link < 0 ? __ldg(m.patch_gain - link - 1) : 2.0;
+}
+
+CPF_DEV void reflect_exact(const MeshView &m, const Tet &T, D3 Pxf, D3 &E, D3 &u)
 {
     const D3 d = xsub(E, Pxf);
 #pragma unroll
@@ -215,11 +225,12 @@ CPF_DEV void reflect_exact(const Tet &T, D3 Pxf, D3 &E, D3 &u)
         if (fabs(dT) < CPF_TOL) dT = CPF_TOL;
         if (fabs(fd) < CPF_TOL) fd = CPF_TOL;
         if (dT == CPF_TOL || fd == CPF_TOL) {
+            const double gain = face_gain(m, T, j);
             D3 r = xsub(E, A);
             double sp = -__fma_rn(r.z, n.z, __fma_rn(r.y, n.y, __dmul_rn(r.x, n.x)));
-            sp = __dadd_rn(sp, sp);
+            sp = __dmul_rn(gain, sp);
             double sv = -__fma_rn(u.z, n.z, __fma_rn(u.y, n.y, __dmul_rn(u.x, n.x)));
-            sv = __dadd_rn(sv, sv);
+            sv = __dmul_rn(gain, sv);
             E = D3{ __fma_rn(sp, n.x, E.x), __fma_rn(sp, n.y, E.y), __fma_rn(sp, n.z, E.z) };
             u = D3{ __fma_rn(sv, n.x, u.x), __fma_rn(sv, n.y, u.y), __fma_rn(sv, n.z, u.z) };
             return;
@@ -533,7 +544,7 @@ CPF_DEV bool exact_crossing(const MeshView &m, int tet, int js, bool flipped, co
     return true;
 }
 
-CPF_DEV bool wall_reflect_on_path(const MeshView &m, int startTet, unsigned path, int nHops, int wallTet, int js, const D3 &P,
+CPF_DEV bool wall_reflect_on_path(const MeshView &m, int startTet, unsigned path, int nHops, int wallTet, int js, int wallLink, const D3 &P,
                                   const D3 &disp, D3 &Phit, D3 &E, D3 &u)
 {
     E = xadd(P, disp);
@@ -552,11 +563,12 @@ CPF_DEV bool wall_reflect_on_path(const MeshView &m, int startTet, unsigned path
     if (!exact_crossing(m, cur, js, flipped, E, S, A, n)) return false;
     Phit = S;
     if (!(fabs(xdot(xsub(A, Phit), n)) < CPF_TOL)) return false;
+    const double gain = __ldg(m.patch_gain - wallLink - 1);
     const D3 r = xsub(E, A);
     double sp = -__fma_rn(r.z, n.z, __fma_rn(r.y, n.y, __dmul_rn(r.x, n.x)));
-    sp = __dadd_rn(sp, sp);
+    sp = __dmul_rn(gain, sp);
     double sv = -__fma_rn(u.z, n.z, __fma_rn(u.y, n.y, __dmul_rn(u.x, n.x)));
-    sv = __dadd_rn(sv, sv);
+    sv = __dmul_rn(gain, sv);
     E = D3{ __fma_rn(sp, n.x, E.x), __fma_rn(sp, n.y, E.y), __fma_rn(sp, n.z, E.z) };
     u = D3{ __fma_rn(sv, n.x, u.x), __fma_rn(sv, n.y, u.y), __fma_rn(sv, n.z, u.z) };
     return true;

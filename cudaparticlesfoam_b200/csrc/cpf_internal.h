@@ -78,6 +78,7 @@ struct cpf_context {
     double *d_uvert = nullptr;
     int *d_pc_off = nullptr, *d_pc_cells = nullptr; // point -> cells CSR (vertex interpolation from the cell field)
     uint8_t *d_patch_kind = nullptr;
+    double *d_patch_gain = nullptr; // [nPatches] 1 + restitution coefficient (2 = the reference's specular reflection)
     double guard = 1e-7, hmin = 0.0;
     bool filter_ok = true; // coordinates small enough against the smallest tet for the filtered walk (cpf_mesh.cu)
     double bbox_lo[3] = { 0, 0, 0 }, bbox_hi[3] = { 0, 0, 0 };

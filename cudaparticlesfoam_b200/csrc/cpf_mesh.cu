@@ -246,21 +246,10 @@ __global__ void k_pack_positions(long long n, const double *__restrict__ xyz, do
     if (i < n) out[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0);
 }
 
-int fail(cpf_context *ctx, int code, const char *fmt, ...)
-{
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    if (ctx) ctx->err = buf;
-    return code;
-}
-
 static void free_mesh(cpf_context *ctx)
 {
     cudaFree(ctx->d_vpos); cudaFree(ctx->d_tetv); cudaFree(ctx->d_tetrec); cudaFree(ctx->d_tetfast); cudaFree(ctx->d_tetnrm); cudaFree(ctx->d_tetcode); cudaFree(ctx->d_tetcell);
-    cudaFree(ctx->d_ucell[0]); cudaFree(ctx->d_ucell[1]); cudaFree(ctx->d_ustage); ctx->d_ustage = nullptr; cudaFree(ctx->d_uvert); cudaFree(ctx->d_patch_kind); cudaFree(ctx->d_pc_off); cudaFree(ctx->d_pc_cells);
+    cudaFree(ctx->d_ucell[0]); cudaFree(ctx->d_ucell[1]); cudaFree(ctx->d_ustage); ctx->d_ustage = nullptr; cudaFree(ctx->d_uvert); cudaFree(ctx->d_patch_kind); cudaFree(ctx->d_patch_gain); ctx->d_patch_gain = nullptr; cudaFree(ctx->d_pc_off); cudaFree(ctx->d_pc_cells);
     ctx->d_vpos = nullptr; ctx->d_tetv = nullptr; ctx->d_tetrec = nullptr; ctx->d_tetfast = nullptr; ctx->d_tetnrm = nullptr; ctx->d_tetcode = nullptr; ctx->d_tetcell = nullptr;
     ctx->d_ucell[0] = ctx->d_ucell[1] = nullptr; ctx->d_uvert = nullptr; ctx->d_patch_kind = nullptr; ctx->d_pc_off = ctx->d_pc_cells = nullptr;
     free_bvh(ctx);
@@ -416,6 +405,7 @@ MeshView mesh_view(const cpf_context *ctx)
     m.ucell = ctx->d_ucell[ctx->ucur];
     m.uvert = ctx->d_uvert;
     m.patch_kind = ctx->d_patch_kind;
+    m.patch_gain = ctx->d_patch_gain;
     m.nPoints = ctx->nPoints; m.nTets = ctx->nTets; m.nCells = (int)ctx->nCells;
     m.guard = ctx->guard;
     m.guardf = (float)ctx->guard * 1.0000002f;

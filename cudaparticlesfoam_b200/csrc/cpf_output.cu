@@ -27,6 +27,8 @@
 #include <thread>
 #include <vector>
 
+#include <new>
+
 #include "cpf_internal.h"
 
 using namespace cpf;
@@ -407,17 +409,31 @@ int cpf_checkpoint_load(cpf_context *ctx, const char *path)
         fclose(fp);
         return fail(ctx, CPF_ERR_INVALID, "cpf_checkpoint_load: random-walk generator or seed differs from the checkpointed run");
     }
+    // the particle count comes from the file: bound it by the file's own size before anything is allocated from it
+    const long at = ftell(fp);
+    fseek(fp, 0, SEEK_END);
+    const long long fileLeft = (long long)ftell(fp) - at;
+    fseek(fp, at, SEEK_SET);
+    const long long perParticle = (long long)(sizeof(double) * 8 + sizeof(int) + (h.has_rng_state ? sizeof(curandState_t) : 0));
+    if (h.n >= (1ll << 31) || h.n * perParticle > fileLeft) {
+        fclose(fp);
+        return fail(ctx, CPF_ERR_INVALID, "cpf_checkpoint_load: %s claims %lld particles but holds %lld bytes of state", path, h.n, fileLeft);
+    }
     const size_t n = (size_t)h.n;
-    std::vector<double> p(n * 4), v(n * 4);
-    std::vector<int> tet(n);
+    std::vector<double> p, v;
+    std::vector<int> tet;
     std::vector<curandState_t> states;
+    try { // the ABI never throws
+        p.resize(n * 4); v.resize(n * 4); tet.resize(n);
+        if (h.has_rng_state) states.resize(n);
+    } catch (const std::bad_alloc &) {
+        fclose(fp);
+        return fail(ctx, CPF_ERR_NOMEM, "cpf_checkpoint_load: out of host memory for %lld particles", h.n);
+    }
     bool ok = true;
     if (n) {
         ok = fread(p.data(), sizeof(double) * 4, n, fp) == n && fread(v.data(), sizeof(double) * 4, n, fp) == n && fread(tet.data(), sizeof(int), n, fp) == n;
-        if (ok && h.has_rng_state) {
-            states.resize(n);
-            ok = fread(states.data(), sizeof(curandState_t), n, fp) == n;
-        }
+        if (ok && h.has_rng_state) ok = fread(states.data(), sizeof(curandState_t), n, fp) == n;
     }
     fclose(fp);
     if (!ok) return fail(ctx, CPF_ERR_INVALID, "cpf_checkpoint_load: %s is truncated", path);

@@ -33,7 +33,16 @@ __global__ void k_scatter(const MeshView m, long long n, int *__restrict__ curso
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int t = tet[i];
-    const int dst = atomicAdd(cursor + sort_key(m, t), 1);
+    // particles arrive nearly sorted: neighbouring lanes mostly share the key, so one atomic per (warp, key) instead of
+    // one per particle; the lanes of a group take consecutive slots in lane order (keeps equal keys in their old order)
+    const int key = sort_key(m, t);
+    const unsigned act = __activemask();
+    const unsigned grp = __match_any_sync(act, key);
+    const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(cursor + key, __popc(grp));
+    base = __shfl_sync(act, base, leader);
+    const int dst = base + __popc(grp & ((1u << lane) - 1u));
     pos2[dst] = pos[i];
     tet2[dst] = t;
     pid2[dst] = pid[i];

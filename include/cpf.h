@@ -116,6 +116,12 @@ int cpf_mesh_upload_poly(cpf_context *ctx, int nPoints, const double *points, in
                          const int *faceOffsets, const int *faceVerts, const int *owner, int nInternal,
                          const int *neighbour, int nCells, const double *cellCentres, const int *tetBasePt,
                          int nPatches, const int *patchStart, const int *patchKind);
+/* Per-patch rebound model (extension; the reference reflects specularly everywhere,
+ * query/ConvexQuery.cu:287-295, query/RTQuery.cu:92-107, 165-166 TODO): restitution coefficient
+ * e[p] in (0, 1] of every boundary patch; at a wall contact the normal part of the remaining
+ * displacement and of the reported velocity is returned scaled by e (x' = x - (1 + e)(x.n) n).
+ * e = 1 everywhere (the default) is the reference bit for bit.  Call after the mesh upload. */
+int cpf_set_patch_restitution(cpf_context *ctx, int nPatches, const double *e);
 /* Same for an explicit tet list (HostTetMesh{positions,indices}); tetCell may be NULL (tet == cell). */
 int cpf_mesh_upload_tets(cpf_context *ctx, int nVerts, const double *positions, long long nTets,
                          const int *tetVerts, const int *tetCell, int nCells);

@@ -40,6 +40,7 @@ typedef struct {
     int integrator;            /* 0 Euler, 1 RK2 (midpoint), 4 RK4 */
     int vertexVelocity;        /* 0: U is [nTets][3], 1: U is [nVerts][3] (P1 / cellPoint-style) */
     const unsigned char *faceKind; /* [nFaces] 0 reflect, 1 escape; NULL = all reflect */
+    const double *faceGain;        /* [nFaces] 1 + restitution coefficient of the face's patch; NULL = 2 (specular) everywhere */
     const double *U;
 } ext_opts;
 
@@ -114,6 +115,35 @@ static void ext_s1(double *p, int tet, double *vel, double *disp, double dt, con
     vel[0] = v.x; vel[1] = v.y; vel[2] = v.z; vel[3] = -1.0;
 }
 
+/* reflectInTet (cpf_oracle.c reflect_in_tet) with the rebound model: the mirrored part of the end point and of the
+ * velocity is scaled by gain = 1 + e of the matching face's patch; gain = 2 reproduces s + s bit for bit. */
+static void ext_reflect_in_tet(v3 Pxf, v3 *P_end, v3 *vel, int tet, const orc_mesh *m, const double *faceGain)
+{
+    const double tol = ORC_TOL;
+    const v3 d = v3_sub(*P_end, Pxf);
+    for (int i = 0; i < 4; ++i) {
+        const int f = m->tetfacets[4 * tet + i];
+        v3 A;
+        v3 n = face_inward_normal(m, f, tet, &A);
+        double face_dist = ref_dot(v3_sub(A, Pxf), n);
+        double dT = face_dist / ref_dot(d, n);
+        if (isinf(dT)) dT = -1.0;
+        if (fabs(dT) < tol) dT = tol;
+        if (fabs(face_dist) < tol) face_dist = tol;
+        if (dT == tol || face_dist == tol) {
+            const double gain = faceGain ? faceGain[f] : 2.0;
+            v3 r = v3_sub(*P_end, A);
+            double sp = -fma(r.z, n.z, fma(r.y, n.y, r.x * n.x));
+            sp = gain * sp;
+            double sv = -fma(vel->z, n.z, fma(vel->y, n.y, vel->x * n.x));
+            sv = gain * sv;
+            P_end->x = fma(sp, n.x, P_end->x); P_end->y = fma(sp, n.y, P_end->y); P_end->z = fma(sp, n.z, P_end->z);
+            vel->x = fma(sv, n.x, vel->x); vel->y = fma(sv, n.y, vel->y); vel->z = fma(sv, n.z, vel->z);
+            return;
+        }
+    }
+}
+
 /* S4 generalised: convexReflector with a per-patch action at every wall contact.  ESCAPE: the
  * particle is parked at the exit point, deactivated (w = 0) and keeps the negative id
  * -(tet at exit + 1); returns 1 when the particle escaped. */
@@ -144,7 +174,7 @@ static int ext_s4(double *p, double *disp, double *vel, int *tetIO, const orc_me
             *tetIO = -(cur + 1);
             return 1;
         }
-        reflect_in_tet(P_hit, &P_end, &u, cur, m);
+        ext_reflect_in_tet(P_hit, &P_end, &u, cur, m, o->faceGain);
     }
     v3 nd = v3_sub(P_end, P_hit);
     p[0] = P_hit.x; p[1] = P_hit.y; p[2] = P_hit.z;
@@ -157,10 +187,10 @@ static int ext_s4(double *p, double *disp, double *vel, int *tetIO, const orc_me
 /* generalised sub-step loop (default ConvexPoly build only); returns the number of escapes */
 long orc_ext_substeps(long n, int nSteps, double *p, int *tet, double *vel, double *disp, double dt,
                       MESH_ARGS, const double *U, int vertexVelocity, int integrator,
-                      const unsigned char *faceKind, int reflectWall, const double *xi, double D)
+                      const unsigned char *faceKind, int reflectWall, const double *xi, double D, const double *faceGain)
 {
     MESH_INIT;
-    ext_opts o = { integrator, vertexVelocity, faceKind, U };
+    ext_opts o = { integrator, vertexVelocity, faceKind, faceGain, U };
     long escaped = 0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : escaped)
     for (long i = 0; i < n; ++i) {

@@ -269,6 +269,19 @@ def face_kinds(pm, mesh: TetMesh, patch_kind) -> np.ndarray:
     return kinds
 
 
+def face_gains(pm, mesh: TetMesh, restitution) -> np.ndarray:
+    """[nFaces] float64 gain = 1 + restitution coefficient of the patch a boundary face lies on (2 elsewhere)."""
+    restitution = np.asarray(restitution, dtype=np.float64)
+    poly_patch = np.full(pm.n_faces, -1, dtype=np.int64)
+    for p in range(len(pm.patch_starts) - 1):
+        poly_patch[pm.patch_starts[p]:pm.patch_starts[p + 1]] = p
+    tf = tet_polyface(pm)
+    gains = np.full(mesh.n_faces, 2.0)
+    bd = poly_patch[tf] >= 0
+    gains[mesh.tetfacets[bd, 0]] = 1.0 + restitution[poly_patch[tf[bd]]]
+    return gains
+
+
 def point_values(pm, Ucell) -> np.ndarray:
     Uv = np.empty((pm.n_points + pm.n_cells, 3))
     lib().orc_point_values(C.c_int(pm.n_points), C.c_int(pm.n_cells), C.c_int(pm.n_faces), C.c_int(pm.n_internal), _i(pm.face_offsets),
@@ -278,7 +291,7 @@ def point_values(pm, Ucell) -> np.ndarray:
 
 
 def ext_substeps(mesh: TetMesh, cl: Cloud, U, n_steps, dt, *, vertex_velocity=False, integrator=0, face_kind=None, reflect=True,
-                 xi=None, D=0.0) -> int:
+                 xi=None, D=0.0, face_gain=None) -> int:
     """Generalised loop of oracle/cpf_oracle_ext.c (RK2=1 / RK4=4, vertex interpolation, escape patches)."""
     L = lib()
     L.orc_ext_substeps.restype = C.c_long
@@ -293,7 +306,8 @@ def ext_substeps(mesh: TetMesh, cl: Cloud, U, n_steps, dt, *, vertex_velocity=Fa
         fk = face_kind.ctypes.data_as(C.POINTER(C.c_ubyte))
     return int(L.orc_ext_substeps(C.c_long(cl.n), C.c_int(n_steps), _d(cl.p), _i(cl.tet), _d(cl.vel), _d(cl.disp), C.c_double(dt),
                                   *mesh.args(), _d(U), C.c_int(int(vertex_velocity)), C.c_int(int(integrator)), fk,
-                                  C.c_int(int(reflect)), xp, C.c_double(D)))
+                                  C.c_int(int(reflect)), xp, C.c_double(D),
+                                  None if face_gain is None else _d(np.ascontiguousarray(face_gain, dtype=np.float64))))
 
 
 def move(cl):
