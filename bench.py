@@ -207,7 +207,8 @@ class Rig:
         rng = {"philox": api.RNG_PHILOX, "xorwow": api.RNG_XORWOW, "none": api.RNG_NONE}[rng_name] if w["D"] > 0 else api.RNG_NONE
         self.tr = tr = api.ParticleTracker(device=local_rank, rng=rng, diffusion_coeff=w["D"], dt=w["dt"], sort_interval=args.sort_interval,
                                            fuse_substeps=args.fuse, path=api.PATH_EXACT if args.exact else api.PATH_FILTERED, integrator=integ,
-                                           interp=api.INTERP_VERTEX if args.interp == "vertex" else api.INTERP_TET)
+                                           interp=api.INTERP_VERTEX if args.interp == "vertex" else api.INTERP_TET,
+                                           locator=api.LOCATOR_BARY if getattr(args, "locator", "convex") == "bary" else api.LOCATOR_CONVEX)
         # one explicit non-default stream shared by torch (pinned copies, timing events) and the library
         self.stream = torch.cuda.Stream(device=self.dev)
         torch.cuda.set_stream(self.stream)
@@ -244,14 +245,16 @@ class Rig:
         self.h2d = self.pm.n_cells * 24
         self.d2h = 0
 
-    # U already resident in HBM (on rank 0; the library broadcasts it over NCCL when world > 1)
+    # U already resident in HBM (on rank 0; the library broadcasts it over NCCL when world > 1, one step ahead: the
+    # exchange of U(k+1) runs on the library's copy stream beside the sub-steps of step k)
     def step_resident(self, k):
         tr = self.tr
         if self.world == 1:
             tr.update_velocity_ptr(self.u_dev[k % len(self.u_dev)].data_ptr(), True)
+            tr.advect(None, self.deltaT)
         else:
-            tr.update_velocity_bcast(self.u_dev[k % len(self.fields)].data_ptr() if self.rank == 0 else None, root=0, on_device=True)
-        tr.advect(None, self.deltaT)
+            tr.advect(None, self.deltaT)
+            tr.update_velocity_bcast(self.u_dev[(k + 1) % len(self.fields)].data_ptr() if self.rank == 0 else None, root=0, on_device=2)
         if self.reseed_every and (k + 1) % self.reseed_every == 0:
             tr.reseed_inactive(*self.slab)
 
@@ -392,7 +395,7 @@ def run_ours(args, w, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": cfg,
         "details": {"rng": args.rng if w["D"] > 0 else "none", "substeps_per_launch": sub_per_launch, "sort_interval": args.sort_interval,
-                    "initial_order": "shuffled" if args.shuffled else "sorted by cell", "path": "exact" if args.exact else "filtered",
+                    "initial_order": "shuffled" if args.shuffled else "sorted by cell", "path": "exact" if (args.exact or args.locator == "bary") else "filtered", "locator": args.locator,
                     "e2e_path": ("pinned host U -> cpf_update_velocity (H2D + repack on the copy stream, one step ahead of the sub-steps) -> "
                                  "cpf_advect -> cpf_stats_request / cpf_stats_collect (one step late)" if world == 1 else
                                  "rank 0 pinned host U -> cpf_update_velocity_bcast (H2D + ncclBroadcast + repack on the copy stream, one step ahead) "
@@ -599,6 +602,7 @@ def main():
     ap.add_argument("--sort-interval", type=int, default=50)
     ap.add_argument("--integrator", choices=["euler", "rk2", "rk4"], default=None, help="default: the workload's (C2 is RK2, C4 RK4; reference is Euler)")
     ap.add_argument("--interp", choices=["cell", "vertex"], default="cell", help="vertex = cellPoint-style interpolation (extension; reference default is the cell value)")
+    ap.add_argument("--locator", choices=["convex", "bary"], default="convex", help="bary = the reference's RTX=true build (barycentric point walk + RTreflection): reference arithmetic only")
     ap.add_argument("--shuffled", action="store_true", help="locality probe (SURVEY 8d): no initial sort by cell; combine with --sort-interval 0")
     ap.add_argument("--fuse", type=int, default=10, help="sub-steps per launch sequence (0 = library default)")
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default: the workload's)")

@@ -287,8 +287,9 @@ class ParticleTracker:
         self._chk(self.lib.cpf_comm_info(self.h, C.byref(r), C.byref(n), C.byref(v)))
         return r.value, n.value, v.value
 
-    def update_velocity_bcast(self, U, root: int = 0, on_device: bool = False):
-        """U: numpy cell field / device pointer on `root`, None elsewhere."""
+    def update_velocity_bcast(self, U, root: int = 0, on_device=False):
+        """U: numpy cell field / device pointer on `root`, None elsewhere.  on_device: False/0 host, True/1 device memory ready
+        in compute-stream order, 2 device memory that is complete already (the exchange overlaps the enqueued sub-steps)."""
         if U is None:
             self._chk(self.lib.cpf_update_velocity_bcast(self.h, None, 0, int(root)))
         elif isinstance(U, (int, np.integer)):

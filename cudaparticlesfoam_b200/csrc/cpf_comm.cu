@@ -203,7 +203,7 @@ int cpf_update_velocity_bcast(cpf_context *ctx, const double *U, int on_device, 
     // a DEVICE source is ready in compute-stream order: the copy stream waits for "now" there.  A host source needs no
     // such wait (that wait would put the exchange of step k+1 behind the sub-steps of step k instead of beside them);
     // the staging buffer itself is only ever touched on the copy stream.
-    if (c->rank == root && on_device) { rc = field_exchange_begin(ctx); if (rc) return rc; }
+    if (c->rank == root && on_device == 1) { rc = field_exchange_begin(ctx); if (rc) return rc; } // on_device == 2: complete already
     const double *src = c->d_stage;
     if (c->rank == root) {
         if (on_device) src = U; // broadcast straight out of the caller's device buffer (ready in compute-stream order)
@@ -225,7 +225,7 @@ int cpf_update_velocity_slices(cpf_context *ctx, long long cellOffset, long long
     int rc = ensure_stage(ctx, bytes);
     if (rc) return rc;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (on_device) { rc = field_exchange_begin(ctx); if (rc) return rc; }
+    if (on_device == 1) { rc = field_exchange_begin(ctx); if (rc) return rc; }
     if (nLocal) CPF_CUDA(ctx, cudaMemcpyAsync(c->d_stage + 3 * cellOffset, Ulocal, sizeof(double) * 3 * (size_t)nLocal, kind, ctx->copyStream));
     if (c->nranks > 1) {
         // the slice table is exchanged once (and again whenever this rank's slice changes): 2 x 8 bytes per rank

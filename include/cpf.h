@@ -203,7 +203,11 @@ int cpf_comm_unique_id(void *id, size_t bytes);
 int cpf_comm_init(cpf_context *ctx, const void *id, size_t bytes, int rank, int nranks);
 int cpf_comm_info(cpf_context *ctx, int *rank, int *nranks, int *ncclVersion);
 /* The coupled solver's per-step field: `root` passes the whole cell field (host or device memory), the
- * others pass NULL; ncclBroadcast + repack on the context's stream (src/advect.H:44-57 + 59-89). */
+ * others pass NULL; upload (root), ncclBroadcast and repack run on the library's copy stream with their
+ * own communicator, beside the sub-steps already enqueued (src/advect.H:44-57 + 59-89).  on_device: 0 = host
+ * memory, 1 = device memory that is ready in the order of the context's stream (the exchange then starts
+ * after the work enqueued so far), 2 = device memory whose contents are complete already (no ordering:
+ * the exchange of step k+1 overlaps the sub-steps of step k). */
 int cpf_update_velocity_bcast(cpf_context *ctx, const double *U, int on_device, int root);
 /* Decomposed solver runs: every rank passes only the nLocal cells it owns, as global
  * cell ids [cellOffset, cellOffset + nLocal) of the replicated mesh; the slices are exchanged
