@@ -861,9 +861,12 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 #define CPF_LEAN_SMEM_STATE 0 /* 1: displacement and activity flag of a lane live in shared memory instead of 8 registers */
 #endif
 #define CPF_LEAN_SMEM_BYTES(nSub, xiBytes, stateful) ((size_t)CPF_LEAN_THREADS * ((size_t)(xiBytes) * 3 * (size_t)(nSub) + (CPF_LEAN_SMEM_STATE ? 32 : 0) + ((stateful) ? sizeof(curandState_t) : 0)))
-template <int RNG, bool CFV>
+//   * LOC = CPF_LOCATOR_BARY (RTX=true build): the same kernel around visit_bary32 -- the walk goes towards the end point
+//     Q = P + disp (kept where the convex walk keeps disp), no start-point check, walls always deferred.
+template <int RNG, bool CFV, int LOC = CPF_LOCATOR_CONVEX>
 __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / CPF_LEAN_THREADS) k_lean(const MeshView m, const ParticleView pv, const StepParams sp)
 {
+    constexpr bool BARY = LOC == CPF_LOCATOR_BARY;
     constexpr int NT = CPF_LEAN_THREADS;
     typedef typename Rng<RNG>::Xi Xi;
     constexpr bool STATEFUL = Rng<RNG>::STATEFUL;
@@ -902,7 +905,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
             f32_load(m, tet, f);
             org = first_origin<CF>(m, tet, f);
             O = ld_vertex(m.vpos, org);
-            if (start_point_clear(m, f, (float)(P.x - O.x), (float)(P.y - O.y), (float)(P.z - O.z))) mode = 0;
+            if (BARY || start_point_clear(m, f, (float)(P.x - O.x), (float)(P.y - O.y), (float)(P.z - O.z))) mode = 0;
             else deferAt = 0;
         }
     }
@@ -919,18 +922,22 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
                 disp.y = __fma_rn((double)x[NT], sp.randDisp, disp.y);
                 disp.z = __fma_rn((double)x[2 * NT], sp.randDisp, disp.z);
             }
-            walkf_begin(ws, O, P, disp, tet, org, false);
+            if (BARY) {
+                disp = xadd(P, disp); // Q: the point the barycentric walk looks for, and the S5 result
+                walkf_begin(ws, O, disp, D3{ 0.0, 0.0, 0.0 }, tet, org, false);
+            } else walkf_begin(ws, O, P, disp, tet, org, false);
             if (CPF_LEAN_SMEM_STATE) { sd[0] = disp.x; sd[NT] = disp.y; sd[2 * NT] = disp.z; }
             visits = 0;
             mode = 1;
         }
         if (mode == 1) {
             ++visits;
-            const int oc = visit_fast32<false, CF>(m, f, O, P, ws, visits >= 48);
+            const int oc = BARY ? visit_bary32<CF>(m, f, O, disp, ws, visits >= 48) : visit_fast32<false, CF>(m, f, O, P, ws, visits >= 48);
             if (oc == CPF_V_DONE) {
                 tet = ws.cur;
                 org = ws.org;
-                if (CPF_LEAN_SMEM_STATE) P = xadd(P, D3{ sd[0], sd[NT], sd[2 * NT] });
+                if (BARY) P = CPF_LEAN_SMEM_STATE ? D3{ sd[0], sd[NT], sd[2 * NT] } : disp;
+                else if (CPF_LEAN_SMEM_STATE) P = xadd(P, D3{ sd[0], sd[NT], sd[2 * NT] });
                 else P = xadd(P, disp);
                 hops += (unsigned)visits;
                 mode = (++s >= sp.nSub) ? 2 : 0;
@@ -1103,6 +1110,28 @@ static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleVi
     return CPF_OK;
 }
 
+// RTX=true build on the filtered policy: all-particles pass around visit_bary32, then the exact finisher (k_exact<BARY>)
+// for what it refused -- wall contacts included: RTreflection always runs in the reference's arithmetic.
+template <int R>
+static int launch_filtered_bary(cpf_context *ctx, const MeshView &m, const ParticleView &pv, const StepParams &sp, dim3 grid, int nSub)
+{
+    typedef typename Rng<R>::Xi Xi;
+    constexpr bool STATEFUL = Rng<R>::STATEFUL;
+    cudaStream_t st = ctx->stream;
+    CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * 64, st));
+    StepParams a = sp;
+    a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
+    const dim3 lgrid((unsigned)((pv.n + CPF_LEAN_THREADS - 1) / CPF_LEAN_THREADS));
+    const size_t lb = CPF_LEAN_SMEM_BYTES(nSub, R == CPF_RNG_NONE ? 0 : sizeof(Xi), STATEFUL);
+    if (m.tetcell == nullptr) k_lean<R, true, CPF_LOCATOR_BARY><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
+    else k_lean<R, false, CPF_LOCATOR_BARY><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
+    StepParams z = sp;
+    z.queueIn = ctx->d_queue[0]; z.countIn = ctx->d_queue_count;
+    k_exact<CPF_LOCATOR_BARY, R, 2><<<dim3(std::min<unsigned>(grid.x, 148u * 8u)), 128, 0, st>>>(m, pv, z);
+    ctx->launches += 2;
+    return CPF_OK;
+}
+
 template <int R>
 static int launch_filtered_rng(cpf_context *ctx, const MeshView &m, const ParticleView &pv, const StepParams &sp, dim3 grid, int nSub)
 {
@@ -1156,8 +1185,14 @@ int launch_substeps(cpf_context *ctx, int nSub, double dt, bool writeVel)
     sp.interp = ctx->cfg.interp;
     const bool filteredOk = ctx->cfg.locator == CPF_LOCATOR_CONVEX && ctx->cfg.path == CPF_PATH_FILTERED && ctx->filter_ok;
     if (ctx->cfg.locator == CPF_LOCATOR_BARY) {
-        CPF_RNG_SWITCH(rng, (k_exact<CPF_LOCATOR_BARY, R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
-        ctx->launches++;
+        if (ctx->cfg.path == CPF_PATH_FILTERED && ctx->filter_ok) {
+            int rc = CPF_OK;
+            CPF_RNG_SWITCH(rng, (rc = launch_filtered_bary<R>(ctx, m, pv, sp, grid, nSub)));
+            if (rc) return rc;
+        } else {
+            CPF_RNG_SWITCH(rng, (k_exact<CPF_LOCATOR_BARY, R, 0><<<grid, 128, 0, st>>>(m, pv, sp)));
+            ctx->launches++;
+        }
     } else if (!filteredOk) {
         if (ctx->cfg.interp != CPF_INTERP_TET || ctx->cfg.integrator != CPF_EULER) { CPF_RNG_SWITCH(rng, (k_general<R, 0><<<grid, 128, 0, st>>>(m, pv, sp))); }
         else { CPF_RNG_SWITCH(rng, (k_exact_convex<R, 0><<<grid, 128, 0, st>>>(m, pv, sp))); }

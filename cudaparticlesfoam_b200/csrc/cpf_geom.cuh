@@ -517,6 +517,60 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
     return CPF_V_HOP;
 }
 
+// ------------------------------------------------------------------------------------------------
+// RTX=true build (CPF_LOCATOR_BARY): the reference's baryTetSearch (query/RTQuery.cu:35-90) does not walk the segment, it
+// walks towards the END POINT Q = P + disp: barycentric coordinates of Q in the current tet, inside if all >= 0, else
+// across the face of the smallest one.  On the fp32 record the four plane functions e_j = N_j . (Q - O) are V6 times those
+// coordinates, so the same walk is: all e_j >= g -> Q is certified inside (the reference's w_min >= 0 cannot depend on
+// rounding); else the smallest e_j must be clearly negative (<= -g) and clearly the smallest (gap to the runner-up >= 2 g:
+// the reference's first-minimum tie break never decides) -> hop across that face.  Boundary faces (the reflection of
+// RTreflection), the visit cap and everything unclear are refused: the exact kernel redoes the sub-step.
+// ws.rx.. hold Q - O (ws.dx.. unused, Dd = 0), ws.t_in > 0 marks "entered through a hop".
+// ------------------------------------------------------------------------------------------------
+template <int CFV>
+CPF_DEV int visit_bary32(const MeshView &m, Fast32 &f, D3 &O, const D3 &Q, WalkF &ws, bool lastVisit)
+{
+    if (ws.RD3 < 0.f) walkf_rebase(ws, O, Q);
+    const float (&N)[3][3] = f.N;
+    float e[4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) e[j] = ws.rx * N[j][0] + ws.ry * N[j][1] + ws.rz * N[j][2];
+    e[3] = f.V6 - e[0] - e[1] - e[2];
+    const float E = fabsf(f.E);
+    const float g = fmaf(m.guardf, f.V6, 3.814697265625e-6f * (E * E) * (E + ws.RD3));
+    float m1 = e[0];
+    int js = 0;
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+        if (e[j] < m1) { m1 = e[j]; js = j; }
+    if (m1 >= g) return CPF_V_DONE;
+    const float INF = __int_as_float(0x7f800000);
+    float m2 = INF;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m2 = fminf(m2, (j == js) ? INF : e[j]);
+    if (!(m1 <= -g) || !(m2 - m1 >= 2.f * g)) return CPF_V_REFUSE;
+    const int link = sel4(f.link.x, f.link.y, f.link.z, f.link.w, js);
+    if (link < 0 || lastVisit) return CPF_V_REFUSE; // boundary: RTreflection runs in the reference's arithmetic
+    ws.cur = link >> 2;
+    ws.t_in = 1.f;
+    if (mesh_is_cfv<CFV>(m)) {
+        if (js == 3) {
+            ws.org = f.aux;
+            O = ld_vertex(m.vpos, f.aux);
+            ws.RD3 = -1.f;
+        }
+        f32_load(m, ws.cur, f);
+    } else {
+        f32_load(m, ws.cur, f);
+        if (f.aux != ws.org) {
+            ws.org = f.aux;
+            O = ld_vertex(m.vpos, f.aux);
+            walkf_rebase(ws, O, Q);
+        }
+    }
+    return CPF_V_HOP;
+}
+
 // Wall contact on the first leg of a sub-step, in the reference's arithmetic but only for the faces the filter
 // has certified (C1-C3 passed at every visit; `path` holds the stored exit slot of each hop, 2 bits per hop; the
 // exit face js of the last tet is a boundary face):

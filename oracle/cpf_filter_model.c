@@ -305,4 +305,51 @@ void orc_filter_substep(long n, double *p, const double *disp, double *vel, int 
     }
 }
 
+/* ---- RTX=true build: the fp32 walk towards the END POINT (cpf_geom.cuh visit_bary32) ------------------------------------
+ * out[i] = tet certified to contain Q = P + disp, or -1 (refused: unclear minimum, boundary face, visit cap); to be compared
+ * with the reference's baryTetSearch (s3_locate_bary). */
+void orc_filter_bary_walk(long n, const double *p, const double *disp, const int *tet, const void *recsIn, const double *pos,
+                          double guard, double errScale, int *out, int *visits)
+{
+    const fm_rec *recs = (const fm_rec *)recsIn;
+    const float INF = INFINITY, G = (float)guard * 1.0000002f, ES = (float)errScale * 3.814697265625e-6f;
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) {
+        out[i] = -1;
+        visits[i] = 0;
+        int cur = tet[i];
+        if (cur < 0 || p[4 * i + 3] == 0.0) continue;
+        const double Q[3] = { p[4 * i] + disp[4 * i], p[4 * i + 1] + disp[4 * i + 1], p[4 * i + 2] + disp[4 * i + 2] };
+        const fm_rec *f = recs + cur;
+        const double *O = pos + 3 * (long)f->origin;
+        float rx = (float)(Q[0] - O[0]), ry = (float)(Q[1] - O[1]), rz = (float)(Q[2] - O[2]);
+        float RD3 = 3.f * fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz));
+        for (int it = 0; it < 48; ++it) {
+            visits[i]++;
+            float e[4];
+            for (int j = 0; j < 3; ++j) e[j] = rx * f->N[j][0] + ry * f->N[j][1] + rz * f->N[j][2];
+            const float V = f->V6, E = fabsf(f->E);
+            e[3] = V - e[0] - e[1] - e[2];
+            const float g = fmaf(G, V, ES * (E * E) * (E + RD3));
+            float m1 = e[0];
+            int js = 0;
+            for (int j = 1; j < 4; ++j) if (e[j] < m1) { m1 = e[j]; js = j; }
+            if (m1 >= g) { out[i] = cur; break; }
+            float m2 = INF;
+            for (int j = 0; j < 4; ++j) if (j != js) m2 = fminf(m2, e[j]);
+            if (!(m1 <= -g) || !(m2 - m1 >= 2.f * g)) break;
+            const int link = f->link[js];
+            if (link < 0 || it == 47) break;
+            cur = link >> 2;
+            const int oldOrigin = f->origin;
+            f = recs + cur;
+            if (f->origin != oldOrigin) {
+                O = pos + 3 * (long)f->origin;
+                rx = (float)(Q[0] - O[0]); ry = (float)(Q[1] - O[1]); rz = (float)(Q[2] - O[2]);
+                RD3 = 3.f * fmaxf(fmaxf(fabsf(rx), fabsf(ry)), fabsf(rz));
+            }
+        }
+    }
+}
+
 int orc_filter_rec_bytes(void) { return (int)sizeof(fm_rec); }

@@ -204,6 +204,16 @@ class FilterModel:
                               _i(out), _i(vis))
         return out, vis
 
+    def bary_walk(self, p4: np.ndarray, disp4: np.ndarray, tet: np.ndarray, *, guard=None, err_scale=1.0):
+        """RTX=true build: -> (tet certified to contain P + disp or -1 where the filter refused, visits)"""
+        n = p4.shape[0]
+        out = np.empty(n, dtype=np.int32)
+        vis = np.empty(n, dtype=np.int32)
+        lib().orc_filter_bary_walk(C.c_long(n), _d(np.ascontiguousarray(p4)), _d(np.ascontiguousarray(disp4)),
+                                   _i(np.ascontiguousarray(tet, dtype=np.int32)), self.recs.ctypes.data_as(C.c_void_p), _d(self.mesh.pos),
+                                   C.c_double(self.guard if guard is None else guard), C.c_double(err_scale), _i(out), _i(vis))
+        return out, vis
+
     def substep(self, cl: "Cloud", disp4: np.ndarray, *, skip_replay=False) -> np.ndarray:
         """One sub-step of every particle as the wall-capable fast pass does it; in place on cl.p / cl.vel / cl.tet where
         certified.  -> status (0 refused, 1 certified, 2 certified with one in-place wall reflection)"""

@@ -206,3 +206,100 @@ def test_in_place_wall_reflection_is_the_references_reflection(synth, orc):
                 cb = sb == 2
                 assert (bad.p[cb, :3] != ref.p[cb, :3]).any(axis=1).sum() > 5  # rare (last bits), but bit-exactness is the bar
     assert n_wall > 100000
+
+
+def test_start_points_certified_by_the_previous_substep_need_no_start_check(synth, orc):
+    """inside a launch the product checks a particle's start point ONCE (C1) and afterwards relies on
+    "the end point C2 certified is the next start point".  Chains of sub-steps through the model with the start check
+    dropped wherever the previous sub-step was certified -- half of the displacements aimed to END within 1e-9 .. 1e-2 tet
+    sizes of a face, an edge or a vertex of the tet they end in, so that the next sub-step starts as close to a feature as
+    C2 lets it -- must still only certify what the reference's walk decides."""
+    rng = np.random.default_rng(20261018)
+    n, K = 40000, 6
+    checked = skipped = 0
+    for name, pm, _ in _cases(synth):
+        mesh = orc.tet_mesh_from_poly(pm)
+        fm = orc.FilterModel(mesh)
+        span = pm.hi - pm.lo
+        h = span / 8.0
+        p = np.ones((n, 4))
+        p[:, :3] = pm.lo + (0.05 + 0.9 * rng.random((n, 3))) * span
+        tet = orc.locate_brute(mesh, p)
+        ok = tet >= 0
+        p, tet = p[ok], tet[ok]
+        certified = np.zeros(p.shape[0], dtype=np.uint8)
+        for k in range(K):
+            m = p.shape[0]
+            d = rng.normal(size=(m, 3)) * h * 10.0 ** rng.uniform(-1.5, -0.3, size=(m, 1))
+            # aimed half: end next to a feature of the CURRENT tet (vertex / edge midpoint / face centroid), pulled towards the
+            # tet's centroid by a tiny fraction: the end point sits just inside, the next start is as borderline as C2 allows
+            aim = np.flatnonzero(rng.random(m) < 0.5)
+            V = mesh.pos[mesh.idx[tet[aim]]]                       # [a, 4, 3]
+            kind = rng.integers(0, 3, size=aim.size)
+            wgt = np.zeros((aim.size, 4))
+            for q in range(aim.size):
+                sel = rng.permutation(4)[: kind[q] + 1]
+                wgt[q, sel] = 1.0 / (kind[q] + 1)
+            feat = (V * wgt[:, :, None]).sum(axis=1)
+            cen = V.mean(axis=1)
+            eps = 10.0 ** rng.uniform(-9.0, -2.0, size=(aim.size, 1))
+            d[aim] = feat + eps * (cen - feat) - p[aim, :3]
+            disp = np.zeros((m, 4))
+            disp[:, :3] = d
+            out, vis = fm.walk(p, disp, tet, skip_c1_first=certified)
+            cl = orc.Cloud.make(p, tet)
+            cl.disp[:] = disp
+            orc.locate_convex(mesh, cl)
+            cert = out >= 0
+            wrong = cert & (out != cl.tet)
+            assert not wrong.any(), (name, k, int(wrong.sum()), int(certified[wrong].sum()))
+            checked += int(cert.sum())
+            skipped += int((cert & (certified > 0)).sum())
+            # S5 for everything that stayed inside; what hit a wall starts again from a fresh interior point
+            inside = cl.tet >= 0
+            pn = p.copy()
+            pn[:, :3] = p[:, :3] + disp[:, :3]
+            fresh = ~inside
+            pn[fresh, :3] = pm.lo + (0.3 + 0.4 * rng.random((int(fresh.sum()), 3))) * span
+            tn = cl.tet.copy()
+            if fresh.any():
+                tn[fresh] = orc.locate_brute(mesh, pn[fresh])
+            keep = tn >= 0
+            p, tet = pn[keep], tn[keep]
+            certified = (cert & inside)[keep].astype(np.uint8)
+    assert checked > 400000 and skipped > 150000, (checked, skipped)
+
+
+def test_fp32_barycentric_walk_certifies_only_what_baryTetSearch_decides(synth, orc):
+    """RTX=true build (CPF_LOCATOR_BARY): the product's fp32 walk towards the end point (cpf_geom.cuh visit_bary32, modelled
+    by orc_filter_bary_walk) against the reference's baryTetSearch (query/RTQuery.cu:35-90, oracle s3_locate_bary), over the
+    same random and feature-grazing segments as the convex walk: a certified result must be the reference's tet; end points
+    exactly on vertices, edges and faces, equal minima and wall contacts must be refused."""
+    rng = np.random.default_rng(77)
+    total = certified = 0
+    for name, pm, min_rate in _cases(synth):
+        mesh = orc.tet_mesh_from_poly(pm)
+        fm = orc.FilterModel(mesh)
+        for rep in range(2):
+            p, disp, tet0 = _segments(rng, pm, mesh, orc, 60000)
+            ok = tet0 >= 0
+            p, disp, tet0 = p[ok], disp[ok], tet0[ok]
+            out, vis = fm.bary_walk(p, disp, tet0)
+            cl = orc.Cloud.make(p, tet0)
+            cl.disp[:] = disp
+            orc.locate_bary(mesh, cl)
+            cert = out >= 0
+            wrong = cert & (out != cl.tet)
+            assert not wrong.any(), (name, int(wrong.sum()), p[wrong][:3], disp[wrong][:3], out[wrong][:3], cl.tet[wrong][:3])
+            n = p.shape[0]
+            benign = np.zeros(n, dtype=bool)
+            benign[6 * (60000 // 8):] = True
+            benign = benign[:n] & (cl.tet >= 0)
+            assert cert[benign].mean() > min_rate, (name, cert[benign].mean())
+            total += n
+            certified += int(cert.sum())
+        # the band is what makes it sound here too
+        if name == "regular":
+            out0, _ = fm.bary_walk(p, disp, tet0, guard=0.0, err_scale=0.0)
+            assert int(((out0 >= 0) & (out0 != cl.tet)).sum()) > 20
+    assert total > 500000 and certified > 0.25 * total
