@@ -716,7 +716,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                     if (wall_reflect_on_path(m, tet, ws.path, visits - 1, ws.cur, ws.wall_js, ws.wall_link, P, disp, Phit, Eref, u)) {
                         disp = Eref;
                         const int wallTet = ws.cur;
-                        walkf_begin(ws, O, Phit, xsub(Eref, Phit), wallTet, ws.org, false); // leg 1: from the hit point (certified by C3), same tet
+                        walkf_begin(ws, O, Phit, xsub(Eref, Phit), wallTet, ws.org); // leg 1: from the hit point (certified by C3), same tet
                         hops += visits;
                         visits = 0;
                         leg = 1;
@@ -740,7 +740,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                     if (INTEG) { // k1 = v(P, tet); first stage point P + dt/2 * k1 (RK2 midpoint and RK4 alike)
                         k1s = u0;
                         Pst = axpy3(__dmul_rn(0.5, sp.dt), k1s, P);
-                        walkf_begin(ws, O, P, xsub(Pst, P), tet, org, false);
+                        walkf_begin(ws, O, P, xsub(Pst, P), tet, org);
                         stage = 1;
                     } else {
                         if (VERT) vel = u0;
@@ -751,7 +751,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                             disp.y = __fma_rn((double)s_xi[(s * 3 + 1) * 128 + threadIdx.x], sp.randDisp, disp.y);
                             disp.z = __fma_rn((double)s_xi[(s * 3 + 2) * 128 + threadIdx.x], sp.randDisp, disp.z);
                         }
-                        walkf_begin(ws, O, P, disp, tet, org, false);
+                        walkf_begin(ws, O, P, disp, tet, org);
                     }
                     visits = 0;
                     leg = 0;
@@ -760,7 +760,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
             }
             if (active && !wallWait) {
                 ++visits;
-                const int oc = visit_fast32<false, CPF_CFV_RUNTIME>(m, f, O, (WALL && leg) ? Phit : P, ws);
+                const int oc = visit_fast32<CPF_CFV_RUNTIME>(m, f, O, (WALL && leg) ? Phit : P, ws);
                 if (INTEG && stage > 0 && (oc == CPF_V_DONE || oc == CPF_V_WALL)) {
                     // the stage point lies in ws.cur (or beyond a certified wall face of it): take that cell's velocity
                     hops += visits;
@@ -792,10 +792,10 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                             disp.y = __fma_rn((double)s_xi[(s * 3 + 1) * 128 + threadIdx.x], sp.randDisp, disp.y);
                             disp.z = __fma_rn((double)s_xi[(s * 3 + 2) * 128 + threadIdx.x], sp.randDisp, disp.z);
                         }
-                        walkf_begin(ws, O, P, disp, tet, org, false);
+                        walkf_begin(ws, O, P, disp, tet, org);
                         stage = 0;
                     } else {
-                        walkf_begin(ws, O, P, xsub(Pst, P), tet, org, false);
+                        walkf_begin(ws, O, P, xsub(Pst, P), tet, org);
                         ++stage;
                     }
                 } else if (oc == CPF_V_DONE) {
@@ -850,17 +850,14 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 // the kernel the step time is made of and it is bound by instruction issue, not by memory:
 //   * thread i = particle i, no queue input, no wall handling, no stage walks: a lane is in one of three modes
 //     (0 = sub-step prologue due, 1 = walking, 2 = finished or deferred), one register;
-//   * C1 once per particle (start_point_clear, all lanes converged), never inside the loop (visit_fast32<false>);
+//   * C1 once per particle (start_point_clear, all lanes converged), never inside the loop (visit_fast32);
 //   * the cell velocity of the NEXT sub-step is fetched where the final tet of a sub-step becomes known, so the
 //     load is in flight while the other lanes of the warp run their exit-face section;
 //   * CFV (cell id = origin vertex id - nPoints, every OpenFOAM decomposition) is a template parameter.
 #ifndef CPF_LEAN_THREADS
 #define CPF_LEAN_THREADS 128
 #endif
-#ifndef CPF_LEAN_SMEM_STATE
-#define CPF_LEAN_SMEM_STATE 0 /* 1: displacement and activity flag of a lane live in shared memory instead of 8 registers */
-#endif
-#define CPF_LEAN_SMEM_BYTES(nSub, xiBytes, stateful) ((size_t)CPF_LEAN_THREADS * ((size_t)(xiBytes) * 3 * (size_t)(nSub) + (CPF_LEAN_SMEM_STATE ? 32 : 0) + ((stateful) ? sizeof(curandState_t) : 0)))
+#define CPF_LEAN_SMEM_BYTES(nSub, xiBytes, stateful) ((size_t)CPF_LEAN_THREADS * ((size_t)(xiBytes) * 3 * (size_t)(nSub) + ((stateful) ? sizeof(curandState_t) : 0)))
 //   * LOC = CPF_LOCATOR_BARY (RTX=true build): the same kernel around visit_bary32 -- the walk goes towards the end point
 //     Q = P + disp (kept where the convex walk keeps disp), no start-point check, walls always deferred.
 template <int RNG, bool CFV, int LOC = CPF_LOCATOR_CONVEX>
@@ -871,10 +868,9 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
     typedef typename Rng<RNG>::Xi Xi;
     constexpr bool STATEFUL = Rng<RNG>::STATEFUL;
     extern __shared__ double s_dyn[];
-    // [disp x | disp y | disp z | w] per thread (CPF_LEAN_SMEM_STATE), then the deviates [sub-step][component][thread],
-    // then (stateful generator) the state after the chunk, committed only if the particle finishes its chunk here
-    double *sd = s_dyn + threadIdx.x;
-    Xi *xi = reinterpret_cast<Xi *>(s_dyn + (CPF_LEAN_SMEM_STATE ? 4 * NT : 0)) + threadIdx.x;
+    // the deviates [sub-step][component][thread], then (stateful generator) the state after the chunk, committed only if
+    // the particle finishes its chunk here
+    Xi *xi = reinterpret_cast<Xi *>(s_dyn) + threadIdx.x;
     curandState_t *stash = reinterpret_cast<curandState_t *>(xi - threadIdx.x + 3 * NT * (STATEFUL ? sp.nSub : 0)) + threadIdx.x;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool have = i < pv.n;
@@ -909,7 +905,6 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
             else deferAt = 0;
         }
     }
-    if (CPF_LEAN_SMEM_STATE) sd[3 * NT] = w;
     WalkF ws;
     while (__any_sync(0xffffffffu, mode != 2)) {
         if (mode == 0) {
@@ -924,21 +919,18 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
             }
             if (BARY) {
                 disp = xadd(P, disp); // Q: the point the barycentric walk looks for, and the S5 result
-                walkf_begin(ws, O, disp, D3{ 0.0, 0.0, 0.0 }, tet, org, false);
-            } else walkf_begin(ws, O, P, disp, tet, org, false);
-            if (CPF_LEAN_SMEM_STATE) { sd[0] = disp.x; sd[NT] = disp.y; sd[2 * NT] = disp.z; }
+                walkf_begin(ws, O, disp, D3{ 0.0, 0.0, 0.0 }, tet, org);
+            } else walkf_begin(ws, O, P, disp, tet, org);
             visits = 0;
             mode = 1;
         }
         if (mode == 1) {
             ++visits;
-            const int oc = BARY ? visit_bary32<CF>(m, f, O, disp, ws, visits >= 48) : visit_fast32<false, CF>(m, f, O, P, ws, visits >= 48);
+            const int oc = BARY ? visit_bary32<CF>(m, f, O, disp, ws, visits >= 48) : visit_fast32<CF>(m, f, O, P, ws, visits >= 48);
             if (oc == CPF_V_DONE) {
                 tet = ws.cur;
                 org = ws.org;
-                if (BARY) P = CPF_LEAN_SMEM_STATE ? D3{ sd[0], sd[NT], sd[2 * NT] } : disp;
-                else if (CPF_LEAN_SMEM_STATE) P = xadd(P, D3{ sd[0], sd[NT], sd[2 * NT] });
-                else P = xadd(P, disp);
+                P = BARY ? disp : xadd(P, disp);
                 hops += (unsigned)visits;
                 mode = (++s >= sp.nSub) ? 2 : 0;
             } else if (oc != CPF_V_HOP) {
@@ -949,7 +941,6 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
         }
     }
     if (live) {
-        if (CPF_LEAN_SMEM_STATE) w = sd[3 * NT];
         if constexpr (STATEFUL) { if (deferAt < 0 && s >= sp.nSub) pv.rng[i] = *stash; }
         st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
         st_stream_i(pv.tet + i, tet);

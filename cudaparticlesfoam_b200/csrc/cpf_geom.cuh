@@ -294,18 +294,8 @@ CPF_DEV void f32_load(const MeshView &m, int tet, Fast32 &f)
     const uint4 *p = m.tetfast + 4ll * tet;
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
-#if CPF_REC_SPLIT
-    asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]) : "l"(p + 2));
-    asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "l"(p + 3));
-#else
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "l"(p + 2));
-#endif
-#if CPF_REC_SCALAR_E
-    // word 15 (E) again on its own: ptxas keeps E's loop-carried home outside the vector-load registers and would copy it
-    // there right behind the load (a wait for the record inside the hop); the scalar load lands in the home register
-    asm("ld.global.nc.u32 %0, [%1+60];" : "=r"(w[15]) : "l"(p));
-#endif
     f.link = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
 #pragma unroll
     for (int k = 0; k < 3; ++k)
@@ -315,17 +305,6 @@ CPF_DEV void f32_load(const MeshView &m, int tet, Fast32 &f)
     f.V6 = __uint_as_float(w[14]);
     f.E = __uint_as_float(w[15]);
 }
-
-#ifndef CPF_REC_SCALAR_E
-#define CPF_REC_SCALAR_E 0
-#endif
-#ifndef CPF_REC_SPLIT
-#define CPF_REC_SPLIT 0
-#endif
-#ifndef CPF_HOP_PREFETCH
-#define CPF_HOP_PREFETCH 0 /* measured: prefetch at the hop + load at the next visit is 2 % slower than loading at the hop */
-#endif
-CPF_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 CPF_DEV float rcp_ftz(float x)
 {
@@ -355,7 +334,6 @@ struct WalkF {
     float rx, ry, rz, dx, dy, dz, RD3, Dd, t_in;
     int cur;
     int org;                // origin vertex id of the tet `cur` (the record only names it for generic tet meshes)
-    bool c1;                // C1 still to be checked (first visit of a walk whose start point nothing has certified yet)
     int wall_js, wall_link; // set with CPF_V_WALL
     unsigned path;          // stored exit slot of every hop of this leg, 2 bits each (wall handling)
 };
@@ -381,13 +359,12 @@ CPF_DEV void walkf_rebase(WalkF &ws, const D3 &O, const D3 &P0)
     ws.RD3 = 3.f * (fmaxf(fmaxf(fabsf(ws.rx), fabsf(ws.ry)), fabsf(ws.rz)) + ws.Dd);
 }
 
-CPF_DEV void walkf_begin(WalkF &ws, const D3 &O, const D3 &P0, const D3 &disp, int tet, int org, bool c1)
+CPF_DEV void walkf_begin(WalkF &ws, const D3 &O, const D3 &P0, const D3 &disp, int tet, int org)
 {
     ws.dx = (float)disp.x; ws.dy = (float)disp.y; ws.dz = (float)disp.z;
     ws.Dd = fmaxf(fmaxf(fabsf(ws.dx), fabsf(ws.dy)), fabsf(ws.dz));
     walkf_rebase(ws, O, P0);
     ws.t_in = 0.f;
-    ws.c1 = c1;
     ws.cur = tet;
     ws.org = org;
     ws.path = 0u;
@@ -409,7 +386,8 @@ CPF_DEV bool start_point_clear(const MeshView &m, const Fast32 &f, float rx, flo
 }
 
 // One tet visit.  Checks, all against g = G*V6 + ERR (header comment above):
-//   C1  start point of the walk clear of every face plane -- FIRST visit only and only while ws.c1 is set (DYN_C1).
+//   C1  start point of the walk clear of every face plane -- NOT here: the kernels check it once per particle and launch,
+//       with all lanes converged, before their visit loop (start_point_clear).
 //       Entry points of later visits need no test of their own: they are the exit points C3 certified in the tet
 //       before, and on the shared face the barycentric coordinates w.r.t. its three vertices are the same in both
 //       tets.  Start points of later sub-steps are the end points C2 certified (P + disp in fp64 moves them by
@@ -421,27 +399,11 @@ CPF_DEV bool start_point_clear(const MeshView &m, const Fast32 &f, float rx, flo
 // lastVisit: the caller's visit cap is reached -- a hop out of this tet is refused BEFORE the next record is requested
 // (keeps every use of the caller's state ahead of the loads: nothing in the hop path then touches a register the
 // loads write, which ptxas otherwise resolves with a copy right behind them, i.e. a wait for the record inside the hop)
-template <bool DYN_C1, int CFV>
+template <int CFV>
 CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, WalkF &ws, bool lastVisit = false)
 {
     const float INF = __int_as_float(0x7f800000);
-#if CPF_HOP_PREFETCH
-    // Entered through a face in the visit before (t_in > 0): that visit only PREFETCHED this tet's record and, in another
-    // cell, the origin's position -- prefetches name no register, so the warp carries no scoreboard dependency through the
-    // loop tail and the other lanes' sub-step prologue, and the loads below hit L1.
-    if (ws.t_in > 0.f) {
-        f32_load(m, ws.cur, f);
-        if (mesh_is_cfv<CFV>(m)) {
-            if (ws.RD3 < 0.f) { O = ld_vertex(m.vpos, ws.org); walkf_rebase(ws, O, P0); }
-        } else if (f.aux != ws.org) { // generic tet mesh: the record names its own origin
-            ws.org = f.aux;
-            O = ld_vertex(m.vpos, f.aux);
-            walkf_rebase(ws, O, P0);
-        }
-    }
-#else
     if (ws.RD3 < 0.f) walkf_rebase(ws, O, P0); // entered another cell in the hop before: its origin has arrived by now
-#endif
     const float (&N)[3][3] = f.N;
     const float V = f.V6;
     float a[4], b[4], e[4];
@@ -458,10 +420,6 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
     const float g = fmaf(m.guardf, V, 3.814697265625e-6f * (E * E) * (E + ws.RD3));
 #pragma unroll
     for (int j = 0; j < 4; ++j) e[j] = a[j] + b[j];
-    if (DYN_C1 && ws.c1) {
-        ws.c1 = false;
-        if (!(fminf(fminf(a[0], a[1]), fminf(a[2], a[3])) >= g)) return CPF_V_REFUSE;
-    }
     if (fminf(fminf(e[0], e[1]), fminf(e[2], e[3])) >= g) return CPF_V_DONE; // C2 and "inside" in one
     if (!(fminf(fminf(fabsf(e[0]), fabsf(e[1])), fminf(fabsf(e[2]), fabsf(e[3]))) >= g)) return CPF_V_REFUSE;
     // Exit face: smallest crossing parameter among the faces whose plane the end point is behind.  For those the
@@ -489,15 +447,6 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
     ws.cur = link >> 2;
     ws.t_in = t;
     ws.path = (ws.path << 2) | (unsigned)js;
-#if CPF_HOP_PREFETCH
-    prefetch_l1(m.tetfast + 4ll * ws.cur);
-    prefetch_l1(m.tetfast + 4ll * ws.cur + 2);
-    if (mesh_is_cfv<CFV>(m) && js == 3) { // through the face opposite the cell centre: another cell, whose origin id this record names
-        ws.org = f.aux;
-        prefetch_l1(m.vpos + f.aux);
-        ws.RD3 = -1.f;
-    }
-#else
     if (mesh_is_cfv<CFV>(m)) {
         if (js == 3) { // through the face opposite the cell centre: another cell, whose origin id this record already names
             ws.org = f.aux;
@@ -513,7 +462,6 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
             walkf_rebase(ws, O, P0);
         }
     }
-#endif
     return CPF_V_HOP;
 }
 
