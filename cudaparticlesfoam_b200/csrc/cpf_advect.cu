@@ -157,6 +157,19 @@ template <> struct Rng<CPF_RNG_PHILOX> {
         return true;
     }
     CPF_DEV void close(const ParticleView &, long long) {}
+    // whole blocks b0, b0+1, ... (b0 = the block holding the chunk's first deviate) into rows 4k..4k+3: no per-slot bounds
+    // (k_lean; the reader starts (3 step0) & 3 rows in)
+    CPF_DEV void stage_blocks(Xi *xi, int stride, unsigned nBlocks, bool live)
+    {
+        if (!live) return;
+        const unsigned long long b0 = (3ull * step0) >> 2;
+        for (unsigned k = 0; k < nBlocks; ++k) {
+            double z[4];
+            block(b0 + k, z);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xi[(4 * k + j) * stride] = (Xi)z[j];
+        }
+    }
     // deviates of the sub-steps [sFrom, nSub) of a chunk into xi[(3 q + c) * stride]: block by block, every output used
     CPF_DEV void stage(Xi *xi, int stride, int nSub, int sFrom, bool live)
     {
@@ -857,9 +870,45 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 #ifndef CPF_LEAN_THREADS
 #define CPF_LEAN_THREADS 128
 #endif
-#define CPF_LEAN_SMEM_BYTES(nSub, xiBytes, stateful) ((size_t)CPF_LEAN_THREADS * ((size_t)(xiBytes) * 3 * (size_t)(nSub) + ((stateful) ? sizeof(curandState_t) : 0)))
+// dynamic shared memory of k_lean per CTA: the staged deviates [row][thread] (rows: 3 per sub-step; the stateless stream
+// stages whole Philox blocks, i.e. up to 3 rows in front of and behind the chunk; no random walk: one row for the
+// start-tet slots) and the XORWOW state after the chunk
+#define CPF_LEAN_SMEM_BYTES(rows, xiBytes, stateful) ((size_t)CPF_LEAN_THREADS * ((size_t)(xiBytes) * (size_t)((rows) ? (rows) : 1) + ((stateful) ? sizeof(curandState_t) : 0)))
+// rows staged for nSub sub-steps starting at global sub-step step0 (host and device agree through this one function)
+__host__ __device__ inline unsigned lean_rows(int rng, int nSub, unsigned long long step0)
+{
+    if (rng == CPF_RNG_NONE) return 0u;
+    if (rng != CPF_RNG_PHILOX) return 3u * (unsigned)nSub;
+    const unsigned off = (unsigned)((3ull * step0) & 3ull);
+    return 4u * ((off + 3u * (unsigned)nSub + 3u) >> 2);
+}
+
+// shared-window accessors: the loop keeps ONE running 32-bit address per lane instead of re-deriving
+// base + (3 s + c) * NT + tid at every sub-step
+template <typename Xi, int OFF> CPF_DEV double lds_xi(unsigned a)
+{
+    if constexpr (sizeof(Xi) == 4) {
+        float r;
+        asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(r) : "r"(a), "n"(OFF));
+        return (double)r;
+    } else {
+        double r;
+        asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(r) : "r"(a), "n"(OFF));
+        return r;
+    }
+}
+CPF_DEV void sts_i32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+CPF_DEV int lds_i32(unsigned a) { int r; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+
 //   * LOC = CPF_LOCATOR_BARY (RTX=true build): the same kernel around visit_bary32 -- the walk goes towards the end point
 //     Q = P + disp (kept where the convex walk keeps disp), no start-point check, walls always deferred.
+// Loop shape: every iteration is ONE tet visit of every lane that still has work; a lane whose visit ends its sub-step
+// runs S5 and the S1/S2 prologue of its next sub-step right there (the first prologue runs before the loop with all lanes
+// converged), so the loop head carries no mode dispatch.  Per-lane loop state besides the walk: the running deviate
+// address xs, `left` (> 0: sub-steps still to do, the lane is walking; 0: chunk finished; < 0: stopped with -left
+// sub-steps to do -- refused, frozen or not started), the visit cap as a value of the visit counter, and the cell of the
+// last prologue.  The start tet of the current sub-step -- needed only if the sub-step is refused -- waits in shared
+// memory, in the slot of the sub-step's first deviate (already consumed by then).
 template <int RNG, bool CFV, int LOC = CPF_LOCATOR_CONVEX>
 __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / CPF_LEAN_THREADS) k_lean(const MeshView m, const ParticleView pv, const StepParams sp)
 {
@@ -867,11 +916,12 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
     constexpr int NT = CPF_LEAN_THREADS;
     typedef typename Rng<RNG>::Xi Xi;
     constexpr bool STATEFUL = Rng<RNG>::STATEFUL;
+    constexpr int ROW = NT * (int)sizeof(Xi);                      // bytes between two staged rows of a lane
+    constexpr unsigned STEP = RNG == CPF_RNG_NONE ? 0u : 3u * ROW; // no deviates: xs stays on the lane's start-tet slot
     extern __shared__ double s_dyn[];
-    // the deviates [sub-step][component][thread], then (stateful generator) the state after the chunk, committed only if
-    // the particle finishes its chunk here
+    const unsigned rows = lean_rows(RNG, sp.nSub, sp.step0);
     Xi *xi = reinterpret_cast<Xi *>(s_dyn) + threadIdx.x;
-    curandState_t *stash = reinterpret_cast<curandState_t *>(xi - threadIdx.x + 3 * NT * (STATEFUL ? sp.nSub : 0)) + threadIdx.x;
+    curandState_t *stash = reinterpret_cast<curandState_t *>(xi - threadIdx.x + (size_t)NT * rows) + threadIdx.x;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool have = i < pv.n;
     double4 p4 = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -880,81 +930,89 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
     D3 P{ p4.x, p4.y, p4.z };
     double w = p4.w;
     const bool live = have && (w != 0.0);
+    unsigned xs = (unsigned)__cvta_generic_to_shared(xi);
     if (RNG != CPF_RNG_NONE) {
         Rng<RNG> rng;
         if (live) rng.open(pv, i, sp);
-        rng.stage(xi, NT, sp.nSub, 0, live);
+        if constexpr (RNG == CPF_RNG_PHILOX) {
+            xs += (unsigned)((3ull * sp.step0) & 3ull) * (unsigned)ROW; // the chunk's first deviate inside its first block
+            rng.stage_blocks(xi, NT, rows >> 2, live);
+        } else rng.stage(xi, NT, sp.nSub, 0, live);
         if constexpr (STATEFUL) { if (live) *stash = rng.st; }
     }
     Fast32 f;
-    D3 O{ 0.0, 0.0, 0.0 }, disp{ 0.0, 0.0, 0.0 }, u0{ 0.0, 0.0, 0.0 };
-    int deferAt = -1, s = 0, mode = 2, cell = -1, visits = 0, org = -1;
-    unsigned hops = 0, frz = 0;
+    D3 O{ 0.0, 0.0, 0.0 }, disp{ 0.0, 0.0, 0.0 };
+    int cell = -1, left = -sp.nSub;
+    unsigned hops = 0, cap = 0, frz = 0;
     constexpr int CF = CFV ? CPF_CFV_YES : CPF_CFV_NO;
-    auto fetch_velocity = [&]() {
-        cell = CFV ? org - m.nPoints : __ldg(m.tetcell + tet);
-        u0 = ld_ucell(m, cell);
+    WalkF ws;
+    ws.cur = tet;
+    ws.org = -1;
+    // S1 + S2 of the sub-step whose deviates sit at xs, then the walk set up from (P, ws.cur, ws.org, O)
+    auto begin_substep = [&]() {
+        cell = CFV ? ws.org - m.nPoints : __ldg(m.tetcell + ws.cur);
+        const D3 u0 = ld_ucell(m, cell);
+        disp = D3{ __dsub_rn(__fma_rn(sp.dt, u0.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, u0.y, P.y), P.y),
+                   __dsub_rn(__fma_rn(sp.dt, u0.z, P.z), P.z) };
+        if (RNG != CPF_RNG_NONE) {
+            disp.x = __fma_rn(lds_xi<Xi, 0>(xs), sp.randDisp, disp.x);
+            disp.y = __fma_rn(lds_xi<Xi, ROW>(xs), sp.randDisp, disp.y);
+            disp.z = __fma_rn(lds_xi<Xi, 2 * ROW>(xs), sp.randDisp, disp.z);
+        }
+        sts_i32(xs, ws.cur); // behind the read of the same slot
+        if (BARY) {
+            disp = xadd(P, disp); // Q: the point the barycentric walk looks for, and the S5 result
+            ws.dx = ws.dy = ws.dz = 0.f;
+            ws.Dd = 0.f;
+            walkf_rebase(ws, O, disp);
+        } else {
+            ws.dx = (float)disp.x; ws.dy = (float)disp.y; ws.dz = (float)disp.z;
+            ws.Dd = fmaxf(fmaxf(fabsf(ws.dx), fabsf(ws.dy)), fabsf(ws.dz));
+            walkf_rebase(ws, O, P);
+        }
+        ws.t_in = 0.f;
+        cap = hops + 47u; // the 48th visit of a sub-step must end it
     };
     if (live) {
         if (tet < 0) { w = 0.0; frz = 1u; } // S1: left the domain -> frozen (particles.cu:334-338)
         else {
             f32_load(m, tet, f);
-            org = first_origin<CF>(m, tet, f);
-            O = ld_vertex(m.vpos, org);
-            if (BARY || start_point_clear(m, f, (float)(P.x - O.x), (float)(P.y - O.y), (float)(P.z - O.z))) mode = 0;
-            else deferAt = 0;
+            ws.org = first_origin<CF>(m, tet, f);
+            O = ld_vertex(m.vpos, ws.org);
+            if (BARY || start_point_clear(m, f, (float)(P.x - O.x), (float)(P.y - O.y), (float)(P.z - O.z))) left = sp.nSub;
+            else sts_i32(xs, tet); // refused before its first sub-step
         }
     }
-    WalkF ws;
-    while (__any_sync(0xffffffffu, mode != 2)) {
-        if (mode == 0) {
-            fetch_velocity();
-            disp = D3{ __dsub_rn(__fma_rn(sp.dt, u0.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, u0.y, P.y), P.y),
-                       __dsub_rn(__fma_rn(sp.dt, u0.z, P.z), P.z) };
-            if (RNG != CPF_RNG_NONE) {
-                const Xi *x = xi + s * (3 * NT);
-                disp.x = __fma_rn((double)x[0], sp.randDisp, disp.x);
-                disp.y = __fma_rn((double)x[NT], sp.randDisp, disp.y);
-                disp.z = __fma_rn((double)x[2 * NT], sp.randDisp, disp.z);
-            }
-            if (BARY) {
-                disp = xadd(P, disp); // Q: the point the barycentric walk looks for, and the S5 result
-                walkf_begin(ws, O, disp, D3{ 0.0, 0.0, 0.0 }, tet, org);
-            } else walkf_begin(ws, O, P, disp, tet, org);
-            visits = 0;
-            mode = 1;
-        }
-        if (mode == 1) {
-            ++visits;
-            const int oc = BARY ? visit_bary32<CF>(m, f, O, disp, ws, visits >= 48) : visit_fast32<CF>(m, f, O, P, ws, visits >= 48);
-            if (oc == CPF_V_DONE) {
-                tet = ws.cur;
-                org = ws.org;
+    if (left > 0) begin_substep();
+    while (__any_sync(0xffffffffu, left > 0)) {
+        if (left > 0) {
+            const int oc = BARY ? visit_bary32<CF>(m, f, O, disp, ws, hops >= cap) : visit_fast32<CF>(m, f, O, P, ws, hops >= cap);
+            if (oc == CPF_V_HOP) ++hops;
+            else if (oc == CPF_V_DONE) {
                 P = BARY ? disp : xadd(P, disp);
-                hops += (unsigned)visits;
-                mode = (++s >= sp.nSub) ? 2 : 0;
-            } else if (oc != CPF_V_HOP) {
-                hops += (unsigned)visits;
-                deferAt = s;
-                mode = 2;
-            }
+                xs += STEP;
+                if (--left > 0) begin_substep();
+            } else left = -left;
         }
     }
+    const bool deferred = left < 0 && live && frz == 0u;
+    const int s = sp.nSub - abs(left); // sub-steps completed here
+    if (live && frz == 0u) hops += (unsigned)s + (left < 0 ? 1u : 0u); // tet visits = hops + one final visit per sub-step (+ the refused one)
     if (live) {
-        if constexpr (STATEFUL) { if (deferAt < 0 && s >= sp.nSub) pv.rng[i] = *stash; }
+        if constexpr (STATEFUL) { if (left == 0) pv.rng[i] = *stash; }
         st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
-        st_stream_i(pv.tet + i, tet);
-        if (sp.writeVel && cell >= 0 && deferAt < 0) {
+        st_stream_i(pv.tet + i, deferred ? lds_i32(xs) : ws.cur);
+        if (sp.writeVel && cell >= 0 && !deferred) {
             st_stream4(pv.vel + i, vel4(ld_ucell(m, cell)));
         }
     }
-    const unsigned mask = __ballot_sync(0xffffffffu, deferAt >= 0); // deferral queue: one atomic per warp
+    const unsigned mask = __ballot_sync(0xffffffffu, deferred); // deferral queue: one atomic per warp
     if (mask) {
         const int lane = threadIdx.x & 31;
         int qb = 0;
         if (lane == 0) qb = (int)atomicAdd(sp.countOut, (unsigned)__popc(mask));
         qb = __shfl_sync(0xffffffffu, qb, 0);
-        if (deferAt >= 0) sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, deferAt);
+        if (deferred) sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, s);
     }
     flush_counters(sp, 0u, 0u, hops, (unsigned)s, 0u, frz);
 }
@@ -1079,7 +1137,7 @@ static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleVi
     a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
     if constexpr (I == CPF_EULER && !V) {
         const dim3 lgrid((unsigned)((pv.n + CPF_LEAN_THREADS - 1) / CPF_LEAN_THREADS));
-        const size_t lb = CPF_LEAN_SMEM_BYTES(nSub, R == CPF_RNG_NONE ? 0 : sizeof(Xi), STATEFUL);
+        const size_t lb = CPF_LEAN_SMEM_BYTES(lean_rows(R, nSub, sp.step0), sizeof(Xi), STATEFUL);
         if (m.tetcell == nullptr) k_lean<R, true><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
         else k_lean<R, false><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
     } else {
@@ -1113,7 +1171,7 @@ static int launch_filtered_bary(cpf_context *ctx, const MeshView &m, const Parti
     StepParams a = sp;
     a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
     const dim3 lgrid((unsigned)((pv.n + CPF_LEAN_THREADS - 1) / CPF_LEAN_THREADS));
-    const size_t lb = CPF_LEAN_SMEM_BYTES(nSub, R == CPF_RNG_NONE ? 0 : sizeof(Xi), STATEFUL);
+    const size_t lb = CPF_LEAN_SMEM_BYTES(lean_rows(R, nSub, sp.step0), sizeof(Xi), STATEFUL);
     if (m.tetcell == nullptr) k_lean<R, true, CPF_LOCATOR_BARY><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
     else k_lean<R, false, CPF_LOCATOR_BARY><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
     StepParams z = sp;
