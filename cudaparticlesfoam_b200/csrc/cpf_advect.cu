@@ -17,9 +17,6 @@
 #ifndef CPF_MIN_BLOCKS
 #define CPF_MIN_BLOCKS 4
 #endif
-#ifndef CPF_MAX_ROUNDS
-#define CPF_MAX_ROUNDS 0 /* further [one exact sub-step -> resume fast] rounds before the exact finisher (measured: 0 is fastest) */
-#endif
 #ifndef CPF_FAST_MIN_BLOCKS
 #define CPF_FAST_MIN_BLOCKS 7
 #endif
@@ -29,11 +26,11 @@
 #ifndef CPF_WALL_MIN_BLOCKS
 #define CPF_WALL_MIN_BLOCKS 4 /* k_fast with in-place wall reflection (queue passes) */
 #endif
+#ifndef CPF_FIN_MIN_BLOCKS
+#define CPF_FIN_MIN_BLOCKS 3 /* the finishing pass (wall reflection + exact sub-steps in place) */
+#endif
 #ifndef CPF_WALL_BATCH
 #define CPF_WALL_BATCH 32 /* lanes of a warp that must be waiting at a wall before they reflect together (32: all that are left; measured 4 < 8 < 16 < 32) */
-#endif
-#ifndef CPF_WALL_PASS
-#define CPF_WALL_PASS 1 /* wall-capable fast pass over the refusals of the all-particles pass, before any exact work */
 #endif
 #define CPF_TAIL __device__ __forceinline__
 
@@ -194,6 +191,9 @@ template <> struct Rng<CPF_RNG_PHILOX> {
 // exact sub-step tails (S3+S4+S5)
 // ------------------------------------------------------------------------------------------------
 struct Tally { unsigned hops, exact, refl, esc, frz; };
+// deferral queue entry {particle, sub-step | flags}: CPF_Q_WALL = the all-particles pass stopped at a CERTIFIED wall contact
+// (the wall-capable pass can reflect it in place); without it the fp32 filter itself refused, and will again
+enum { CPF_Q_SUBSTEP = 0xffff, CPF_Q_WALL = 0x10000 };
 CPF_DEV double4 vel4(D3 u) { return make_double4(u.x, u.y, u.z, -1.0); }
 
 // Default build: convex line walk + reflector.  The reference's reflector re-walks the segment
@@ -265,6 +265,13 @@ CPF_TAIL void tail_convex_exact(const MeshView &m, D3 &P, D3 disp, D3 &vel, int 
     const D3 nd = xsub(E, Phit);
     tet = next;
     P = xadd(Phit, nd); // p = P_hit (S4) then p += disp (S5)
+}
+
+// the same as an out-of-line call: the finishing pass (k_fast<..., FIN = 1>) runs a refused sub-step through it without
+// carrying the reflector's registers through its fp32 visit loop
+__device__ __noinline__ void exact_substep_convex(const MeshView &m, D3 &P, D3 disp, D3 &vel, int &tet, double &w, int reflect, Tally &ty)
+{
+    tail_convex_exact(m, P, disp, vel, tet, w, reflect, ty);
 }
 
 // RTX=true build: barycentric point walk + RTreflection
@@ -344,6 +351,17 @@ CPF_DEV D3 displacement(const MeshView &m, const StepParams &sp, Rng<RNG> &rng, 
     return disp;
 }
 
+// First slot of a thread in a grid-stride loop (stride = gridDim.x * blockDim.x).  Queue passes spread the entries over
+// ALL warps of the grid -- lane k of warp g takes entry g + k * (number of warps) -- instead of packing 32 neighbours
+// into one warp: the passes are short, divergent and latency-bound, a queue of a few 1e4 entries fills a fraction of the
+// resident warps when packed, and every lane less in a warp is one serialised rare-event section less.
+CPF_DEV long long first_slot(bool queue)
+{
+    if (!queue) return (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned wpb = blockDim.x >> 5;
+    return (long long)(blockIdx.x * wpb + (threadIdx.x >> 5)) + (long long)(threadIdx.x & 31u) * ((long long)gridDim.x * wpb);
+}
+
 // frz: particles this kernel froze (S1: negative tet id -> w := 0); with the escapes it lets the host derive the number of
 // active particles from the counters alone (cpf_stats_request light mode)
 CPF_DEV void flush_counters(const StepParams &sp, unsigned refl, unsigned exact, unsigned hops, unsigned nsteps, unsigned esc = 0u, unsigned frz = 0u)
@@ -367,10 +385,10 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact(const MeshView m,
     Tally ty{ 0u, 0u, 0u, 0u, 0u };
     unsigned nsteps = 0;
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
-    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
+    for (long long slot = first_slot(QMODE != 0); slot < total; slot += (long long)gridDim.x * blockDim.x) {
         long long i = slot;
         int s0 = 0;
-        if (QMODE) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y; }
+        if (QMODE) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y & CPF_Q_SUBSTEP; }
         const int s1 = (QMODE == 1) ? min(s0 + 1, sp.nSub) : sp.nSub;
         if (s0 >= s1) continue;
         double4 p4 = ld_stream4(pv.pos + i);
@@ -418,12 +436,12 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact_convex(const Mesh
     unsigned nsteps = 0;
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride) { // warp-uniform trip count
-        const long long slot = base + threadIdx.x;
+    for (long long base = 0; base < total; base += stride) { // grid-uniform trip count
+        const long long slot = base + first_slot(QMODE != 0);
         long long i = slot;
         int s = 0;
         bool have = slot < total;
-        if (QMODE && have) { const int2 q = sp.queueIn[slot]; i = q.x; s = q.y; have = s < sp.nSub; }
+        if (QMODE && have) { const int2 q = sp.queueIn[slot]; i = q.x; s = q.y & CPF_Q_SUBSTEP; have = s < sp.nSub; }
         const int sStop = (QMODE == 1) ? min(s + 1, sp.nSub) : sp.nSub;
         double4 p4 = make_double4(0.0, 0.0, 0.0, 0.0);
         int tet = -1;
@@ -579,10 +597,10 @@ __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const Part
     Tally ty{ 0u, 0u, 0u, 0u, 0u };
     unsigned nsteps = 0;
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
-    for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
+    for (long long slot = first_slot(QMODE != 0); slot < total; slot += (long long)gridDim.x * blockDim.x) {
         long long i = slot;
         int s0 = 0;
-        if (QMODE) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y; }
+        if (QMODE) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y & CPF_Q_SUBSTEP; }
         if (s0 >= sp.nSub) continue;
         double4 p4 = ld_stream4(pv.pos + i);
         int tet = ld_stream_i(pv.tet + i);
@@ -659,10 +677,16 @@ __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const Part
 // refused stage walk defers the whole sub-step to k_general.
 // VERT = 1 (extension): velocities from the vertex (cellPoint-style) interpolation, evaluated in the reference's
 // arithmetic (vertex_velocity_exact) at the particle and at the stage points; only the walks are filtered.
-template <int RNG, int QMODE, int WALL, int INTEG, int VERT>
-__global__ void __launch_bounds__(128, (WALL || VERT) ? CPF_WALL_MIN_BLOCKS : (INTEG == CPF_RK4 ? CPF_RK_MIN_BLOCKS - 1 : INTEG ? CPF_RK_MIN_BLOCKS : CPF_FAST_MIN_BLOCKS))
+// FIN = 1 (Euler, cell value; the LAST kernel of the launch sequence): nothing is deferred.  A sub-step the filter
+// refuses is run right here, from its start (P, tet -- both untouched while a walk is under way), in the reference's
+// arithmetic (exact_substep_convex), and the lane goes back to the fp32 walk for its next sub-step after a C1 check of
+// the new start point (which no C2 has certified).  One kernel, and one exact sub-step per refusal, instead of a
+// wall-capable pass followed by a finisher that ran ALL remaining sub-steps of its particles in fp64.
+template <int RNG, int QMODE, int WALL, int INTEG, int VERT, int FIN = 0>
+__global__ void __launch_bounds__(128, FIN ? CPF_FIN_MIN_BLOCKS : (WALL || VERT) ? CPF_WALL_MIN_BLOCKS : (INTEG == CPF_RK4 ? CPF_RK_MIN_BLOCKS - 1 : INTEG ? CPF_RK_MIN_BLOCKS : CPF_FAST_MIN_BLOCKS))
 k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 {
+    static_assert(!FIN || (!INTEG && !VERT), "the in-place exact sub-step is the Euler / cell-value one");
     constexpr bool KEEPV = INTEG || VERT; // the reported velocity is not simply U[cell]: carry it
     typedef typename Rng<RNG>::Xi Xi;
     constexpr bool STATEFUL = Rng<RNG>::STATEFUL;
@@ -672,15 +696,19 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
     // chunk in this kernel -- a deferred particle keeps its chunk-start state in memory, the next kernel re-draws from it
     curandState_t *stash = reinterpret_cast<curandState_t *>(s_xi + 3 * 128 * (STATEFUL ? sp.nSub : 0)) + threadIdx.x;
     unsigned hops = 0, nsteps = 0, refl = 0, frz = 0;
+    Tally ty{ 0u, 0u, 0u, 0u, 0u }; // FIN: what the exact sub-steps count
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride) { // warp-uniform trip count
-        const long long slot = base + threadIdx.x;
+    for (long long base = 0; base < total; base += stride) { // grid-uniform trip count
+        const long long slot = base + first_slot(QMODE != 0);
         int deferAt = -1;
+        bool needExact = false, exactVel = false, frzHit = false; // FIN: sub-step s is to be redone exactly / the velocity to report is velX
+        D3 velX{ 0.0, 0.0, 0.0 };
         long long i = slot;
         int s = 0, sBegin = 0;
         bool have = slot < total;
-        if (QMODE && have) { const int2 q = sp.queueIn[slot]; i = q.x; s = q.y; have = s < sp.nSub; }
+        bool wallHint = true;
+        if (QMODE && have) { const int2 q = sp.queueIn[slot]; i = q.x; s = q.y & CPF_Q_SUBSTEP; wallHint = (q.y & CPF_Q_WALL) != 0; have = s < sp.nSub; }
         sBegin = s;
         double4 p4 = make_double4(0.0, 0.0, 0.0, 0.0);
         int tet = -1;
@@ -713,10 +741,41 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
             O = ld_vertex(m.vpos, org);
             // C1, once per particle and launch, all lanes converged: the start point nothing in this kernel has certified
             // (later sub-steps start where C2 certified the end point, later visits where C3 certified the exit point)
-            if (!start_point_clear(m, f, (float)(P.x - O.x), (float)(P.y - O.y), (float)(P.z - O.z))) { deferAt = s; active = false; }
+            // FIN: an entry the filter itself refused goes straight to its exact sub-step (same arithmetic, same refusal) --
+            // and all such lanes of the warp do so in the same iteration
+            if ((FIN && !wallHint) || !start_point_clear(m, f, (float)(P.x - O.x), (float)(P.y - O.y), (float)(P.z - O.z))) {
+                if (FIN) needExact = true;
+                else { deferAt = s; active = false; }
+            }
         }
         bool wallWait = false; // WALL: certified wall contact, waiting for the warp's next batched reflection
         while (__any_sync(0xffffffffu, active)) {
+            if (FIN && active && needExact) {
+                needExact = false;
+                cell = m.tetcell ? __ldg(m.tetcell + tet) : org - m.nPoints;
+                velX = ld_ucell(m, cell);
+                D3 dX{ __dsub_rn(__fma_rn(sp.dt, velX.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, velX.y, P.y), P.y),
+                       __dsub_rn(__fma_rn(sp.dt, velX.z, P.z), P.z) };
+                if (RNG != CPF_RNG_NONE) {
+                    dX.x = __fma_rn((double)s_xi[(s * 3 + 0) * 128 + threadIdx.x], sp.randDisp, dX.x);
+                    dX.y = __fma_rn((double)s_xi[(s * 3 + 1) * 128 + threadIdx.x], sp.randDisp, dX.y);
+                    dX.z = __fma_rn((double)s_xi[(s * 3 + 2) * 128 + threadIdx.x], sp.randDisp, dX.z);
+                }
+                exact_substep_convex(m, P, dX, velX, tet, w, sp.reflect, ty);
+                ty.exact++;
+                exactVel = true;
+                velValid = true;
+                needPro = true;
+                wallWait = false;
+                leg = 0;
+                if (++s >= sp.nSub || w == 0.0) active = false;
+                else if (tet >= 0) { // back to the fp32 walk: C1 for a start point no C2 has certified
+                    f32_load(m, tet, f);
+                    org = first_origin<CPF_CFV_RUNTIME>(m, tet, f);
+                    O = ld_vertex(m.vpos, org);
+                    if (!start_point_clear(m, f, (float)(P.x - O.x), (float)(P.y - O.y), (float)(P.z - O.z))) needExact = true;
+                } // tet < 0: frozen by the S1 of the next prologue
+            }
             if (WALL) {
                 // The reflection is long and rare per lane: lanes that reach a wall wait until CPF_WALL_BATCH of them
                 // have gathered (or nobody else can move), then reflect together instead of one or two at a time.
@@ -738,13 +797,13 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                         else if (sp.writeVel && s == sp.nSub - 1) { st_stream4(pv.vel + i, make_double4(u.x, u.y, u.z, -1.0)); velDone = true; }
                     } else {
                         hops += visits;
-                        deferAt = s;
-                        active = false;
+                        if (FIN) needExact = true;
+                        else { deferAt = s; active = false; }
                     }
                 }
             }
-            if (active && !wallWait && needPro) {
-                if (tet < 0) active = false; // S1: left the domain -> frozen (particles.cu:334-338), w := 0 below
+            if (active && !wallWait && needPro && !(FIN && needExact)) {
+                if (tet < 0) { active = false; frzHit = true; } // S1: left the domain -> frozen (particles.cu:334-338), w := 0 below
                 else {
                     cell = m.tetcell ? __ldg(m.tetcell + tet) : org - m.nPoints;
                     D3 u0;
@@ -771,7 +830,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                     needPro = false;
                 }
             }
-            if (active && !wallWait) {
+            if (active && !wallWait && !(FIN && needExact)) {
                 ++visits;
                 const int oc = visit_fast32<CPF_CFV_RUNTIME>(m, f, O, (WALL && leg) ? Phit : P, ws);
                 if (INTEG && stage > 0 && (oc == CPF_V_DONE || oc == CPF_V_WALL)) {
@@ -819,6 +878,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                     else P = xadd(P, disp);
                     hops += visits;
                     needPro = true;
+                    exactVel = false;
                     if (++s >= sp.nSub) active = false;
                 } else if (oc != CPF_V_HOP || visits >= 48) {
                     if (WALL && oc == CPF_V_WALL && visits <= 15 && leg == 0 && (!INTEG || stage == 0) && sp.reflect && ws.Dd < 10.f &&
@@ -826,20 +886,22 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
                         wallWait = true;
                     } else {
                         hops += visits;
-                        deferAt = s;
-                        active = false;
+                        if (FIN) needExact = true;
+                        else { deferAt = s; active = false; }
                     }
                 }
             }
         }
         if (live) {
-            if (tet < 0 && deferAt < 0) { w = 0.0; frz++; } // frozen in a prologue (tet only turns negative through the exact kernels)
+            if (frzHit) { w = 0.0; frz++; } // frozen in a prologue (tet turns negative through exact sub-steps only)
             nsteps += (unsigned)(s - sBegin);
             if constexpr (STATEFUL) { if (deferAt < 0 && s >= sp.nSub) pv.rng[i] = *stash; }
             st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
             st_stream_i(pv.tet + i, tet);
             if (KEEPV) {
                 if (sp.writeVel && velValid && deferAt < 0) st_stream4(pv.vel + i, make_double4(vel.x, vel.y, vel.z, -1.0));
+            } else if (FIN && exactVel) { // the particle's latest sub-step ran exactly: the velocity its reflector left
+                if (sp.writeVel) st_stream4(pv.vel + i, make_double4(velX.x, velX.y, velX.z, -1.0));
             } else if (sp.writeVel && cell >= 0 && deferAt < 0 && !velDone) {
                 st_stream4(pv.vel + i, vel4(ld_ucell(m, cell)));
             }
@@ -855,7 +917,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
         }
         if (!QMODE) break;
     }
-    flush_counters(sp, refl, 0u, hops, nsteps, 0u, frz);
+    flush_counters(sp, refl + ty.refl, ty.exact, hops + ty.hops, nsteps, ty.esc, frz);
 }
 
 // k_lean<RNG,CFV>: the all-particles pass of the filtered policy for the reference's own configuration (Euler, cell
@@ -869,6 +931,12 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 //   * CFV (cell id = origin vertex id - nPoints, every OpenFOAM decomposition) is a template parameter.
 #ifndef CPF_LEAN_THREADS
 #define CPF_LEAN_THREADS 128
+#endif
+#ifndef CPF_LEAN_PREFETCH
+#define CPF_LEAN_PREFETCH 0
+#endif
+#ifndef CPF_LEAN_PF_LINES
+#define CPF_LEAN_PF_LINES 0
 #endif
 // dynamic shared memory of k_lean per CTA: the staged deviates [row][thread] (rows: 3 per sub-step; the stateless stream
 // stages whole Philox blocks, i.e. up to 3 rows in front of and behind the chunk; no random walk: one row for the
@@ -927,16 +995,38 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
     double4 p4 = make_double4(0.0, 0.0, 0.0, 0.0);
     int tet = -1;
     if (have) { p4 = ld_stream4(pv.pos + i); tet = ld_stream_i(pv.tet + i); }
+#if CPF_LEAN_PREFETCH > 0
+    {   // L2 prefetch of the records around the start tets of the particles CPF_LEAN_PREFETCH CTAs ahead
+        const long long j = i + (long long)CPF_LEAN_PREFETCH * NT;
+        if (j < pv.n) {
+            const int t = __ldg(pv.tet + j);
+            if (t >= 0) {
+                const char *q = reinterpret_cast<const char *>(m.tetfast) + 64ll * t;
+#pragma unroll
+                for (int k = -CPF_LEAN_PF_LINES; k <= CPF_LEAN_PF_LINES; ++k) {
+                    const long long tk = (long long)t + 2 * k;
+                    if (tk >= 0 && tk < m.nTets) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 128 * k));
+                }
+            }
+        }
+    }
+#endif
     D3 P{ p4.x, p4.y, p4.z };
     double w = p4.w;
     const bool live = have && (w != 0.0);
     unsigned xs = (unsigned)__cvta_generic_to_shared(xi);
     if (RNG != CPF_RNG_NONE) {
         Rng<RNG> rng;
-        if (live) rng.open(pv, i, sp);
+#ifdef CPF_LEAN_STAGE_EARLY
+        // the stateless stream does not wait for the particle record: a dead slot's deviates are drawn and never read
+        const bool drawFor = STATEFUL ? live : have;
+#else
+        const bool drawFor = live;
+#endif
+        if (drawFor) rng.open(pv, i, sp);
         if constexpr (RNG == CPF_RNG_PHILOX) {
             xs += (unsigned)((3ull * sp.step0) & 3ull) * (unsigned)ROW; // the chunk's first deviate inside its first block
-            rng.stage_blocks(xi, NT, rows >> 2, live);
+            rng.stage_blocks(xi, NT, rows >> 2, drawFor);
         } else rng.stage(xi, NT, sp.nSub, 0, live);
         if constexpr (STATEFUL) { if (live) *stash = rng.st; }
     }
@@ -944,6 +1034,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
     D3 O{ 0.0, 0.0, 0.0 }, disp{ 0.0, 0.0, 0.0 };
     int cell = -1, left = -sp.nSub;
     unsigned hops = 0, cap = 0, frz = 0;
+    bool atWall = false;
     constexpr int CF = CFV ? CPF_CFV_YES : CPF_CFV_NO;
     WalkF ws;
     ws.cur = tet;
@@ -992,7 +1083,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
                 P = BARY ? disp : xadd(P, disp);
                 xs += STEP;
                 if (--left > 0) begin_substep();
-            } else left = -left;
+            } else { left = -left; atWall = oc == CPF_V_WALL; }
         }
     }
     const bool deferred = left < 0 && live && frz == 0u;
@@ -1012,7 +1103,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
         int qb = 0;
         if (lane == 0) qb = (int)atomicAdd(sp.countOut, (unsigned)__popc(mask));
         qb = __shfl_sync(0xffffffffu, qb, 0);
-        if (deferred) sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, s);
+        if (deferred) sp.queueOut[qb + __popc(mask & ((1u << lane) - 1u))] = make_int2((int)i, s | (atWall ? CPF_Q_WALL : 0));
     }
     flush_counters(sp, 0u, 0u, hops, (unsigned)s, 0u, frz);
 }
@@ -1105,57 +1196,43 @@ template <int RNG> __global__ void k_debug_normals(const ParticleView pv, const 
     default: { constexpr int R = CPF_RNG_NONE; CALL; } break;                   \
     }
 
-// Filtered policy (ConvexPoly locator), random walk R, integrator I, interpolation V:
-//   lean fast kernel over all particles -> wall-capable fast pass over its refusals
-//   -> [one exact sub-step -> resume fast (wall-capable)]* (Euler, stateless R only, CPF_MAX_ROUNDS) -> exact finisher.
+// Filtered policy (ConvexPoly locator), random walk R, integrator I, interpolation V.
+//   Euler, cell value (the reference's configuration): k_lean over all particles -> ONE finishing pass over its refusals
+//   (k_fast<..., FIN = 1>: fp32 walk with in-place wall reflection, a refused sub-step in the reference's arithmetic in place).
+//   RK2 / RK4 / vertex interpolation: k_fast over all particles -> wall-capable k_fast over its refusals -> k_general.
 // With the stateful XORWOW stream a kernel commits the generator state only for particles that finish their chunk in it;
-// every later kernel re-draws from the chunk-start state (Rng::skip / staged deviates), so the stream stays the reference's.
+// every later kernel re-draws from the chunk-start state (staged deviates / Rng::skip), so the stream stays the reference's.
 template <int R, int I, int V>
 static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleView &pv, const StepParams &sp, dim3 grid, int nSub)
 {
     typedef typename Rng<R>::Xi Xi;
     constexpr bool STATEFUL = Rng<R>::STATEFUL;
     cudaStream_t st = ctx->stream;
-    const int rounds = (I == CPF_EULER && !V && !STATEFUL) ? std::max(0, std::min(CPF_MAX_ROUNDS, nSub - 1)) : 0;
     CPF_CUDA(ctx, cudaMemsetAsync(ctx->d_queue_count, 0, sizeof(unsigned) * 64, st));
     // queue kernels: one resident wave on the 148 SMs of a B200 (grid-stride loops inside)
-    const dim3 wgrid(std::min<unsigned>(grid.x, 148u * CPF_WALL_MIN_BLOCKS));
-    const dim3 egrid(std::min<unsigned>(grid.x, 148u * 8u));
+    const dim3 wgrid(std::min<unsigned>(grid.x, 148u * ((I == CPF_EULER && !V) ? CPF_FIN_MIN_BLOCKS : CPF_WALL_MIN_BLOCKS)));
     const size_t xiBytes = R == CPF_RNG_NONE ? 0 : sizeof(Xi) * 3 * 128 * (size_t)nSub + (STATEFUL ? sizeof(curandState_t) * 128 : 0);
-    auto queue_params = [&](int q, bool withOut) { // queue q lives in d_queue[q & 1], its length in d_queue_count[q]
-        StepParams x = sp;
-        x.queueIn = ctx->d_queue[q & 1]; x.countIn = ctx->d_queue_count + q;
-        if (withOut) { x.queueOut = ctx->d_queue[(q + 1) & 1]; x.countOut = ctx->d_queue_count + q + 1; }
-        return x;
-    };
-    auto fast_queue_pass = [&](int q) {
-        const StepParams b = queue_params(q, true);
-        k_fast<R, 2, 1, I, V><<<wgrid, 128, xiBytes, st>>>(m, pv, b);
-        ctx->launches++;
-    };
-    StepParams a = sp;
+    StepParams a = sp; // all-particles pass: refusals into queue 0
     a.queueOut = ctx->d_queue[0]; a.countOut = ctx->d_queue_count;
+    StepParams b = sp; // first queue pass: queue 0 -> queue 1
+    b.queueIn = ctx->d_queue[0]; b.countIn = ctx->d_queue_count;
     if constexpr (I == CPF_EULER && !V) {
         const dim3 lgrid((unsigned)((pv.n + CPF_LEAN_THREADS - 1) / CPF_LEAN_THREADS));
         const size_t lb = CPF_LEAN_SMEM_BYTES(lean_rows(R, nSub, sp.step0), sizeof(Xi), STATEFUL);
         if (m.tetcell == nullptr) k_lean<R, true><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
         else k_lean<R, false><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
+        k_fast<R, 2, 1, CPF_EULER, 0, 1><<<wgrid, 128, xiBytes, st>>>(m, pv, b);
+        ctx->launches += 2;
     } else {
+        const dim3 egrid(std::min<unsigned>(grid.x, 148u * 8u));
+        b.queueOut = ctx->d_queue[1]; b.countOut = ctx->d_queue_count + 1;
+        StepParams z = sp; // the rest in the reference's arithmetic
+        z.queueIn = ctx->d_queue[1]; z.countIn = ctx->d_queue_count + 1;
         k_fast<R, 0, 0, I, V><<<grid, 128, xiBytes, st>>>(m, pv, a);
+        k_fast<R, 2, 1, I, V><<<wgrid, 128, xiBytes, st>>>(m, pv, b);
+        k_general<R, 2><<<egrid, 128, 0, st>>>(m, pv, z);
+        ctx->launches += 3;
     }
-    ctx->launches++;
-    int q = 0;
-    if (CPF_WALL_PASS) fast_queue_pass(q++);
-    for (int r = 0; r < rounds; ++r) {
-        const StepParams e = queue_params(q, false);
-        k_exact_convex<R, 1><<<egrid, 128, 0, st>>>(m, pv, e);
-        ctx->launches++;
-        fast_queue_pass(q++);
-    }
-    const StepParams z = queue_params(q, false);
-    if (I == CPF_EULER && !V) k_exact_convex<R, 2><<<egrid, 128, 0, st>>>(m, pv, z);
-    else k_general<R, 2><<<egrid, 128, 0, st>>>(m, pv, z); // RK2 / RK4 / vertex interpolation: the rest in the reference's arithmetic
-    ctx->launches++;
     return CPF_OK;
 }
 
