@@ -52,8 +52,14 @@ WORKLOADS = {
                                  desc="C5: channel 1e6 cells, 1e8 tracers over 8 GPUs (1.25e7 per GPU), through-flow, outlet patch "
                                       "ESCAPE, escaped tracers compacted away by the counting sort"),
     # BASELINE.json configs[1]
+    # (outlet ESCAPE + re-injection: under the reference's all-reflecting walls the uniform part of the field parks the
+    # whole cloud on the x+ wall within one box transit -- round 2 measured 0.64 reflections per particle-step there)
     "box100_1e6": dict(mesh="box", dims=(100, 100, 100), jitter=0.1, n=1_000_000, dt=0.004, ncycles=10, D=0.0, field="vortex",
-                       integrator="rk2", desc="C2: box 100^3 hex (1e6 cells), 1e6 tracers, RK2, frozen uniform+vortex field"),
+                       integrator="rk2", escape=("x+",), reseed_every=5,
+                       desc="C2: box 100^3 hex (1e6 cells), 1e6 tracers, RK2, frozen uniform+vortex field, outlet patch ESCAPE, "
+                            "escaped tracers re-seeded behind the inlet every 5 steps (steady state)"),
+    "box100_1e6_allreflect": dict(mesh="box", dims=(100, 100, 100), jitter=0.1, n=1_000_000, dt=0.004, ncycles=10, D=0.0, field="vortex",
+                                  integrator="rk2", desc="as box100_1e6 with the reference's all-reflecting walls (the cloud piles up on the x+ wall)"),
     # BASELINE.json configs[0]: pitzDaily stand-in, launch-latency regime (1e5 tracers; a step = one save interval of 10 sub-steps)
     "pitz_1e5": dict(mesh="pitz", n=100_000, dt=1e-5, ncycles=10, D=5.7e-6, field="pitz", integrator="euler",
                      desc="C1: pitzDaily-sized block (12 225 hex cells), 1e5 tracers, Euler, frozen flow, random walk, "

@@ -355,9 +355,10 @@ CPF_DEV D3 displacement(const MeshView &m, const StepParams &sp, Rng<RNG> &rng, 
 // ALL warps of the grid -- lane k of warp g takes entry g + k * (number of warps) -- instead of packing 32 neighbours
 // into one warp: the passes are short, divergent and latency-bound, a queue of a few 1e4 entries fills a fraction of the
 // resident warps when packed, and every lane less in a warp is one serialised rare-event section less.
-CPF_DEV long long first_slot(bool queue)
+CPF_DEV long long first_slot(bool queue, long long total)
 {
-    if (!queue) return (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // a queue longer than the grid (most particles deferred: a cloud held against a wall) is better off packed (coalesced)
+    if (!queue || total >= (long long)gridDim.x * blockDim.x) return (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned wpb = blockDim.x >> 5;
     return (long long)(blockIdx.x * wpb + (threadIdx.x >> 5)) + (long long)(threadIdx.x & 31u) * ((long long)gridDim.x * wpb);
 }
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact(const MeshView m,
     Tally ty{ 0u, 0u, 0u, 0u, 0u };
     unsigned nsteps = 0;
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
-    for (long long slot = first_slot(QMODE != 0); slot < total; slot += (long long)gridDim.x * blockDim.x) {
+    for (long long slot = first_slot(QMODE != 0, total); slot < total; slot += (long long)gridDim.x * blockDim.x) {
         long long i = slot;
         int s0 = 0;
         if (QMODE) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y & CPF_Q_SUBSTEP; }
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(128, CPF_MIN_BLOCKS) k_exact_convex(const Mesh
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long base = 0; base < total; base += stride) { // grid-uniform trip count
-        const long long slot = base + first_slot(QMODE != 0);
+        const long long slot = base + first_slot(QMODE != 0, total);
         long long i = slot;
         int s = 0;
         bool have = slot < total;
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__(128, 3) k_general(const MeshView m, const Part
     Tally ty{ 0u, 0u, 0u, 0u, 0u };
     unsigned nsteps = 0;
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
-    for (long long slot = first_slot(QMODE != 0); slot < total; slot += (long long)gridDim.x * blockDim.x) {
+    for (long long slot = first_slot(QMODE != 0, total); slot < total; slot += (long long)gridDim.x * blockDim.x) {
         long long i = slot;
         int s0 = 0;
         if (QMODE) { const int2 q = sp.queueIn[slot]; i = q.x; s0 = q.y & CPF_Q_SUBSTEP; }
@@ -700,7 +701,7 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
     const long long total = QMODE ? (long long)*sp.countIn : pv.n;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long base = 0; base < total; base += stride) { // grid-uniform trip count
-        const long long slot = base + first_slot(QMODE != 0);
+        const long long slot = base + first_slot(QMODE != 0, total);
         int deferAt = -1;
         bool needExact = false, exactVel = false, frzHit = false; // FIN: sub-step s is to be redone exactly / the velocity to report is velX
         D3 velX{ 0.0, 0.0, 0.0 };
@@ -932,11 +933,8 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 #ifndef CPF_LEAN_THREADS
 #define CPF_LEAN_THREADS 128
 #endif
-#ifndef CPF_LEAN_PREFETCH
-#define CPF_LEAN_PREFETCH 0
-#endif
-#ifndef CPF_LEAN_PF_LINES
-#define CPF_LEAN_PF_LINES 0
+#ifndef CPF_LEAN_RK4_BLOCKS
+#define CPF_LEAN_RK4_BLOCKS 7
 #endif
 // dynamic shared memory of k_lean per CTA: the staged deviates [row][thread] (rows: 3 per sub-step; the stateless stream
 // stages whole Philox blocks, i.e. up to 3 rows in front of and behind the chunk; no random walk: one row for the
@@ -977,9 +975,15 @@ CPF_DEV int lds_i32(unsigned a) { int r; asm volatile("ld.shared.s32 %0, [%1];" 
 // sub-steps to do -- refused, frozen or not started), the visit cap as a value of the visit counter, and the cell of the
 // last prologue.  The start tet of the current sub-step -- needed only if the sub-step is refused -- waits in shared
 // memory, in the slot of the sub-step's first deviate (already consumed by then).
-template <int RNG, bool CFV, int LOC = CPF_LOCATOR_CONVEX>
-__global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / CPF_LEAN_THREADS) k_lean(const MeshView m, const ParticleView pv, const StepParams sp)
+//   * INTEG = CPF_RK2 / CPF_RK4 (extensions; convex locator): a sub-step is a chain of walks from the
+//     same start (P, tet) -- one per stage point P + h k, then the move walk -- through the same loop: a stage walk that
+//     ends (in a tet, or at a certified wall face of it) yields that cell's velocity and sets up the next walk.  The
+//     start tet and its origin id wait in two shared-memory rows of their own, the stage cells of RK4 in three registers
+//     (their velocities are re-read when v_eff is formed: no fp64 accumulators are carried through the walks).
+template <int RNG, bool CFV, int LOC = CPF_LOCATOR_CONVEX, int INTEG = CPF_EULER>
+__global__ void __launch_bounds__(CPF_LEAN_THREADS, (INTEG == CPF_RK4 ? CPF_LEAN_RK4_BLOCKS : CPF_FAST_MIN_BLOCKS) * 128 / CPF_LEAN_THREADS) k_lean(const MeshView m, const ParticleView pv, const StepParams sp)
 {
+    static_assert(!INTEG || LOC == CPF_LOCATOR_CONVEX, "stage walks are segment walks");
     constexpr bool BARY = LOC == CPF_LOCATOR_BARY;
     constexpr int NT = CPF_LEAN_THREADS;
     typedef typename Rng<RNG>::Xi Xi;
@@ -989,40 +993,21 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
     extern __shared__ double s_dyn[];
     const unsigned rows = lean_rows(RNG, sp.nSub, sp.step0);
     Xi *xi = reinterpret_cast<Xi *>(s_dyn) + threadIdx.x;
-    curandState_t *stash = reinterpret_cast<curandState_t *>(xi - threadIdx.x + (size_t)NT * rows) + threadIdx.x;
+    curandState_t *stash = reinterpret_cast<curandState_t *>(xi - threadIdx.x + (size_t)NT * (rows + (INTEG ? 2u : 0u))) + threadIdx.x;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool have = i < pv.n;
     double4 p4 = make_double4(0.0, 0.0, 0.0, 0.0);
     int tet = -1;
     if (have) { p4 = ld_stream4(pv.pos + i); tet = ld_stream_i(pv.tet + i); }
-#if CPF_LEAN_PREFETCH > 0
-    {   // L2 prefetch of the records around the start tets of the particles CPF_LEAN_PREFETCH CTAs ahead
-        const long long j = i + (long long)CPF_LEAN_PREFETCH * NT;
-        if (j < pv.n) {
-            const int t = __ldg(pv.tet + j);
-            if (t >= 0) {
-                const char *q = reinterpret_cast<const char *>(m.tetfast) + 64ll * t;
-#pragma unroll
-                for (int k = -CPF_LEAN_PF_LINES; k <= CPF_LEAN_PF_LINES; ++k) {
-                    const long long tk = (long long)t + 2 * k;
-                    if (tk >= 0 && tk < m.nTets) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 128 * k));
-                }
-            }
-        }
-    }
-#endif
     D3 P{ p4.x, p4.y, p4.z };
     double w = p4.w;
     const bool live = have && (w != 0.0);
     unsigned xs = (unsigned)__cvta_generic_to_shared(xi);
+    const unsigned t0 = xs + rows * (unsigned)ROW; // INTEG: the rows of the sub-step's start tet and (t0 + ROW) its origin id
     if (RNG != CPF_RNG_NONE) {
         Rng<RNG> rng;
-#ifdef CPF_LEAN_STAGE_EARLY
         // the stateless stream does not wait for the particle record: a dead slot's deviates are drawn and never read
         const bool drawFor = STATEFUL ? live : have;
-#else
-        const bool drawFor = live;
-#endif
         if (drawFor) rng.open(pv, i, sp);
         if constexpr (RNG == CPF_RNG_PHILOX) {
             xs += (unsigned)((3ull * sp.step0) & 3ull) * (unsigned)ROW; // the chunk's first deviate inside its first block
@@ -1039,10 +1024,68 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
     WalkF ws;
     ws.cur = tet;
     ws.org = -1;
+    int stage = 0, c1 = -1, c2 = -1, c3 = -1; // INTEG: 0 = move walk, 1.. = walk to the stage point of k2..; RK4: cells of k1..k3
+    // a walk along the fp64 displacement d from (P, ws.cur, ws.org, O)
+    auto begin_walk = [&](const D3 &d) {
+        ws.dx = (float)d.x; ws.dy = (float)d.y; ws.dz = (float)d.z;
+        ws.Dd = fmaxf(fmaxf(fabsf(ws.dx), fabsf(ws.dy)), fabsf(ws.dz));
+        walkf_rebase(ws, O, P);
+        ws.t_in = 0.f;
+        cap = hops + 47u; // the 48th visit of a walk must end it
+    };
+    // S2 with the effective velocity v: disp = (P + dt v) - P (+ random walk), and the move walk
+    auto begin_move = [&](const D3 &v) {
+        disp = D3{ __dsub_rn(__fma_rn(sp.dt, v.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, v.y, P.y), P.y),
+                   __dsub_rn(__fma_rn(sp.dt, v.z, P.z), P.z) };
+        if (RNG != CPF_RNG_NONE) {
+            disp.x = __fma_rn(lds_xi<Xi, 0>(xs), sp.randDisp, disp.x);
+            disp.y = __fma_rn(lds_xi<Xi, ROW>(xs), sp.randDisp, disp.y);
+            disp.z = __fma_rn(lds_xi<Xi, 2 * ROW>(xs), sp.randDisp, disp.z);
+        }
+        begin_walk(disp);
+    };
+    // INTEG: a stage walk has ended in ws.cur -- that cell's velocity, back to the start of the sub-step, next walk
+    auto stage_done = [&]() {
+        ++hops; // the stage walk's final visit
+        const int cs = CFV ? ws.org - m.nPoints : __ldg(m.tetcell + ws.cur);
+        const D3 kx = ld_ucell(m, cs);
+        const int tet0 = lds_i32(t0), org0 = lds_i32(t0 + ROW);
+        if (ws.cur != tet0) { // every walk of a sub-step starts from (P, tet)
+            f32_load(m, tet0, f);
+            if (ws.org != org0) O = ld_vertex(m.vpos, org0);
+        }
+        ws.cur = tet0;
+        ws.org = org0;
+        D3 v = kx;
+        bool last = true;
+        if (INTEG == CPF_RK4) {
+            if (stage == 1) { c2 = cs; last = false; begin_walk(xsub(axpy3(__dmul_rn(0.5, sp.dt), kx, P), P)); }
+            else if (stage == 2) { c3 = cs; last = false; begin_walk(xsub(axpy3(sp.dt, kx, P), P)); }
+            else {
+                const D3 k1 = ld_ucell(m, c1), k23 = xadd(ld_ucell(m, c2), ld_ucell(m, c3));
+                v.x = __ddiv_rn(__fma_rn(2.0, k23.x, __dadd_rn(k1.x, kx.x)), 6.0);
+                v.y = __ddiv_rn(__fma_rn(2.0, k23.y, __dadd_rn(k1.y, kx.y)), 6.0);
+                v.z = __ddiv_rn(__fma_rn(2.0, k23.z, __dadd_rn(k1.z, kx.z)), 6.0);
+            }
+        }
+        if (last) {
+            if (sp.writeVel && left == 1) st_stream4(pv.vel + i, vel4(v)); // v_eff of the call's last sub-step (a finisher that redoes it writes again)
+            begin_move(v);
+            stage = 0;
+        } else ++stage;
+    };
     // S1 + S2 of the sub-step whose deviates sit at xs, then the walk set up from (P, ws.cur, ws.org, O)
     auto begin_substep = [&]() {
         cell = CFV ? ws.org - m.nPoints : __ldg(m.tetcell + ws.cur);
         const D3 u0 = ld_ucell(m, cell);
+        if constexpr (INTEG != CPF_EULER) { // k1 = v(P, tet); first stage point P + dt/2 k1 (RK2 midpoint and RK4 alike)
+            sts_i32(t0, ws.cur);
+            sts_i32(t0 + ROW, ws.org);
+            c1 = cell;
+            stage = 1;
+            begin_walk(xsub(axpy3(__dmul_rn(0.5, sp.dt), u0, P), P));
+            return;
+        }
         disp = D3{ __dsub_rn(__fma_rn(sp.dt, u0.x, P.x), P.x), __dsub_rn(__fma_rn(sp.dt, u0.y, P.y), P.y),
                    __dsub_rn(__fma_rn(sp.dt, u0.z, P.z), P.z) };
         if (RNG != CPF_RNG_NONE) {
@@ -1071,7 +1114,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
             ws.org = first_origin<CF>(m, tet, f);
             O = ld_vertex(m.vpos, ws.org);
             if (BARY || start_point_clear(m, f, (float)(P.x - O.x), (float)(P.y - O.y), (float)(P.z - O.z))) left = sp.nSub;
-            else sts_i32(xs, tet); // refused before its first sub-step
+            else sts_i32(INTEG ? t0 : xs, tet); // refused before its first sub-step
         }
     }
     if (left > 0) begin_substep();
@@ -1079,6 +1122,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
         if (left > 0) {
             const int oc = BARY ? visit_bary32<CF>(m, f, O, disp, ws, hops >= cap) : visit_fast32<CF>(m, f, O, P, ws, hops >= cap);
             if (oc == CPF_V_HOP) ++hops;
+            else if (INTEG != CPF_EULER && stage > 0 && (oc == CPF_V_DONE || oc == CPF_V_WALL)) stage_done();
             else if (oc == CPF_V_DONE) {
                 P = BARY ? disp : xadd(P, disp);
                 xs += STEP;
@@ -1092,8 +1136,8 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, CPF_FAST_MIN_BLOCKS * 128 / 
     if (live) {
         if constexpr (STATEFUL) { if (left == 0) pv.rng[i] = *stash; }
         st_stream4(pv.pos + i, make_double4(P.x, P.y, P.z, w));
-        st_stream_i(pv.tet + i, deferred ? lds_i32(xs) : ws.cur);
-        if (sp.writeVel && cell >= 0 && !deferred) {
+        st_stream_i(pv.tet + i, deferred ? lds_i32(INTEG ? t0 : xs) : ws.cur);
+        if (INTEG == CPF_EULER && sp.writeVel && cell >= 0 && !deferred) {
             st_stream4(pv.vel + i, vel4(ld_ucell(m, cell)));
         }
     }
@@ -1228,6 +1272,12 @@ static int launch_filtered(cpf_context *ctx, const MeshView &m, const ParticleVi
         b.queueOut = ctx->d_queue[1]; b.countOut = ctx->d_queue_count + 1;
         StepParams z = sp; // the rest in the reference's arithmetic
         z.queueIn = ctx->d_queue[1]; z.countIn = ctx->d_queue_count + 1;
+        if constexpr (!V) { // cell value: the lean all-particles pass with stage walks
+            const dim3 lgrid((unsigned)((pv.n + CPF_LEAN_THREADS - 1) / CPF_LEAN_THREADS));
+            const size_t lb = CPF_LEAN_SMEM_BYTES(lean_rows(R, nSub, sp.step0) + 2u, sizeof(Xi), STATEFUL);
+            if (m.tetcell == nullptr) k_lean<R, true, CPF_LOCATOR_CONVEX, I><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
+            else k_lean<R, false, CPF_LOCATOR_CONVEX, I><<<lgrid, CPF_LEAN_THREADS, lb, st>>>(m, pv, a);
+        } else
         k_fast<R, 0, 0, I, V><<<grid, 128, xiBytes, st>>>(m, pv, a);
         k_fast<R, 2, 1, I, V><<<wgrid, 128, xiBytes, st>>>(m, pv, b);
         k_general<R, 2><<<egrid, 128, 0, st>>>(m, pv, z);
@@ -1269,7 +1319,7 @@ static int launch_filtered_rng(cpf_context *ctx, const MeshView &m, const Partic
 
 // most sub-steps one launch sequence may fuse: the staged deviates of a chunk must fit the 48 KB of shared memory a
 // kernel gets without opting in (3 x 4 B per sub-step and thread, stateless streams; 3 x 8 B + the 48-byte state, XORWOW)
-int max_fused_substeps(const cpf_context *ctx) { return ctx->cfg.rng == CPF_RNG_XORWOW ? 14 : 16; }
+int max_fused_substeps(const cpf_context *ctx) { return ctx->cfg.rng == CPF_RNG_XORWOW ? (ctx->cfg.integrator == CPF_EULER ? 14 : 13) : 16; } // RK: two more rows (start tet, origin)
 // library default (cfg.fuse_substeps == 0); XORWOW: 10 sub-steps = 36 KB of staged fp64 deviates + states, 6 CTAs per SM
 int default_fused_substeps(const cpf_context *ctx) { return ctx->cfg.rng == CPF_RNG_XORWOW ? 10 : 16; }
 

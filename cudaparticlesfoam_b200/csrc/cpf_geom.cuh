@@ -306,6 +306,26 @@ CPF_DEV void f32_load(const MeshView &m, int tet, Fast32 &f)
     f.E = __uint_as_float(w[15]);
 }
 
+// the same, pinned where it is written (volatile): the speculative request of the next record must not sink below the
+// checks that follow it
+CPF_DEV void f32_load_pinned(const MeshView &m, int tet, Fast32 &f)
+{
+    unsigned w[16];
+    const uint4 *p = m.tetfast + 4ll * tet;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]) : "l"(p + 2));
+    f.link = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f.N[k][c] = __uint_as_float(w[4 + 3 * k + c]);
+    f.aux = (int)w[13];
+    f.V6 = __uint_as_float(w[14]);
+    f.E = __uint_as_float(w[15]);
+}
+
 CPF_DEV float rcp_ftz(float x)
 {
     float r;
@@ -441,6 +461,20 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
     for (int j = 0; j < 4; ++j) h[j] = (j == js) ? INF : fmaf(t, b[j], a[j]);
     const float c3m = fminf(fminf(h[0], h[1]), fminf(h[2], h[3]));
     const int link = sel4(f.link.x, f.link.y, f.link.z, f.link.w, js);
+    // The record behind the selected face is requested BEFORE the C3 / range verdict is known (the compare chain runs while
+    // the load is in flight).  A lane whose visit is refused never looks at its record registers again (it stops, or
+    // reloads after an exact sub-step), and nothing is requested at a wall or at the visit cap.
+    if (mesh_is_cfv<CFV>(m) && link >= 0 && !lastVisit) {
+        const int aux = f.aux;
+        if (js == 3) O = ld_vertex(m.vpos, aux);
+        f32_load_pinned(m, link >> 2, f);
+        if (!((c3m >= g) && (t > ws.t_in) && (t <= 1.f))) return CPF_V_REFUSE;
+        ws.cur = link >> 2;
+        ws.t_in = t;
+        ws.path = (ws.path << 2) | (unsigned)js;
+        if (js == 3) { ws.org = aux; ws.RD3 = -1.f; }
+        return CPF_V_HOP;
+    }
     if (!((c3m >= g) && (t > ws.t_in) && (t <= 1.f))) return CPF_V_REFUSE; // incl. "no candidate" (t = inf)
     if (link < 0) { ws.wall_js = js; ws.wall_link = link; return CPF_V_WALL; }
     if (lastVisit) return CPF_V_REFUSE;
