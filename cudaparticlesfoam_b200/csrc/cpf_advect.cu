@@ -933,6 +933,9 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 #ifndef CPF_LEAN_THREADS
 #define CPF_LEAN_THREADS 128
 #endif
+#ifndef CPF_LEAN_PFU
+#define CPF_LEAN_PFU 1
+#endif
 #ifndef CPF_LEAN_RK4_BLOCKS
 #define CPF_LEAN_RK4_BLOCKS 7
 #endif
@@ -1118,9 +1121,10 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, (INTEG == CPF_RK4 ? CPF_LEAN
         }
     }
     if (left > 0) begin_substep();
+    constexpr bool PFU = CFV && !BARY && INTEG == CPF_EULER && CPF_LEAN_PFU;
     while (__any_sync(0xffffffffu, left > 0)) {
         if (left > 0) {
-            const int oc = BARY ? visit_bary32<CF>(m, f, O, disp, ws, hops >= cap) : visit_fast32<CF>(m, f, O, P, ws, hops >= cap);
+            const int oc = BARY ? visit_bary32<CF>(m, f, O, disp, ws, hops >= cap) : visit_fast32<CF, PFU>(m, f, O, P, ws, hops >= cap);
             if (oc == CPF_V_HOP) ++hops;
             else if (INTEG != CPF_EULER && stage > 0 && (oc == CPF_V_DONE || oc == CPF_V_WALL)) stage_done();
             else if (oc == CPF_V_DONE) {

@@ -51,6 +51,12 @@ CPF_DEV int ld_stream_i(const int *p)
     asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
+// L1 prefetch as ONE predicated instruction: it stays in the basic block it is written in, and -- unlike a load -- it
+// holds no dependency barrier, so the reconvergence points between it and the use of the line do not wait for it
+CPF_DEV void prefetch_l1_if(const void *p, bool on)
+{
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %1, 0; @q prefetch.global.L1 [%0]; }" ::"l"(p), "r"((int)on));
+}
 CPF_DEV void st_stream_i(int *p, int v) { asm volatile("st.global.cs.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,7 +425,9 @@ CPF_DEV bool start_point_clear(const MeshView &m, const Fast32 &f, float rx, flo
 // lastVisit: the caller's visit cap is reached -- a hop out of this tet is refused BEFORE the next record is requested
 // (keeps every use of the caller's state ahead of the loads: nothing in the hop path then touches a register the
 // loads write, which ptxas otherwise resolves with a copy right behind them, i.e. a wait for the record inside the hop)
-template <int CFV>
+// PFU (cell-centre decompositions): a lane whose sub-step ends here will want this cell's velocity for its next one; the
+// line is requested from the common block, ahead of the divergent sections.
+template <int CFV, bool PFU = false>
 CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, WalkF &ws, bool lastVisit = false)
 {
     const float INF = __int_as_float(0x7f800000);
@@ -440,7 +448,9 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
     const float g = fmaf(m.guardf, V, 3.814697265625e-6f * (E * E) * (E + ws.RD3));
 #pragma unroll
     for (int j = 0; j < 4; ++j) e[j] = a[j] + b[j];
-    if (fminf(fminf(e[0], e[1]), fminf(e[2], e[3])) >= g) return CPF_V_DONE; // C2 and "inside" in one
+    const bool done = fminf(fminf(e[0], e[1]), fminf(e[2], e[3])) >= g; // C2 and "inside" in one
+    if (PFU) prefetch_l1_if(m.ucell + (ws.org - m.nPoints), done);
+    if (done) return CPF_V_DONE;
     if (!(fminf(fminf(fabsf(e[0]), fabsf(e[1])), fminf(fabsf(e[2]), fabsf(e[3]))) >= g)) return CPF_V_REFUSE;
     // Exit face: smallest crossing parameter among the faces whose plane the end point is behind.  For those the
     // start/entry point is certified in front (true a_j + t_in b_j >= G V6), so b_j < 0 and t_j > t_in >= 0: positive
@@ -477,7 +487,8 @@ CPF_DEV int visit_fast32(const MeshView &m, Fast32 &f, D3 &O, const D3 &P0, Walk
     }
     if (!((c3m >= g) && (t > ws.t_in) && (t <= 1.f))) return CPF_V_REFUSE; // incl. "no candidate" (t = inf)
     if (link < 0) { ws.wall_js = js; ws.wall_link = link; return CPF_V_WALL; }
-    if (lastVisit) return CPF_V_REFUSE;
+    // cell-centre decompositions known at compile time took every hop above: no second load site of the record
+    if (lastVisit || CFV == CPF_CFV_YES) return CPF_V_REFUSE;
     ws.cur = link >> 2;
     ws.t_in = t;
     ws.path = (ws.path << 2) | (unsigned)js;
