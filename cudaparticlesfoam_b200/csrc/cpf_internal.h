@@ -87,6 +87,7 @@ struct cpf_context {
 
     // BVH (sorted tet order + 8-ary implicit tree of float boxes)
     int *d_bvh_tet = nullptr;                 // [nTets] tet ids in Morton order
+    float4 *d_bvh_tet_lo = nullptr, *d_bvh_tet_hi = nullptr; // box of every tet, in the order of d_bvh_tet
     std::vector<cpf::BvhLevel> bvh;           // level 0 = groups of 8 tets
     float4 *d_bvh_top_lo = nullptr, *d_bvh_top_hi = nullptr; // concatenated top levels (staged in smem)
     int bvh_top_first_level = 0, bvh_top_nodes = 0;

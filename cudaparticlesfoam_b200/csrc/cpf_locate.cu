@@ -6,7 +6,7 @@
 //
 // Structure: tets sorted along a 63-bit Morton curve of their centroids; an implicit 8-ary tree of
 // float boxes (rounded outward) over that order, level 0 = groups of 8 tets.  The top levels
-// (<= 2048-node level and everything above it) are staged in shared memory by every CTA; the lower
+// (<= 1024-node level and everything above it) are staged in shared memory, once per CTA of a resident grid; the lower
 // levels and the candidate tets come through L2.  A particle is assigned the LOWEST tet id whose
 // four reference barycentric coordinates (cuda/DeviceTetMesh.cuh:108-156) are all >= 0 -- the same
 // answer as a brute-force scan, independent of traversal order; from a containing tet the
@@ -44,8 +44,10 @@ __global__ void k_morton(long long nTets, const int4 *__restrict__ tetv, const d
     ids[t] = (int)t;
 }
 
+// level 0 (groups of 8 tets in Morton order) and, below it, the box of every single tet in the same order (tlo/thi)
 __global__ void k_bvh_leaves(long long nGroups, long long nTets, const int *__restrict__ order, const int4 *__restrict__ tetv,
-                             const double4 *__restrict__ vpos, float4 *__restrict__ blo, float4 *__restrict__ bhi)
+                             const double4 *__restrict__ vpos, float4 *__restrict__ blo, float4 *__restrict__ bhi,
+                             float4 *__restrict__ tlo, float4 *__restrict__ thi)
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nGroups) return;
@@ -55,12 +57,17 @@ __global__ void k_bvh_leaves(long long nGroups, long long nTets, const int *__re
         if (i >= nTets) break;
         const int4 v = tetv[order[i]];
         const int ids[4] = { v.x, v.y, v.z, v.w };
+        double tlx = 1e300, tly = 1e300, tlz = 1e300, thx = -1e300, thy = -1e300, thz = -1e300;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const D3 p = ld_vertex(vpos, ids[k]);
-            lx = fmin(lx, p.x); ly = fmin(ly, p.y); lz = fmin(lz, p.z);
-            hx = fmax(hx, p.x); hy = fmax(hy, p.y); hz = fmax(hz, p.z);
+            tlx = fmin(tlx, p.x); tly = fmin(tly, p.y); tlz = fmin(tlz, p.z);
+            thx = fmax(thx, p.x); thy = fmax(thy, p.y); thz = fmax(thz, p.z);
         }
+        tlo[i] = make_float4(__double2float_rd(tlx), __double2float_rd(tly), __double2float_rd(tlz), 0.f);
+        thi[i] = make_float4(__double2float_ru(thx), __double2float_ru(thy), __double2float_ru(thz), 0.f);
+        lx = fmin(lx, tlx); ly = fmin(ly, tly); lz = fmin(lz, tlz);
+        hx = fmax(hx, thx); hy = fmax(hy, thy); hz = fmax(hz, thz);
     }
     blo[g] = make_float4(__double2float_rd(lx), __double2float_rd(ly), __double2float_rd(lz), 0.f);
     bhi[g] = make_float4(__double2float_ru(hx), __double2float_ru(hy), __double2float_ru(hz), 0.f);
@@ -93,80 +100,112 @@ struct BvhView {
     int topNodes;
     const float4 *topLo, *topHi;
     const int *order;
+    const float4 *tetLo, *tetHi; // box of every tet, in `order`
     long long nTets;
 };
 
-CPF_DEV bool in_box(const float4 lo, const float4 hi, D3 P)
+// P rounded down / up to float: a float box (rounded outward at build time) contains P iff it overlaps [Plo, Phi] --
+// the test never rejects a box that really contains the point
+struct PF { float lx, ly, lz, hx, hy, hz; };
+CPF_DEV bool in_box(const float4 lo, const float4 hi, const PF &p)
 {
-    return P.x >= (double)lo.x && P.x <= (double)hi.x && P.y >= (double)lo.y && P.y <= (double)hi.y && P.z >= (double)lo.z &&
-           P.z <= (double)hi.z;
+    return p.hx >= lo.x && p.lx <= hi.x && p.hy >= lo.y && p.ly <= hi.y && p.hz >= lo.z && p.lz <= hi.z;
 }
 
-// lostOnly: relocate only particles that are still active but carry a negative tet id (lost after a
-// failed reflection sequence) -- the reference freezes those forever (cuda/particles.cu:334-338)
-__global__ void __launch_bounds__(128) k_locate(const MeshView m, const BvhView bv, const ParticleView pv, const int lostOnly,
-                                                unsigned long long *__restrict__ relocated)
+// Work list of a lost-only pass: slots of the particles that are active but carry a negative tet id (just re-seeded, or
+// lost after a failed reflection sequence -- the reference freezes those forever, cuda/particles.cu:334-338).  One
+// atomic per warp.
+__global__ void k_collect_lost(const ParticleView pv, int *__restrict__ list, unsigned *__restrict__ count)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool want = i < pv.n && pv.pos[i].w != 0.0 && pv.tet[i] < 0;
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (want) list[base + __popc(mask & ((1u << lane) - 1u))] = (int)i;
+}
+
+// One resident wave of CTAs, each staging the top of the tree once and then taking particles in a grid-stride loop
+// (list == nullptr: every particle slot; else the *count entries of list).  Depth-first traversal with the eight children
+// of a node tested where the node is expanded (their boxes are contiguous), so the stack holds only boxes that contain
+// the point.
+__global__ void __launch_bounds__(128) k_locate(const MeshView m, const __grid_constant__ BvhView bv, const ParticleView pv, const int *__restrict__ list,
+                                                const unsigned *__restrict__ count, unsigned long long *__restrict__ relocated)
 {
     extern __shared__ float4 smem[];
+    const long long total = list ? (long long)*count : pv.n;
+    if ((long long)blockIdx.x * blockDim.x >= total) return; // nothing for this CTA: do not stage either
     float4 *sLo = smem, *sHi = smem + bv.topNodes;
     for (int q = threadIdx.x; q < bv.topNodes; q += blockDim.x) { sLo[q] = bv.topLo[q]; sHi[q] = bv.topHi[q]; }
     __syncthreads();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pv.n) return;
-    const double4 p4 = pv.pos[i];
-    if (lostOnly) { if (p4.w == 0.0 || pv.tet[i] >= 0) return; }
-    else if (p4.w == 0.0) { pv.tet[i] = -1; return; }
-    const D3 P{ p4.x, p4.y, p4.z };
-    int best = 0x7fffffff;
-    int stack[72];
-    int sp = 0;
-    const int root = bv.nLevels - 1;
-    stack[sp++] = (root << 26) | 0;
-    while (sp > 0) {
-        const int e = stack[--sp];
-        const int L = e >> 26;
-        const long long g = e & 0x3ffffff;
-        float4 lo, hi;
-        if (L >= bv.topFirst) { lo = sLo[bv.topOffset[L] + g]; hi = sHi[bv.topOffset[L] + g]; }
-        else { lo = __ldg(bv.lo[L] + g); hi = __ldg(bv.hi[L] + g); }
-        if (!in_box(lo, hi, P)) continue;
-        if (L > 0) {
-            const long long nc = bv.n[L - 1];
-            for (int q = 7; q >= 0; --q) {
-                const long long c = 8 * g + q;
-                if (c < nc && sp < 72) stack[sp++] = ((L - 1) << 26) | (int)c;
-            }
-        } else {
-            for (int q = 0; q < 8; ++q) {
-                const long long k = 8 * g + q;
-                if (k >= bv.nTets) break;
-                const int t = __ldg(bv.order + k);
-                if (t >= best) continue;
-                int4 v;
-                const Tet T = load_tet(m, t, v);
-                // cheap reject on the tet's own box before the exact test
-                const double lx = fmin(fmin(T.P[0].x, T.P[1].x), fmin(T.P[2].x, T.P[3].x)), hx = fmax(fmax(T.P[0].x, T.P[1].x), fmax(T.P[2].x, T.P[3].x));
-                if (P.x < lx || P.x > hx) continue;
-                const double ly = fmin(fmin(T.P[0].y, T.P[1].y), fmin(T.P[2].y, T.P[3].y)), hy = fmax(fmax(T.P[0].y, T.P[1].y), fmax(T.P[2].y, T.P[3].y));
-                if (P.y < ly || P.y > hy) continue;
-                const double lz = fmin(fmin(T.P[0].z, T.P[1].z), fmin(T.P[2].z, T.P[3].z)), hz = fmax(fmax(T.P[0].z, T.P[1].z), fmax(T.P[2].z, T.P[3].z));
-                if (P.z < lz || P.z > hz) continue;
-                double w[4];
-                bary_exact(T, P, w);
-                if (w[0] >= 0.0 && w[1] >= 0.0 && w[2] >= 0.0 && w[3] >= 0.0) best = t;
+    unsigned found = 0;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+        const long long i = list ? (long long)list[w] : w;
+        const double4 p4 = pv.pos[i];
+        if (!list && p4.w == 0.0) { pv.tet[i] = -1; continue; }
+        const D3 P{ p4.x, p4.y, p4.z };
+        const PF pf{ __double2float_rd(P.x), __double2float_rd(P.y), __double2float_rd(P.z),
+                     __double2float_ru(P.x), __double2float_ru(P.y), __double2float_ru(P.z) };
+        int best = 0x7fffffff;
+        int stack[64];
+        int sp = 0;
+        const int root = bv.nLevels - 1;
+        {
+            const float4 lo = root >= bv.topFirst ? sLo[bv.topOffset[root]] : __ldg(bv.lo[root]);
+            const float4 hi = root >= bv.topFirst ? sHi[bv.topOffset[root]] : __ldg(bv.hi[root]);
+            if (in_box(lo, hi, pf)) stack[sp++] = (root << 26) | 0;
+        }
+        while (sp > 0) {
+            const int e = stack[--sp];
+            const int L = e >> 26;
+            const long long g = e & 0x3ffffff;
+            if (L > 0) {
+                const int C = L - 1;
+                const long long nc = bv.n[C], c0 = 8 * g;
+                const bool top = C >= bv.topFirst;
+                const float4 *lo = top ? sLo + bv.topOffset[C] : bv.lo[C], *hi = top ? sHi + bv.topOffset[C] : bv.hi[C];
+#pragma unroll
+                for (int q = 7; q >= 0; --q) { // pushed in reverse: the lowest child is expanded first
+                    const long long c = c0 + q;
+                    if (c >= nc) continue;
+                    const float4 a = top ? lo[c] : __ldg(lo + c), b = top ? hi[c] : __ldg(hi + c);
+                    if (in_box(a, b, pf) && sp < 64) stack[sp++] = (C << 26) | (int)c;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const long long k = 8 * g + q;
+                    if (k >= bv.nTets) break;
+                    if (!in_box(__ldg(bv.tetLo + k), __ldg(bv.tetHi + k), pf)) continue; // the tet's own box before anything of the tet is loaded
+                    const int t = __ldg(bv.order + k);
+                    if (t >= best) continue;
+                    Tet T;
+                    const int4 v = ld_int4(m.tetv, t);
+                    T.P[0] = ld_vertex(m.vpos, v.x); T.P[1] = ld_vertex(m.vpos, v.y); T.P[2] = ld_vertex(m.vpos, v.z); T.P[3] = ld_vertex(m.vpos, v.w);
+                    T.code = m.tetcode[t];
+                    double wgt[4];
+                    bary_exact(T, P, wgt);
+                    if (wgt[0] >= 0.0 && wgt[1] >= 0.0 && wgt[2] >= 0.0 && wgt[3] >= 0.0) best = t;
+                }
             }
         }
+        if (list) {
+            if (best != 0x7fffffff) { pv.tet[i] = best; ++found; }
+        } else pv.tet[i] = (best == 0x7fffffff) ? -1 : best;
     }
-    if (lostOnly) {
-        if (best != 0x7fffffff) { pv.tet[i] = best; atomicAdd(relocated, 1ull); }
-        return;
+    if (list) {
+        found = __reduce_add_sync(0xffffffffu, found);
+        if ((threadIdx.x & 31) == 0 && found) atomicAdd(relocated, (unsigned long long)found);
     }
-    pv.tet[i] = (best == 0x7fffffff) ? -1 : best;
 }
 
 void free_bvh(cpf_context *ctx)
 {
     cudaFree(ctx->d_bvh_tet); ctx->d_bvh_tet = nullptr;
+    cudaFree(ctx->d_bvh_tet_lo); cudaFree(ctx->d_bvh_tet_hi); ctx->d_bvh_tet_lo = ctx->d_bvh_tet_hi = nullptr;
     for (auto &l : ctx->bvh) { cudaFree(l.lo); cudaFree(l.hi); }
     ctx->bvh.clear();
     cudaFree(ctx->d_bvh_top_lo); cudaFree(ctx->d_bvh_top_hi);
@@ -207,7 +246,9 @@ int build_bvh(cpf_context *ctx)
     BvhLevel L0{ nullptr, nullptr, n };
     CPF_CUDA(ctx, cudaMalloc(&L0.lo, sizeof(float4) * (size_t)n));
     CPF_CUDA(ctx, cudaMalloc(&L0.hi, sizeof(float4) * (size_t)n));
-    k_bvh_leaves<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, nT, ctx->d_bvh_tet, ctx->d_tetv, ctx->d_vpos, L0.lo, L0.hi);
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_bvh_tet_lo, sizeof(float4) * (size_t)nT));
+    CPF_CUDA(ctx, cudaMalloc(&ctx->d_bvh_tet_hi, sizeof(float4) * (size_t)nT));
+    k_bvh_leaves<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, nT, ctx->d_bvh_tet, ctx->d_tetv, ctx->d_vpos, L0.lo, L0.hi, ctx->d_bvh_tet_lo, ctx->d_bvh_tet_hi);
     ctx->launches++;
     ctx->bvh.push_back(L0);
     while (n > 1) {
@@ -222,9 +263,9 @@ int build_bvh(cpf_context *ctx)
         n = np;
     }
     if ((int)ctx->bvh.size() > CPF_BVH_MAX_LEVELS) return fail(ctx, CPF_ERR_INVALID, "BVH too deep");
-    // top levels (first level with <= 2048 nodes and everything above) -> one contiguous array
+    // top levels (first level with <= 1024 nodes and everything above) -> one contiguous array
     int first = 0;
-    while (first < (int)ctx->bvh.size() - 1 && ctx->bvh[first].n > 2048) ++first;
+    while (first < (int)ctx->bvh.size() - 1 && ctx->bvh[first].n > 1024) ++first;
     ctx->bvh_top_first_level = first;
     ctx->bvh_top_offsets.assign(ctx->bvh.size(), 0);
     int total = 0;
@@ -253,12 +294,26 @@ int locate_particles(cpf_context *ctx, bool lostOnly)
     bv.topNodes = ctx->bvh_top_nodes;
     bv.topLo = ctx->d_bvh_top_lo; bv.topHi = ctx->d_bvh_top_hi;
     bv.order = ctx->d_bvh_tet;
+    bv.tetLo = ctx->d_bvh_tet_lo; bv.tetHi = ctx->d_bvh_tet_hi;
     bv.nTets = ctx->nTets;
     const size_t smem = sizeof(float4) * 2 * (size_t)bv.topNodes;
     CPF_CUDA(ctx, cudaFuncSetAttribute(k_locate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_locate<<<(unsigned)((ctx->n + 127) / 128), 128, smem, ctx->stream>>>(mesh_view(ctx), bv, particle_view(ctx), lostOnly ? 1 : 0,
-                                                                           ctx->d_counters + CNT_LOST);
-    ctx->launches++;
+    int perSm = 0, sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_locate, 128, smem) != cudaSuccess || perSm < 1) perSm = 1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device) != cudaSuccess || sms < 1) sms = 148;
+    const unsigned grid = (unsigned)std::min<long long>((ctx->n + 127) / 128, (long long)sms * perSm);
+    const ParticleView pv = particle_view(ctx);
+    if (lostOnly) { // the work list lives in the first deferral queue (no sub-steps are in flight on this stream), its length in the last counter word
+        int *list = reinterpret_cast<int *>(ctx->d_queue[0]);
+        unsigned *count = ctx->d_queue_count + 63;
+        CPF_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(unsigned), ctx->stream));
+        k_collect_lost<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(pv, list, count);
+        k_locate<<<grid, 128, smem, ctx->stream>>>(mesh_view(ctx), bv, pv, list, count, ctx->d_counters + CNT_LOST);
+        ctx->launches += 2;
+    } else {
+        k_locate<<<grid, 128, smem, ctx->stream>>>(mesh_view(ctx), bv, pv, nullptr, nullptr, ctx->d_counters + CNT_LOST);
+        ctx->launches++;
+    }
     CPF_CUDA(ctx, cudaGetLastError());
     if (!lostOnly) ctx->have_tets = true;
     return CPF_OK;
