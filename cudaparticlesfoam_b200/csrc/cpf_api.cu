@@ -641,9 +641,9 @@ int cpf_reseed_inactive(cpf_context *ctx, const double lo[3], const double hi[3]
     if (nReseeded) *nReseeded = 0;
     if (ctx->n == 0) return CPF_OK;
     cudaSetDevice(ctx->device);
-    int rc = ensure_scratch(ctx, 64);
-    if (rc) return rc;
-    unsigned long long *d_n = (unsigned long long *)ctx->d_scratch;
+    int rc = CPF_OK;
+    // the count of re-seeded particles: two spare words of the queue counters (the scratch buffer holds the location pass's workspace)
+    unsigned long long *d_n = reinterpret_cast<unsigned long long *>(ctx->d_queue_count + 60);
     CPF_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), ctx->stream));
     const int a = ctx->pcur;
     k_reseed_inactive<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n, ctx->d_pos[a], ctx->d_tet[a], ctx->d_pid[a], ctx->d_vel[a],

@@ -112,91 +112,134 @@ CPF_DEV bool in_box(const float4 lo, const float4 hi, const PF &p)
     return p.hx >= lo.x && p.lx <= hi.x && p.hy >= lo.y && p.ly <= hi.y && p.hz >= lo.z && p.lz <= hi.z;
 }
 
-// Work list of a lost-only pass: slots of the particles that are active but carry a negative tet id (just re-seeded, or
-// lost after a failed reflection sequence -- the reference freezes those forever, cuda/particles.cu:334-338).  One
-// atomic per warp.
-__global__ void k_collect_lost(const ParticleView pv, int *__restrict__ list, unsigned *__restrict__ count)
+// Work list of a location pass: key = 30-bit Morton code of the position for the particles to locate (lostOnly: active but
+// carrying a negative tet id -- just re-seeded, or lost after a failed reflection sequence, which the reference freezes
+// forever, cuda/particles.cu:334-338; else: every active particle), 0xffffffff for the others; sorted by key, the list
+// puts neighbouring points into neighbouring lanes, which then walk the same nodes of the tree (lines shared in L1
+// instead of 8 KB of boxes and vertices per point through L2), and the particles to skip at its end.
+CPF_DEV unsigned spread10(unsigned x)
+{
+    x &= 0x3ffu;
+    x = (x | x << 16) & 0x030000ffu;
+    x = (x | x << 8) & 0x0300f00fu;
+    x = (x | x << 4) & 0x030c30c3u;
+    x = (x | x << 2) & 0x09249249u;
+    return x;
+}
+__global__ void k_query_keys(const ParticleView pv, const int lostOnly, double3 lo, double3 inv, unsigned *__restrict__ keys,
+                             int *__restrict__ ids, unsigned *__restrict__ count)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool want = i < pv.n && pv.pos[i].w != 0.0 && pv.tet[i] < 0;
+    bool want = false;
+    if (i < pv.n) {
+        const double4 p = pv.pos[i];
+        want = p.w != 0.0 && (!lostOnly || pv.tet[i] < 0);
+        if (!lostOnly && p.w == 0.0) pv.tet[i] = -1;
+        unsigned key = 0xffffffffu;
+        if (want) {
+            const unsigned ix = (unsigned)fmin(fmax((p.x - lo.x) * inv.x * 1023.0, 0.0), 1023.0);
+            const unsigned iy = (unsigned)fmin(fmax((p.y - lo.y) * inv.y * 1023.0, 0.0), 1023.0);
+            const unsigned iz = (unsigned)fmin(fmax((p.z - lo.z) * inv.z * 1023.0, 0.0), 1023.0);
+            key = spread10(ix) | (spread10(iy) << 1) | (spread10(iz) << 2);
+        }
+        keys[i] = key;
+        ids[i] = (int)i;
+    }
     const unsigned mask = __ballot_sync(0xffffffffu, want);
-    if (!mask) return;
-    const int lane = threadIdx.x & 31;
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(count, (unsigned)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (want) list[base + __popc(mask & ((1u << lane) - 1u))] = (int)i;
+    if (mask && (threadIdx.x & 31) == 0) atomicAdd(count, (unsigned)__popc(mask));
 }
 
+// exact containment test of tet t (the reference's barycentric coordinates, cuda/DeviceTetMesh.cuh:108-156)
+CPF_DEV bool tet_contains(const MeshView &m, int t, const D3 &P)
+{
+    Tet T;
+    const int4 v = ld_int4(m.tetv, t);
+    T.P[0] = ld_vertex(m.vpos, v.x); T.P[1] = ld_vertex(m.vpos, v.y); T.P[2] = ld_vertex(m.vpos, v.z); T.P[3] = ld_vertex(m.vpos, v.w);
+    T.code = m.tetcode[t];
+    double w[4];
+    bary_exact(T, P, w);
+    return w[0] >= 0.0 && w[1] >= 0.0 && w[2] >= 0.0 && w[3] >= 0.0;
+}
+
+#define CPF_LOCATE_CAND 24
 // One resident wave of CTAs, each staging the top of the tree once and then taking particles in a grid-stride loop
-// (list == nullptr: every particle slot; else the *count entries of list).  Depth-first traversal with the eight children
-// of a node tested where the node is expanded (their boxes are contiguous), so the stack holds only boxes that contain
-// the point.
-__global__ void __launch_bounds__(128) k_locate(const MeshView m, const __grid_constant__ BvhView bv, const ParticleView pv, const int *__restrict__ list,
-                                                const unsigned *__restrict__ count, unsigned long long *__restrict__ relocated)
+// (the first *count entries of list, see k_query_keys).
+// Phase 1, boxes only: depth-first traversal in which EVERY step is the same code for every lane -- pop a node, test the
+// eight boxes below it (contiguous; the boxes of the single tets are the level below the leaf groups), push the
+// children / note the tets that contain the point.  Phase 2: the exact test of the noted tets, all lanes in step.
+// Keeping the fp64 tests out of the traversal loop is what keeps the lanes of a warp together: with them inside, a warp
+// ran the exact test once per loop iteration for whichever lane happened to sit at a leaf.
+__global__ void __launch_bounds__(128) k_locate(const MeshView m, const __grid_constant__ BvhView bv, const ParticleView pv,
+                                                const int *__restrict__ list, const unsigned *__restrict__ count, const int lostOnly,
+                                                unsigned long long *__restrict__ relocated)
 {
     extern __shared__ float4 smem[];
-    const long long total = list ? (long long)*count : pv.n;
+    __shared__ const float4 *sPtrLo[CPF_BVH_MAX_LEVELS + 1], *sPtrHi[CPF_BVH_MAX_LEVELS + 1]; // [0]: the tets, [l + 1]: level l
+    __shared__ long long sCnt[CPF_BVH_MAX_LEVELS + 1];
+    const long long total = (long long)*count;
     if ((long long)blockIdx.x * blockDim.x >= total) return; // nothing for this CTA: do not stage either
     float4 *sLo = smem, *sHi = smem + bv.topNodes;
     for (int q = threadIdx.x; q < bv.topNodes; q += blockDim.x) { sLo[q] = bv.topLo[q]; sHi[q] = bv.topHi[q]; }
+    if (threadIdx.x == 0) {
+        sPtrLo[0] = bv.tetLo; sPtrHi[0] = bv.tetHi; sCnt[0] = bv.nTets;
+        for (int l = 0; l < bv.nLevels; ++l) {
+            const bool top = l >= bv.topFirst; // staged levels are read through their (generic) shared-memory address
+            sPtrLo[l + 1] = top ? sLo + bv.topOffset[l] : bv.lo[l];
+            sPtrHi[l + 1] = top ? sHi + bv.topOffset[l] : bv.hi[l];
+            sCnt[l + 1] = bv.n[l];
+        }
+    }
     __syncthreads();
     unsigned found = 0;
     for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
-        const long long i = list ? (long long)list[w] : w;
+        const long long i = (long long)list[w];
         const double4 p4 = pv.pos[i];
-        if (!list && p4.w == 0.0) { pv.tet[i] = -1; continue; }
         const D3 P{ p4.x, p4.y, p4.z };
         const PF pf{ __double2float_rd(P.x), __double2float_rd(P.y), __double2float_rd(P.z),
                      __double2float_ru(P.x), __double2float_ru(P.y), __double2float_ru(P.z) };
         int best = 0x7fffffff;
         int stack[64];
-        int sp = 0;
-        const int root = bv.nLevels - 1;
-        {
-            const float4 lo = root >= bv.topFirst ? sLo[bv.topOffset[root]] : __ldg(bv.lo[root]);
-            const float4 hi = root >= bv.topFirst ? sHi[bv.topOffset[root]] : __ldg(bv.hi[root]);
-            if (in_box(lo, hi, pf)) stack[sp++] = (root << 26) | 0;
-        }
+        int cand[CPF_LOCATE_CAND];
+        int sp = 0, nc = 0;
+        const int root = bv.nLevels; // in the shifted numbering
+        if (in_box(sPtrLo[root][0], sPtrHi[root][0], pf)) stack[sp++] = (root << 26) | 0;
         while (sp > 0) {
             const int e = stack[--sp];
-            const int L = e >> 26;
-            const long long g = e & 0x3ffffff;
-            if (L > 0) {
-                const int C = L - 1;
-                const long long nc = bv.n[C], c0 = 8 * g;
-                const bool top = C >= bv.topFirst;
-                const float4 *lo = top ? sLo + bv.topOffset[C] : bv.lo[C], *hi = top ? sHi + bv.topOffset[C] : bv.hi[C];
+            const int C = (e >> 26) - 1; // the level of the children
+            const long long c0 = 8ll * (e & 0x3ffffff), n = sCnt[C];
+            const float4 *lo = sPtrLo[C] + c0, *hi = sPtrHi[C] + c0;
+            float4 a[8], b[8];
 #pragma unroll
-                for (int q = 7; q >= 0; --q) { // pushed in reverse: the lowest child is expanded first
-                    const long long c = c0 + q;
-                    if (c >= nc) continue;
-                    const float4 a = top ? lo[c] : __ldg(lo + c), b = top ? hi[c] : __ldg(hi + c);
-                    if (in_box(a, b, pf) && sp < 64) stack[sp++] = (C << 26) | (int)c;
+            for (int q = 0; q < 8; ++q) { // all sixteen requests go out before the first test
+                const bool have = c0 + q < n;
+                a[q] = have ? lo[q] : make_float4(1.f, 1.f, 1.f, 0.f);
+                b[q] = have ? hi[q] : make_float4(0.f, 0.f, 0.f, 0.f); // an empty box
+            }
+            unsigned hit = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) hit |= in_box(a[q], b[q], pf) ? 1u << q : 0u;
+            if (C > 0) {
+                for (; hit; hit &= hit - 1u) { // (any order: every containing box is visited)
+                    const int q = __ffs((int)hit) - 1;
+                    if (sp < 64) stack[sp++] = (C << 26) | (int)(c0 + q);
                 }
             } else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const long long k = 8 * g + q;
-                    if (k >= bv.nTets) break;
-                    if (!in_box(__ldg(bv.tetLo + k), __ldg(bv.tetHi + k), pf)) continue; // the tet's own box before anything of the tet is loaded
-                    const int t = __ldg(bv.order + k);
-                    if (t >= best) continue;
-                    Tet T;
-                    const int4 v = ld_int4(m.tetv, t);
-                    T.P[0] = ld_vertex(m.vpos, v.x); T.P[1] = ld_vertex(m.vpos, v.y); T.P[2] = ld_vertex(m.vpos, v.z); T.P[3] = ld_vertex(m.vpos, v.w);
-                    T.code = m.tetcode[t];
-                    double wgt[4];
-                    bary_exact(T, P, wgt);
-                    if (wgt[0] >= 0.0 && wgt[1] >= 0.0 && wgt[2] >= 0.0 && wgt[3] >= 0.0) best = t;
+                for (; hit; hit &= hit - 1u) {
+                    const int t = __ldg(bv.order + c0 + (__ffs((int)hit) - 1));
+                    if (nc < CPF_LOCATE_CAND) cand[nc++] = t;
+                    else if (t < best && tet_contains(m, t, P)) best = t; // more candidates than the list holds: test at once
                 }
             }
         }
-        if (list) {
+        for (int k = 0; k < nc; ++k) {
+            const int t = cand[k];
+            if (t < best && tet_contains(m, t, P)) best = t;
+        }
+        if (lostOnly) {
             if (best != 0x7fffffff) { pv.tet[i] = best; ++found; }
         } else pv.tet[i] = (best == 0x7fffffff) ? -1 : best;
     }
-    if (list) {
+    if (lostOnly) {
         found = __reduce_add_sync(0xffffffffu, found);
         if ((threadIdx.x & 31) == 0 && found) atomicAdd(relocated, (unsigned long long)found);
     }
@@ -303,17 +346,24 @@ int locate_particles(cpf_context *ctx, bool lostOnly)
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device) != cudaSuccess || sms < 1) sms = 148;
     const unsigned grid = (unsigned)std::min<long long>((ctx->n + 127) / 128, (long long)sms * perSm);
     const ParticleView pv = particle_view(ctx);
-    if (lostOnly) { // the work list lives in the first deferral queue (no sub-steps are in flight on this stream), its length in the last counter word
-        int *list = reinterpret_cast<int *>(ctx->d_queue[0]);
-        unsigned *count = ctx->d_queue_count + 63;
-        CPF_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(unsigned), ctx->stream));
-        k_collect_lost<<<(unsigned)((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(pv, list, count);
-        k_locate<<<grid, 128, smem, ctx->stream>>>(mesh_view(ctx), bv, pv, list, count, ctx->d_counters + CNT_LOST);
-        ctx->launches += 2;
-    } else {
-        k_locate<<<grid, 128, smem, ctx->stream>>>(mesh_view(ctx), bv, pv, nullptr, nullptr, ctx->d_counters + CNT_LOST);
-        ctx->launches++;
-    }
+    // the work list: keys | sorted keys in the first deferral queue, ids | sorted ids in the second (no sub-steps are in flight
+    // on this stream; a queue holds 2 n words), its length in the last queue counter word, CUB's workspace in the scratch buffer
+    const long long n = ctx->n;
+    unsigned *keys = reinterpret_cast<unsigned *>(ctx->d_queue[0]), *keys2 = keys + n;
+    int *ids = reinterpret_cast<int *>(ctx->d_queue[1]), *ids2 = ids + n;
+    unsigned *count = ctx->d_queue_count + 63;
+    size_t tmpBytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keys2, ids, ids2, n, 0, 32, ctx->stream);
+    { int rc = ensure_scratch(ctx, tmpBytes); if (rc) return rc; }
+    CPF_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(unsigned), ctx->stream));
+    double3 lo = make_double3(ctx->bbox_lo[0], ctx->bbox_lo[1], ctx->bbox_lo[2]), inv;
+    inv.x = 1.0 / fmax(ctx->bbox_hi[0] - ctx->bbox_lo[0], 1e-300);
+    inv.y = 1.0 / fmax(ctx->bbox_hi[1] - ctx->bbox_lo[1], 1e-300);
+    inv.z = 1.0 / fmax(ctx->bbox_hi[2] - ctx->bbox_lo[2], 1e-300);
+    k_query_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(pv, lostOnly ? 1 : 0, lo, inv, keys, ids, count);
+    CPF_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_scratch, tmpBytes, keys, keys2, ids, ids2, n, 0, 32, ctx->stream));
+    k_locate<<<grid, 128, smem, ctx->stream>>>(mesh_view(ctx), bv, pv, ids2, count, lostOnly ? 1 : 0, ctx->d_counters + CNT_LOST);
+    ctx->launches += 6;
     CPF_CUDA(ctx, cudaGetLastError());
     if (!lostOnly) ctx->have_tets = true;
     return CPF_OK;
