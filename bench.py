@@ -412,14 +412,14 @@ def run_ours(args, w, rank, world, local_rank):
                 "ms_per_step": m["ms_e2e"] / args.steps},
         "gpu_launches": int(m["launches"]),
         "clocks": ck,
-        "roofline": {"bound": "hbm", "kernel": "advect launch sequence: cpf::k_lean + k_fast<queue,wall> + k_exact_convex<rest>", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "advect launch sequence: cpf::k_lean (all particles) + cpf::k_fast<FIN> (finishing pass over its refusals)", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "algorithmic_bytes_per_particle_step": B_ALG,
                      "algorithmic_bytes_per_launch": B_ALG * psteps_rank / max(nl, 1), "avg_launch_ms": avg_launch_ms, "launches_timed": nl,
                      "substeps_per_launch": sub_per_launch, "kernel_share_of_step": prof_ms / m["ms"],
-                     # what the kernel is REALLY limited by (ncu, profiles/r2_summary.md): instruction issue and the L1 data pipe;
+                     # what the kernel is REALLY limited by (ncu, profiles/r2_summary.md): dependent-load latency, instruction issue and the L1 data pipe;
                      # HBM is nearly idle because the particle state stays in registers across the fused sub-steps
-                     "measured_limiter": "instruction issue + L1 data pipe (not HBM)",
+                     "measured_limiter": "latency of the dependent chain visit -> exit face -> next record at 28 warps/SM: issue slots 61 % busy, L1 data pipe 72 %, DRAM 10 % (ncu, profiles/r2_summary.md); not HBM",
                      "real_dram_frac": (traffic / (avg_launch_ms * 1e-3) / 1e9 / peak) if traffic else None,
                      # mesh-inclusive figure: 72 B of state + one 64-byte record per visited tet + the 32-byte
                      # origin position on ~half of the hops + the 32-byte cell velocity per sub-step

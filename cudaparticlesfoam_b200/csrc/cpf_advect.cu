@@ -933,6 +933,9 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 #ifndef CPF_LEAN_THREADS
 #define CPF_LEAN_THREADS 128
 #endif
+#ifndef CPF_LEAN_BARY_TOP
+#define CPF_LEAN_BARY_TOP 1
+#endif
 #ifndef CPF_LEAN_PFU
 #define CPF_LEAN_PFU 1
 #endif
@@ -1120,8 +1123,23 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, (INTEG == CPF_RK4 ? CPF_LEAN
             else sts_i32(INTEG ? t0 : xs, tet); // refused before its first sub-step
         }
     }
-    if (left > 0) begin_substep();
     constexpr bool PFU = CFV && !BARY && INTEG == CPF_EULER && CPF_LEAN_PFU;
+    if constexpr (BARY && CPF_LEAN_BARY_TOP) {
+        // The barycentric walk has no exit-face section for the prologue to hide behind, and is faster (measured: +8 %, and 67
+        // registers) with the loop of the first RTX=true version: the prologue of a sub-step runs at the TOP of the iteration
+        // of its first visit.  (The convex walk is 3 % slower that way.)
+        bool due = left > 0;
+        while (__any_sync(0xffffffffu, left > 0)) {
+            if (left > 0) {
+                if (due) { begin_substep(); due = false; }
+                const int oc = visit_bary32<CF>(m, f, O, disp, ws, hops >= cap);
+                if (oc == CPF_V_HOP) ++hops;
+                else if (oc == CPF_V_DONE) { P = disp; xs += STEP; --left; due = true; }
+                else { left = -left; atWall = oc == CPF_V_WALL; }
+            }
+        }
+    } else {
+    if (left > 0) begin_substep();
     while (__any_sync(0xffffffffu, left > 0)) {
         if (left > 0) {
             const int oc = BARY ? visit_bary32<CF>(m, f, O, disp, ws, hops >= cap) : visit_fast32<CF, PFU>(m, f, O, P, ws, hops >= cap);
@@ -1133,6 +1151,7 @@ __global__ void __launch_bounds__(CPF_LEAN_THREADS, (INTEG == CPF_RK4 ? CPF_LEAN
                 if (--left > 0) begin_substep();
             } else { left = -left; atWall = oc == CPF_V_WALL; }
         }
+    }
     }
     const bool deferred = left < 0 && live && frz == 0u;
     const int s = sp.nSub - abs(left); // sub-steps completed here
