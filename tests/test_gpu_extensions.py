@@ -124,6 +124,44 @@ def test_lost_particle_relocation(synth, orc):
     tr.close()
 
 
+def test_lost_only_pass_equals_full_location_at_scale(synth, orc):
+    """The lost-only pass (compacted, Morton-sorted work list; one resident wave of CTAs in a grid-stride loop) must give
+    the answer of the all-particles pass for exactly the particles it is asked about, and touch nobody else: 3e5 random
+    points -- more than one resident wave of threads, so the grid-stride loop runs -- a third of them marked lost,
+    inactive particles and out-of-domain points mixed in; a sample is checked against brute force."""
+    from cudaparticlesfoam_b200 import api
+
+    n = 300_000
+    pm, mesh, U, p = make_case(synth, orc, dims=(12, 10, 9), jitter=0.2, n=n)
+    rng = np.random.default_rng(7)
+    p[rng.choice(n, 1000, replace=False), 3] = 0.0   # inactive slots
+    outside = rng.choice(n, 50, replace=False)
+    p[outside, 0] += 50.0                             # outside the mesh (some of them inactive as well)
+    tr = api.ParticleTracker(rng=api.RNG_NONE)
+    tr.upload_poly(pm)
+    tr.update_velocity(U)
+    tr.set_particles(p)
+    tr.locate_initial()
+    _, _, t_full = tr.download(pos=False, vel=False)
+    active = p[:, 3] != 0
+    assert (t_full[~active] == -1).all() and (t_full[outside] == -1).all()
+    sample = rng.choice(np.flatnonzero(active), 400, replace=False)
+    assert np.array_equal(t_full[sample], orc.locate_brute(mesh, p[sample]))
+    lost = rng.random(n) < 1.0 / 3.0
+    marker_tet = np.where(lost, -1, t_full).astype(np.int32)
+    marker_tet[~active] = -7                           # an inactive slot keeps whatever id it carries
+    tr.set_tets(marker_tet)
+    tr.relocate_lost()
+    _, _, t_again = tr.download(pos=False, vel=False)
+    want = t_full.copy()
+    want[~active] = -7
+    assert np.array_equal(t_again, want)
+    tr.relocate_lost()                                 # nothing left to do except the out-of-domain points: a no-op
+    _, _, t_third = tr.download(pos=False, vel=False)
+    assert np.array_equal(t_third, want)
+    tr.close()
+
+
 @pytest.mark.parametrize("path", [0, 1], ids=["filtered", "exact"])
 def test_per_patch_restitution_matches_the_oracle(synth, orc, path):
     """Rebound model: a restitution coefficient per boundary patch scales the mirrored part of the end point
