@@ -923,12 +923,14 @@ k_fast(const MeshView m, const ParticleView pv, const StepParams sp)
 
 // k_lean<RNG,CFV>: the all-particles pass of the filtered policy for the reference's own configuration (Euler, cell
 // value) -- k_fast<RNG,0,0,EULER,0> with the per-visit and per-sub-step instruction count cut down, because this is
-// the kernel the step time is made of and it is bound by instruction issue, not by memory:
-//   * thread i = particle i, no queue input, no wall handling, no stage walks: a lane is in one of three modes
-//     (0 = sub-step prologue due, 1 = walking, 2 = finished or deferred), one register;
+// the kernel the step time is made of and it is bound by instruction issue and dependent-load latency, not by memory
+// bandwidth:
+//   * thread i = particle i, no queue input, no wall handling: one loop-carried counter (`left`) says whether a lane
+//     is walking, finished or stopped;
 //   * C1 once per particle (start_point_clear, all lanes converged), never inside the loop (visit_fast32);
-//   * the cell velocity of the NEXT sub-step is fetched where the final tet of a sub-step becomes known, so the
-//     load is in flight while the other lanes of the warp run their exit-face section;
+//   * the cell velocity of the NEXT sub-step is requested into L1 (one predicated prefetch, which holds no dependency
+//     barrier) from the common block of the visit that ends a sub-step, ahead of the divergent sections: ptxas drains every
+//     barrier at a reconvergence point, so a LOAD placed there would be waited for before the exit-face section runs;
 //   * CFV (cell id = origin vertex id - nPoints, every OpenFOAM decomposition) is a template parameter.
 #ifndef CPF_LEAN_THREADS
 #define CPF_LEAN_THREADS 128
@@ -973,7 +975,8 @@ CPF_DEV void sts_i32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;"
 CPF_DEV int lds_i32(unsigned a) { int r; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
 
 //   * LOC = CPF_LOCATOR_BARY (RTX=true build): the same kernel around visit_bary32 -- the walk goes towards the end point
-//     Q = P + disp (kept where the convex walk keeps disp), no start-point check, walls always deferred.
+//     Q = P + disp (kept where the convex walk keeps disp), no start-point check, walls always deferred; its loop runs
+//     the prologue at the top of the iteration of a sub-step's first visit instead of in place (see there).
 // Loop shape: every iteration is ONE tet visit of every lane that still has work; a lane whose visit ends its sub-step
 // runs S5 and the S1/S2 prologue of its next sub-step right there (the first prologue runs before the loop with all lanes
 // converged), so the loop head carries no mode dispatch.  Per-lane loop state besides the walk: the running deviate
