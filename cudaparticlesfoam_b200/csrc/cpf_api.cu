@@ -337,9 +337,26 @@ extern "C" int cpf_set_patch_restitution(cpf_context *ctx, int nPatches, const d
     return CPF_OK;
 }
 
+static int mesh_upload_poly(cpf_context *ctx, int nPoints, const double *points, int nFaces, const int *faceOffsets,
+                            const int *faceVerts, const int *owner, int nInternal, const int *neighbour, int nCells,
+                            const double *cellCentres, const int *tetBasePt, int nPatches, const int *patchStart, const int *patchKind);
+// the ABI never throws: the host-side decomposition works in std::vector
 int cpf_mesh_upload_poly(cpf_context *ctx, int nPoints, const double *points, int nFaces, const int *faceOffsets,
                          const int *faceVerts, const int *owner, int nInternal, const int *neighbour, int nCells,
                          const double *cellCentres, const int *tetBasePt, int nPatches, const int *patchStart, const int *patchKind)
+{
+    try {
+        return mesh_upload_poly(ctx, nPoints, points, nFaces, faceOffsets, faceVerts, owner, nInternal, neighbour, nCells, cellCentres, tetBasePt,
+                                nPatches, patchStart, patchKind);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, CPF_ERR_NOMEM, "cpf_mesh_upload_poly: out of host memory");
+    } catch (const std::exception &e) {
+        return fail(ctx, CPF_ERR_INVALID, "cpf_mesh_upload_poly: %s", e.what());
+    }
+}
+static int mesh_upload_poly(cpf_context *ctx, int nPoints, const double *points, int nFaces, const int *faceOffsets,
+                            const int *faceVerts, const int *owner, int nInternal, const int *neighbour, int nCells,
+                            const double *cellCentres, const int *tetBasePt, int nPatches, const int *patchStart, const int *patchKind)
 {
     if (!ctx) return CPF_ERR_INVALID;
     if (!points || !faceOffsets || !faceVerts || !owner || (nInternal > 0 && !neighbour) || !cellCentres || nPoints <= 0 ||
@@ -430,8 +447,19 @@ int cpf_mesh_upload_poly(cpf_context *ctx, int nPoints, const double *points, in
     return upload_patch_kinds(ctx, nPatches, patchKind);
 }
 
+static int mesh_upload_tets(cpf_context *ctx, int nVerts, const double *positions, long long nTets, const int *tetVerts, const int *tetCell, int nCells);
 int cpf_mesh_upload_tets(cpf_context *ctx, int nVerts, const double *positions, long long nTets, const int *tetVerts,
                          const int *tetCell, int nCells)
+{
+    try {
+        return mesh_upload_tets(ctx, nVerts, positions, nTets, tetVerts, tetCell, nCells);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, CPF_ERR_NOMEM, "cpf_mesh_upload_tets: out of host memory");
+    } catch (const std::exception &e) {
+        return fail(ctx, CPF_ERR_INVALID, "cpf_mesh_upload_tets: %s", e.what());
+    }
+}
+static int mesh_upload_tets(cpf_context *ctx, int nVerts, const double *positions, long long nTets, const int *tetVerts, const int *tetCell, int nCells)
 {
     if (!ctx) return CPF_ERR_INVALID;
     if (!positions || !tetVerts || nVerts <= 0 || nTets <= 0) return fail(ctx, CPF_ERR_INVALID, "cpf_mesh_upload_tets: bad arguments");
